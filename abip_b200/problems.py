@@ -1,0 +1,169 @@
+"""Deterministic synthetic problem generators for the BASELINE.json configs.
+
+All arrays are FP64 / int64 CSC with sorted row indices, no duplicate entries, no empty rows or
+columns.  LPs are feasible and bounded by construction: draw complementary
+x0, s0 >= 0 and y0 ~ N(0,1), then b = A x0, c = A' y0 + s0.
+
+The reference ships no generator for its LP path (its benchmarks read MPS files,
+scripts/bench-lp/README.md); the Lasso-like recipe for the QCP config follows
+scripts/bench-qcp/get_lasso_simu_data.m:1-15 in spirit (random design, sparse ground truth).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+import numpy as np
+import scipy.sparse as sp
+
+
+@dataclass
+class LPProblem:
+    """Standard-form LP  min c'x  s.t. Ax = b, x >= 0, with A in CSC (reference amatrix.h:10-17)."""
+    m: int
+    n: int
+    Ap: np.ndarray  # int64 [n+1]
+    Ai: np.ndarray  # int64 [nnz]
+    Ax: np.ndarray  # float64 [nnz]
+    b: np.ndarray
+    c: np.ndarray
+    name: str = "lp"
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.Ap[-1])
+
+    def csc(self) -> sp.csc_matrix:
+        return sp.csc_matrix((self.Ax, self.Ai, self.Ap), shape=(self.m, self.n))
+
+
+def _finish_lp(A: sp.csc_matrix, rng: np.random.Generator, name: str, meta: dict) -> LPProblem:
+    A = A.tocsc()
+    A.sum_duplicates()
+    A.sort_indices()
+    m, n = A.shape
+    # complementary primal/dual pair: first half of a random permutation basic, rest nonbasic
+    perm = rng.permutation(n)
+    x0 = np.zeros(n)
+    s0 = np.zeros(n)
+    half = n // 2
+    x0[perm[:half]] = rng.uniform(0.1, 1.1, size=half)
+    s0[perm[half:]] = rng.uniform(0.1, 1.1, size=n - half)
+    y0 = rng.standard_normal(m)
+    b = A @ x0
+    c = A.T @ y0 + s0
+    return LPProblem(m=m, n=n, Ap=A.indptr.astype(np.int64), Ai=A.indices.astype(np.int64),
+                     Ax=A.data.astype(np.float64), b=np.asarray(b, dtype=np.float64),
+                     c=np.asarray(c, dtype=np.float64), name=name, meta=meta)
+
+
+def _patch_empty_rows(rows: np.ndarray, cols: np.ndarray, vals: np.ndarray, m: int, n: int,
+                      rng: np.random.Generator):
+    """Give every empty row one entry (in a random column) so diag(AA') > 0 (indirect.c:68-72)."""
+    present = np.zeros(m, dtype=bool)
+    present[rows] = True
+    empty = np.flatnonzero(~present)
+    if empty.size:
+        rows = np.concatenate([rows, empty])
+        cols = np.concatenate([cols, rng.integers(0, n, size=empty.size)])
+        vals = np.concatenate([vals, rng.standard_normal(empty.size)])
+    return rows, cols, vals
+
+
+def random_lp(m: int, n: int, nnz_per_col: int = 5, seed: int = 0, name: str | None = None) -> LPProblem:
+    """cfg 1 family: k nonzeros per column at uniformly random distinct rows, values N(0,1)."""
+    rng = np.random.default_rng(seed)
+    k = min(nnz_per_col, m)
+    # distinct rows per column: sample with a random offset + distinct strides is biased; do it exactly
+    # in chunks with argpartition of random keys when m is small, else rejection on duplicates.
+    if m <= 4096:
+        keys = rng.random((n, m))
+        rows = np.argpartition(keys, k - 1, axis=1)[:, :k].reshape(-1)
+    else:
+        rows = rng.integers(0, m, size=(n, k))
+        for _ in range(50):
+            srt = np.sort(rows, axis=1)
+            dup = (srt[:, 1:] == srt[:, :-1]).any(axis=1)
+            if not dup.any():
+                break
+            rows[dup] = rng.integers(0, m, size=(int(dup.sum()), k))
+        rows = rows.reshape(-1)
+    cols = np.repeat(np.arange(n, dtype=np.int64), k)
+    vals = rng.standard_normal(n * k)
+    rows, cols, vals = _patch_empty_rows(rows.astype(np.int64), cols, vals, m, n, rng)
+    A = sp.coo_matrix((vals, (rows, cols)), shape=(m, n)).tocsc()
+    return _finish_lp(A, rng, name or f"random_lp_m{m}_n{n}", {"family": "random", "seed": seed,
+                                                               "nnz_per_col": k})
+
+
+def mcf_lp(commodities: int = 20, nodes: int = 7500, arcs: int = 47600, side_rows: int = 2400,
+           side_row_nnz: int = 875, seed: int = 0, name: str | None = None) -> LPProblem:
+    """cfg 2 / cfg 4 family: multicommodity-flow structure.
+
+    Columns: flow x[k][e] for K commodities x E arcs, then E capacity slacks.
+    Rows: K*V flow-conservation rows (+1 tail / -1 head), E capacity rows (sum_k x[k][e] + slack_e),
+    R random dense-ish side rows over the flow columns (values N(0,1)).
+    Defaults give m = 199,600 + 400 = 200,000?  (K*V + E + R = 150,000 + 47,600 + 2,400), n = K*E + E
+    = 999,600, nnz ~ 3*K*E + E + R*side_row_nnz ~ 5.0M.
+    """
+    rng = np.random.default_rng(seed)
+    K, V, E, R = commodities, nodes, arcs, side_rows
+    tail = rng.integers(0, V, size=E)
+    head = (tail + 1 + rng.integers(0, V - 1, size=E)) % V  # head != tail
+    # make sure every node is touched: thread a Hamiltonian cycle through the first V arcs
+    if E >= V:
+        order = rng.permutation(V)
+        tail[:V] = order
+        head[:V] = np.roll(order, -1)
+    n_flow = K * E
+    n = n_flow + E
+    m = K * V + E + R
+    e_idx = np.tile(np.arange(E, dtype=np.int64), K)
+    k_idx = np.repeat(np.arange(K, dtype=np.int64), E)
+    col_flow = k_idx * E + e_idx
+    rows = [k_idx * V + tail[e_idx], k_idx * V + head[e_idx], K * V + e_idx,
+            K * V + np.arange(E, dtype=np.int64)]
+    cols = [col_flow, col_flow, col_flow, n_flow + np.arange(E, dtype=np.int64)]
+    vals = [np.ones(n_flow), -np.ones(n_flow), np.ones(n_flow), np.ones(E)]
+    if R > 0:
+        w = min(side_row_nnz, n_flow)
+        sc = rng.integers(0, n_flow, size=(R, w))
+        rows.append(np.repeat(K * V + E + np.arange(R, dtype=np.int64), w))
+        cols.append(sc.reshape(-1))
+        vals.append(rng.standard_normal(R * w))
+    rows = np.concatenate(rows)
+    cols = np.concatenate(cols)
+    vals = np.concatenate(vals)
+    A = sp.coo_matrix((vals, (rows, cols)), shape=(m, n)).tocsc()  # duplicates (rare) are summed
+    A.eliminate_zeros()
+    return _finish_lp(A, rng, name or f"mcf_lp_K{K}_V{V}_E{E}_R{R}",
+                      {"family": "mcf", "seed": seed, "K": K, "V": V, "E": E, "R": R,
+                       "side_row_nnz": side_row_nnz})
+
+
+def cfg1(seed: int = 1) -> LPProblem:
+    """BASELINE.json configs[0]: m=1,000 n=5,000 density 0.5%."""
+    return random_lp(1000, 5000, 5, seed=seed, name="cfg1_lp_m1k_n5k")
+
+
+def cfg2(seed: int = 2, scale: float = 1.0) -> LPProblem:
+    """BASELINE.json configs[1]: m=200k n=1M nnz=5M multicommodity-flow structure (scale<1 shrinks V,E,R)."""
+    V = max(8, int(round(7500 * scale)))
+    E = max(V + 8, int(round(47600 * scale)))
+    R = max(1, int(round(2400 * scale)))
+    w = max(4, min(int(round(875 * min(1.0, scale * 4))), 20 * E))
+    p = mcf_lp(20, V, E, R, w, seed=seed, name=f"cfg2_mcf_lp_scale{scale:g}")
+    return p
+
+
+def cfg4(seed: int = 4, scale: float = 1.0) -> LPProblem:
+    """BASELINE.json configs[3]: m=2M n=10M nnz=60M (same family as cfg2, 6 nnz/col)."""
+    V = max(8, int(round(75000 * scale)))
+    E = max(V + 8, int(round(476000 * scale)))
+    R = max(1, int(round(24000 * scale)))
+    return mcf_lp(20, V, E, R, 1310, seed=seed, name=f"cfg4_mcf_lp_scale{scale:g}")
+
+
+def cfg5_batch(count: int = 4096, base_seed: int = 5000, m: int = 500, n: int = 2000,
+               nnz_per_col: int = 5):
+    """BASELINE.json configs[4]: independent small LPs (density 1% -> 5 nnz per column)."""
+    return [random_lp(m, n, nnz_per_col, seed=base_seed + i, name=f"cfg5_lp_{i}") for i in range(count)]
