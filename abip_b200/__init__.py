@@ -1,0 +1,9 @@
+"""abip_b200 -- B200-native engine for ABIP's inner ADMM iteration (indirect / pcg=1 path).
+
+Product layout: csrc/ (hand-written sm_100a CUDA kernels + the C ABI of include/abip_gpu.h) and the
+host-side mirror of the reference's `abip(data, K, params)` entry (api.py).  No CPU fallback.
+"""
+from .api import abip, lp_solve, get_params, LinSysPlugin, LpEngine  # noqa: F401
+from . import problems  # noqa: F401
+
+__all__ = ["abip", "lp_solve", "get_params", "LinSysPlugin", "LpEngine", "problems"]

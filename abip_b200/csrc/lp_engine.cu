@@ -1,0 +1,888 @@
+// lp_engine.cu -- persistent cooperative kernels of the ABIP-LP engine and the device-resident step ABI
+// (group (3) of include/abip_gpu.h).  sm_100a only; no cuSPARSE/cuBLAS; no CPU fallback.
+#include "lp_engine.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+// =========================================================================================================
+// Kernels
+// =========================================================================================================
+struct IterArgs {
+    double *u, *v, *ut, *u_prev;
+    double *u_sum, *v_sum, *u_avgc, *v_avgc, *u_avg, *v_avg;
+    long j, k;
+    double mu, beta;
+    int half_update;     // stgs->half_update
+    int restart_active;  // total_admm_iter >= restart_thresh: maintain u_avg/v_avg (src/abip.c:601-612)
+    int restart_fire;    // (j + 1 - fre_old) % fre == 0 and restart_active
+    double restart_fre;
+};
+
+// Q-norm / residual sums for one (u, v) pair: src/abip.c:1964-1992 (unweighted) and :385-456 (D/E weighted).
+// Writes 11 partial sums into reducer slots [slot0, slot0+11).
+__device__ __forceinline__ void dev_qnorm_sums(const LpCtx& c, Reducer& R, const double* u, const double* v,
+                                               int half, int slot0) {
+    const int m = c.m, n = c.n;
+    const double tau = u[m + n];
+    const double* y = u;
+    const double* x = u + m;
+    const double* s = v + m;
+    double a[5] = {0, 0, 0, 0, 0};  // S_PR, W_AX, W_PR, BTY, UU_Y
+    spmv_rows(c.A, x, [&](int row, double ax) {
+        const double bi = __ldg(c.b + row);
+        const double pr = fma(-bi, tau, ax);
+        double d2 = 1.0;
+        if (c.D) { const double d = __ldg(c.D + row); d2 = d * d; }
+        const double yi = y[row];
+        a[0] = fma(pr, pr, a[0]);
+        a[1] = fma(ax * ax, d2, a[1]);
+        a[2] = fma(pr * pr, d2, a[2]);
+        a[3] = fma(bi, yi, a[3]);
+        a[4] = fma(yi, yi, a[4]);
+    });
+    R.block_store<5>(a, slot0);
+    double d[6] = {0, 0, 0, 0, 0, 0};  // S_DR, W_ATYS, W_DR, CTX, UU_X, VV
+    spmv_rows(c.AT, y, [&](int row, double aty) {
+        const double cj = __ldg(c.c + row);
+        const double sj = s[row];
+        const double xj = x[row];
+        const double dr0 = aty + sj;
+        const double dr = fma(-cj, tau, dr0);
+        double e2 = 1.0;
+        if (c.E) { const double e = __ldg(c.E + row); e2 = e * e; }
+        d[0] = fma(dr, dr, d[0]);
+        d[1] = fma(dr0 * dr0, e2, d[1]);
+        d[2] = fma(dr * dr, e2, d[2]);
+        d[3] = fma(cj, xj, d[3]);
+        d[4] = fma(xj, xj, d[4]);
+        d[5] = fma(sj, sj, d[5]);
+    });
+    if (half) {  // v_y is nonzero only with half_update
+        GRID_STRIDE(i, m) d[5] = fma(v[i], v[i], d[5]);
+    }
+    R.block_store<6>(d, slot0 + 5);
+}
+
+__device__ __forceinline__ void write_qnorm_sc(double* sc, int base, const double* t, const double* u,
+                                               const double* v, int lm1) {
+    for (int q = 0; q < 11; ++q) sc[base + q] = t[q];
+    sc[base + 11] = u[lm1];
+    sc[base + 12] = v[lm1];
+}
+
+// One full inner ADMM iteration (src/abip.c:2133-2173).
+__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_admm_iter(LpCtx c, IterArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[kMaxRed * kWarps];
+    Reducer R{c.partials, sm, (int)gridDim.x, 0};
+    const int m = c.m, lm1 = c.m + c.n, l = lm1 + 1;
+
+    dev_build_rhs(c, R, grid, a.u, a.v, a.ut, a.u_prev);
+    SolveOut so;
+    dev_solve_lin_sys<true>(c, R, grid, a.ut, a.u, a.k, so);
+    grid.sync();
+    double hd[1];
+    R.finish<1>(hd);
+    const double lam = a.mu / a.beta;
+    const double al = c.alpha;
+    const double dom = (double)(a.j + 1);
+
+    // project_barrier + update_dual_vars (abip.c:717-748, 567-584) or half_update pair (:663-711),
+    // restart_vars (:587-630), compute_avg (:635-659) -- one pass over l
+    GRID_STRIDE(i, l) {
+        double uti = a.ut[i];
+        if (i == lm1) {  // u_t[tau] += u_t[0:l-1].h (abip.c:560); only the owner of this entry may touch it
+            uti += hd[0];
+            a.ut[lm1] = uti;
+        }
+        double un, vn;
+        if (!a.half_update) {
+            if (i < m) {
+                vn = a.v[i];
+                un = uti - vn;
+            } else {
+                const double up = a.u_prev[i];
+                const double vo = a.v[i];
+                const double t = al * uti + (1 - al) * up - vo;
+                un = barrier_prox(t, lam);
+                vn = vo + (un - al * uti - (1.0 - al) * up);
+            }
+        } else {
+            double vh = a.v[i] + 0.5 * (a.u[i] - uti);
+            un = uti - vh;
+            if (i >= m) un = barrier_prox(un, lam);
+            vn = vh + (un - uti);
+        }
+        if (a.restart_active) {
+            double ua = a.u_avg[i] + un, va = a.v_avg[i] + vn;
+            if (a.restart_fire) {
+                ua /= a.restart_fre;
+                va /= a.restart_fre;
+                un = ua;
+                vn = va;
+                ua = 0.0;
+                va = 0.0;
+            }
+            a.u_avg[i] = ua;
+            a.v_avg[i] = va;
+        }
+        a.u[i] = un;
+        const double us = a.u_sum[i] + un;
+        a.u_sum[i] = us;
+        a.u_avgc[i] = us / dom;
+        if (i >= m || a.half_update || a.restart_active) {
+            a.v[i] = vn;
+            const double vs = a.v_sum[i] + vn;
+            a.v_sum[i] = vs;
+            a.v_avgc[i] = vs / dom;
+        }
+    }
+    grid.sync();
+
+    // iterate_Q_norm_resd sums (abip.c:1951-2051); every 10th inner iteration also on the running average
+    const int has_avg = ((a.j + 1) % 10 == 0) ? 1 : 0;
+    dev_qnorm_sums(c, R, a.u, a.v, a.half_update, 0);
+    if (has_avg) dev_qnorm_sums(c, R, a.u_avgc, a.v_avgc, a.half_update, 11);
+    grid.sync();
+    double t[22];
+    if (has_avg) R.finish<22>(t);
+    else {
+        double t11[11];
+        R.finish<11>(t11);
+        for (int q = 0; q < 11; ++q) t[q] = t11[q];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        c.sc[ABIPGPU_SC_CG_ITS] = (double)so.its;
+        c.sc[ABIPGPU_SC_CG_TOL] = so.tol;
+        c.sc[ABIPGPU_SC_CG_RES] = so.res;
+        write_qnorm_sc(c.sc, ABIPGPU_SC_S_PR, t, a.u, a.v, lm1);
+        c.sc[ABIPGPU_SC_HAS_AVG] = (double)has_avg;
+        if (has_avg) write_qnorm_sc(c.sc, ABIPGPU_SC_AVG_BASE, t + 11, a.u_avgc, a.v_avgc, lm1);
+    }
+}
+
+struct BBArgs {
+    double *u_prev, *v_prev, *ut, *u, *v, *ut_next, *u_next, *v_next;
+    int carry;
+    long k;
+    double mu, beta_prev;
+};
+
+// One ADMM step as written inside update_adapt_params (src/adaptive.c:89-123 / :126-156): from (up, vp) produce
+// (ut, un, vn).  When `dots` is set, also reduces the 5 BB inner products of :158-178 where
+// (u_mid, v_mid, v_first) = (up, vp, v_prev of the round).
+__device__ __forceinline__ void dev_bb_half(const LpCtx& c, Reducer& R, cg::grid_group& grid, const double* up,
+                                            const double* vp, double* ut, double* un, double* vn, long k, double lam,
+                                            const double* v_first, bool dots, int& its) {
+    const int m = c.m, lm1 = c.m + c.n, l = lm1 + 1;
+    dev_build_rhs(c, R, grid, up, vp, ut, nullptr);
+    SolveOut so;
+    dev_solve_lin_sys<true>(c, R, grid, ut, up, k, so);
+    its = so.its;
+    grid.sync();
+    double hd[1];
+    R.finish<1>(hd);
+    const double al = c.alpha;
+    double d[5] = {0, 0, 0, 0, 0};  // utut, utv, uu, vv, uv
+    GRID_STRIDE(i, l) {
+        double uti = ut[i];
+        if (i == lm1) {  // only the owner of the tau entry reads/writes it (no cross-block hazard)
+            uti += hd[0];
+            ut[lm1] = uti;
+        }
+        const double upi = up[i], vpi = vp[i];
+        double uo, vo;
+        if (i < m) {
+            uo = uti - vpi;
+            vo = vn[i];  // never written by the reference either (calloc'ed zero, adaptive.c:282-285)
+        } else {
+            const double t = al * uti + (1 - al) * upi - vpi;
+            uo = barrier_prox(t, lam);
+            vo = vpi + (uo - al * uti - (1 - al) * upi);
+            vn[i] = vo;
+        }
+        un[i] = uo;
+        if (dots) {
+            // here (up, vp) = (u, v) of the round and (uo, vo) = (u_next, v_next)
+            const double dut = 2.0 * vpi + uo - upi - vo - v_first[i];
+            const double du = upi - uo;
+            const double dv = (uo - upi) * (al - 1.0) + vo - vpi;
+            d[0] = fma(dut, dut, d[0]);
+            d[1] = fma(dut, dv, d[1]);
+            d[2] = fma(du, du, d[2]);
+            d[3] = fma(dv, dv, d[3]);
+            d[4] = fma(du, dv, d[4]);
+        }
+    }
+    if (dots) R.block_store<5>(d);
+    grid.sync();
+    if (dots) {
+        R.finish<5>(d);
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            for (int q = 0; q < 5; ++q) c.sc[ABIPGPU_SC_BB_UTUT + q] = d[q];
+    }
+}
+
+// One lookback round of the Barzilai-Borwein search (src/adaptive.c:89-178).
+__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_bb_round(LpCtx c, BBArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[kMaxRed * kWarps];
+    Reducer R{c.partials, sm, (int)gridDim.x, 0};
+    const int m = c.m, l = c.m + c.n + 1;
+    const double lam = a.mu / a.beta_prev;
+    if (a.carry) {  // state hand-over of the previous round (adaptive.c:230-247)
+        GRID_STRIDE(i, l) {
+            const double ui = a.u[i];
+            a.u_prev[i] = ui;
+            a.v_prev[i] = (a.carry == 1 && i >= m) ? lam / ui : a.v[i];
+        }
+        grid.sync();
+    }
+    int its1, its2;
+    dev_bb_half(c, R, grid, a.u_prev, a.v_prev, a.ut, a.u, a.v, a.k, lam, nullptr, false, its1);
+    dev_bb_half(c, R, grid, a.u, a.v, a.ut_next, a.u_next, a.v_next, a.k, lam, a.v_prev, true, its2);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        c.sc[ABIPGPU_SC_CG_ITS] = (double)its1;
+        c.sc[ABIPGPU_SC_CG_ITS2] = (double)its2;
+    }
+}
+
+// solve_lin_sys on a device vector; post_g: g_x *= -1 and g_th = h.g (src/abip.c:1922-1924)
+__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
+    k_solve_vec(LpCtx c, double* b, const double* s, long iter, int post_g) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[kMaxRed * kWarps];
+    Reducer R{c.partials, sm, (int)gridDim.x, 0};
+    SolveOut so;
+    dev_solve_lin_sys<false>(c, R, grid, b, s, iter, so);
+    if (post_g) {
+        grid.sync();
+        const int m = c.m, lm1 = c.m + c.n;
+        double a[1] = {0.0};
+        GRID_STRIDE(i, lm1) {
+            double gi = b[i];
+            if (i >= m) { gi = -gi; b[i] = gi; }
+            a[0] = fma(__ldg(c.h + i), gi, a[0]);
+        }
+        R.block_store<1>(a);
+        grid.sync();
+        R.finish<1>(a);
+        if (blockIdx.x == 0 && threadIdx.x == 0) c.sc[ABIPGPU_SC_VEC_NORM2] = a[0];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        c.sc[ABIPGPU_SC_CG_ITS] = (double)so.its;
+        c.sc[ABIPGPU_SC_CG_TOL] = so.tol;
+        c.sc[ABIPGPU_SC_CG_RES] = so.res;
+    }
+}
+
+// y (+)= A x as a stand-alone launch (plugin accum_by_A / accum_by_Atrans and tests)
+__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
+    k_spmv(Csr A, const double* x, double* y, int accumulate) {
+    spmv_rows(A, x, [&](int row, double a) { y[row] = accumulate ? y[row] + a : a; });
+}
+
+// min / sum of u_i v_i over the (x, tau) tail: update_barrier_dynamic, src/abip.c:957-960
+__global__ void __launch_bounds__(kBlock) k_mu_stats(const double* u, const double* v, int m, int l, double* partials,
+                                                     double* sc) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double s_sum[kWarps], s_min[kWarps];
+    double sum = 0.0, mn = 1e10;
+    GRID_STRIDE(i, l) {
+        if (i >= m) {
+            const double xs = u[i] * v[i];
+            sum += xs;
+            mn = fmin(mn, xs);
+        }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int off = 16; off > 0; off >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, off);
+        mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, off));
+    }
+    if (lane == 0) { s_sum[w] = sum; s_min[w] = mn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0, q = 1e10;
+        for (int i = 0; i < kWarps; ++i) { s += s_sum[i]; q = fmin(q, s_min[i]); }
+        partials[blockIdx.x] = s;
+        partials[gridDim.x + blockIdx.x] = q;
+    }
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double s = 0.0, q = 1e10;
+        for (int i = 0; i < (int)gridDim.x; ++i) { s += __ldcg(partials + i); q = fmin(q, __ldcg(partials + gridDim.x + i)); }
+        sc[ABIPGPU_SC_SUM_XS] = s;
+        sc[ABIPGPU_SC_MIN_XS] = q;
+    }
+}
+
+// reinitialize_vars, src/abip.c:996-1075
+__global__ void k_reinit(double* u, double* v, int m, int l, int indx, double sigma) {
+    const int i = m + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= l) return;
+    if (indx == 0) {
+        if (u[i] > v[i]) v[i] = sigma * v[i];
+        else u[i] = sigma * u[i];
+    } else {
+        const double f = (indx == 1) ? sqrt(sigma) : sqrt(1.0 / sigma);
+        u[i] = f * u[i];
+        v[i] = f * v[i];
+    }
+}
+
+// cold_start_vars, src/abip.c:361-381
+__global__ void k_cold_start(double* u, double* v, int m, int l, double val) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= l) return;
+    u[i] = (i < m) ? 0.0 : val;
+    v[i] = (i < m) ? 0.0 : val;
+}
+
+// h = [-b; c], g = h (src/abip.c:1915-1919)
+__global__ void k_build_h(const double* b, const double* c, double* h, double* g, int m, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m + n) return;
+    const double v = (i < m) ? -b[i] : c[i - m];
+    h[i] = v;
+    g[i] = v;
+}
+
+// M = 1 / diag(A A') from CSR(A) (linsys/indirect.c:36-79)
+__global__ void k_precond(Csr A, double* M) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= A.nrows) return;
+    double s = 0.0;
+    for (int k = A.ptr[row]; k < A.ptr[row + 1]; ++k) s = fma(A.val[k], A.val[k], s);
+    M[row] = 1.0 / s;
+}
+
+// =========================================================================================================
+// Host side of the engine
+// =========================================================================================================
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (call);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            fprintf(stderr, "[abip_gpu] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, \
+                    __LINE__, cudaGetErrorString(_e));                                                   \
+            return -1;                                                                                   \
+        }                                                                                                \
+    } while (0)
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// Row-length statistics -> SpMV plan (lanes per row for the vector kernel, threshold + list for the
+// warp-per-row 128-bit kernel).
+static void choose_spmv_plan(const std::vector<int>& ptr, int nrows, const char* env_lanes, int* lanes_log2,
+                             int* long_thresh, std::vector<int>* long_rows, double* mean_short) {
+    const int thresh = env_int("ABIP_GPU_LONG_ROW", 192);
+    long_rows->clear();
+    double sum_short = 0;
+    long n_short = 0;
+    for (int r = 0; r < nrows; ++r) {
+        const int len = ptr[r + 1] - ptr[r];
+        if (len > thresh) long_rows->push_back(r);
+        else { sum_short += len; ++n_short; }
+    }
+    const double mean = n_short ? sum_short / n_short : 1.0;
+    int lg = 0;
+    while (lg < 5 && (1 << lg) < mean) ++lg;  // smallest power of two >= mean short-row length
+    const int forced = env_int(env_lanes, -1);
+    if (forced >= 0 && forced <= 5) lg = forced;
+    *lanes_log2 = lg;
+    *long_thresh = thresh;
+    *mean_short = mean;
+}
+
+struct ABIPGPU_LP {
+    int device = 0;
+    int m = 0, n = 0, l = 0;
+    long nnz = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int num_sms = 0;
+    int grid_admm = 0, grid_bb = 0, grid_solve = 0, grid_spmv = 0, grid_mu = 0;
+    // matrix
+    int *A_ptr = nullptr, *A_idx = nullptr, *AT_ptr = nullptr, *AT_idx = nullptr, *A_long = nullptr, *AT_long = nullptr;
+    double *A_val = nullptr, *AT_val = nullptr;
+    // everything else lives in one slab
+    double* slab = nullptr;
+    size_t slab_doubles = 0;
+    double* vec[32] = {nullptr};
+    long vec_len[32] = {0};
+    double *dM = nullptr, *dD = nullptr, *dE = nullptr, *db = nullptr, *dc = nullptr;
+    double *p = nullptr, *r = nullptr, *Gp = nullptr, *tmp = nullptr, *partials = nullptr, *dsc = nullptr;
+    double *xin = nullptr, *yout = nullptr;  // staging for host-pointer plugin calls [l] each
+    double* hsc = nullptr;                   // pinned host scalar block
+    bool have_scaling = false;
+    LpCtx ctx;
+    ABIPSettings stgs;
+    ABIPGpuStats stats;
+    double B_A = 0, B_AT = 0;  // algorithmic bytes of one SpMV pass
+    char desc[512];
+    bool restart_synced = false;
+};
+
+static int coop_grid(const void* kernel, int num_sms, int* out) {
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, 0));
+    if (occ < 1) {
+        fprintf(stderr, "[abip_gpu] kernel cannot be made resident\n");
+        return -1;
+    }
+    const int cap = env_int("ABIP_GPU_BLOCKS_PER_SM", ABIP_MIN_BLOCKS_PER_SM);
+    *out = num_sms * std::min(occ, std::max(cap, 1));
+    return 0;
+}
+
+template <class... Args>
+static int launch_coop(abipgpu_lp* e, const void* kernel, int grid, Args... args) {
+    void* argv[] = {(void*)&args...};
+    CK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kBlock), argv, 0, e->stream));
+    e->stats.n_kernel_launches++;
+    return 0;
+}
+
+static int read_sc(abipgpu_lp* e, abip_float* sc) {
+    CK(cudaMemcpyAsync(e->hsc, e->dsc, sizeof(double) * ABIPGPU_SC_COUNT, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->stats.d2h_bytes += sizeof(double) * ABIPGPU_SC_COUNT;
+    if (sc) memcpy(sc, e->hsc, sizeof(double) * ABIPGPU_SC_COUNT);
+    return 0;
+}
+
+template <class T>
+static int upload(T** dst, const std::vector<T>& src, abipgpu_lp* e) {
+    const size_t bytes = std::max<size_t>(src.size(), 4) * sizeof(T);
+    CK(cudaMalloc((void**)dst, bytes));
+    if (!src.empty()) CK(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    e->stats.h2d_bytes += src.size() * sizeof(T);
+    return 0;
+}
+
+static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap, const abip_int* Ai,
+                       const abip_float* Ax, const ABIPSettings* stgs, int device) {
+    const long nnz = Ap[n];
+    if (m <= 0 || n <= 0 || nnz <= 0 || nnz >= 2147483647L || (long)m + n + 1 >= 2147483647L) {
+        fprintf(stderr, "[abip_gpu] unsupported size m=%ld n=%ld nnz=%ld (int32 device indices)\n", (long)m,
+                (long)n, nnz);
+        return -1;
+    }
+    e->device = device;
+    e->m = (int)m;
+    e->n = (int)n;
+    e->l = (int)(m + n + 1);
+    e->nnz = nnz;
+    e->stgs = *stgs;
+    memset(&e->stats, 0, sizeof(e->stats));
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (!prop.cooperativeLaunch) {
+        fprintf(stderr, "[abip_gpu] device lacks cooperative launch\n");
+        return -1;
+    }
+    e->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&e->ev0));
+    CK(cudaEventCreate(&e->ev1));
+
+    // CSR(A') is the caller's CSC; CSR(A) by counting sort (the reference's transpose(), indirect.c:81-139)
+    std::vector<int> at_ptr(n + 1), at_idx(nnz), a_ptr(m + 1, 0), a_idx(nnz);
+    std::vector<double> a_val(nnz);
+    for (long j = 0; j <= n; ++j) at_ptr[j] = (int)Ap[j];
+    for (long k = 0; k < nnz; ++k) {
+        if (Ai[k] < 0 || Ai[k] >= m) {
+            fprintf(stderr, "[abip_gpu] row index out of range\n");
+            return -1;
+        }
+        at_idx[k] = (int)Ai[k];
+        a_ptr[Ai[k] + 1]++;
+    }
+    for (long i = 0; i < m; ++i) a_ptr[i + 1] += a_ptr[i];
+    {
+        std::vector<int> fill(a_ptr.begin(), a_ptr.end() - 1);
+        for (long j = 0; j < n; ++j)
+            for (long k = Ap[j]; k < Ap[j + 1]; ++k) {
+                const int q = fill[Ai[k]]++;
+                a_idx[q] = (int)j;
+                a_val[q] = Ax[k];
+            }
+    }
+    std::vector<double> at_val(Ax, Ax + nnz);
+    std::vector<int> a_long, at_long;
+    int lgA, lgAT, thrA, thrAT;
+    double meanA, meanAT;
+    choose_spmv_plan(a_ptr, (int)m, "ABIP_GPU_LANES_A", &lgA, &thrA, &a_long, &meanA);
+    choose_spmv_plan(at_ptr, (int)n, "ABIP_GPU_LANES_AT", &lgAT, &thrAT, &at_long, &meanAT);
+
+    if (upload(&e->A_ptr, a_ptr, e) || upload(&e->A_idx, a_idx, e) || upload(&e->A_val, a_val, e) ||
+        upload(&e->AT_ptr, at_ptr, e) || upload(&e->AT_idx, at_idx, e) || upload(&e->AT_val, at_val, e) ||
+        upload(&e->A_long, a_long, e) || upload(&e->AT_long, at_long, e))
+        return -1;
+
+    // grids (persistent: a multiple of the SM count)
+    if (coop_grid((const void*)k_admm_iter, e->num_sms, &e->grid_admm) ||
+        coop_grid((const void*)k_bb_round, e->num_sms, &e->grid_bb) ||
+        coop_grid((const void*)k_solve_vec, e->num_sms, &e->grid_solve) ||
+        coop_grid((const void*)k_mu_stats, e->num_sms, &e->grid_mu))
+        return -1;
+    e->grid_spmv = e->num_sms * 4;
+    const int gmax = std::max(std::max(e->grid_admm, e->grid_bb), std::max(e->grid_solve, e->grid_mu));
+
+    // one slab for all FP64 vectors, each 256-byte aligned
+    const size_t L = ((size_t)e->l + 31) & ~(size_t)31;
+    const size_t Mm = ((size_t)m + 31) & ~(size_t)31, Nn = ((size_t)n + 31) & ~(size_t)31;
+    const size_t n_l_vecs = 21 + 2;  // ids 0..20 + xin + yout
+    const size_t total = n_l_vecs * L + 7 * Mm + 3 * Nn + (size_t)2 * kMaxRed * gmax + 64 + ABIPGPU_SC_COUNT;
+    CK(cudaMalloc((void**)&e->slab, total * sizeof(double)));
+    CK(cudaMemsetAsync(e->slab, 0, total * sizeof(double), e->stream));
+    e->slab_doubles = total;
+    double* q = e->slab;
+    auto take = [&](size_t k) { double* r = q; q += k; return r; };
+    for (int id = 0; id <= 20; ++id) {
+        e->vec[id] = take(L);
+        e->vec_len[id] = e->l;
+    }
+    e->vec_len[ABIPGPU_VEC_H] = e->vec_len[ABIPGPU_VEC_G] = m + n;
+    e->xin = take(L);
+    e->yout = take(L);
+    e->dM = take(Mm);
+    e->vec[ABIPGPU_VEC_M] = e->dM;  // overrides the l-sized slot: M has its own storage
+    e->vec_len[ABIPGPU_VEC_M] = m;
+    e->dD = take(Mm);
+    e->db = take(Mm);
+    e->p = take(Mm);
+    e->r = take(Mm);
+    e->Gp = take(Mm);
+    take(Mm);
+    e->dE = take(Nn);
+    e->dc = take(Nn);
+    e->tmp = take(Nn);
+    e->partials = take((size_t)2 * kMaxRed * gmax + 64);
+    e->dsc = take(ABIPGPU_SC_COUNT);
+    CK(cudaMallocHost((void**)&e->hsc, sizeof(double) * ABIPGPU_SC_COUNT));
+
+    LpCtx& c = e->ctx;
+    c.m = (int)m;
+    c.n = (int)n;
+    c.A = Csr{e->A_ptr, e->A_idx, e->A_val, (int)m, lgA, a_long.empty() ? 0x7fffffff : thrA, e->A_long, (int)a_long.size()};
+    c.AT = Csr{e->AT_ptr, e->AT_idx, e->AT_val, (int)n, lgAT, at_long.empty() ? 0x7fffffff : thrAT, e->AT_long,
+               (int)at_long.size()};
+    c.M = e->dM;
+    c.D = nullptr;
+    c.E = nullptr;
+    c.b = e->db;
+    c.c = e->dc;
+    c.h = e->vec[ABIPGPU_VEC_H];
+    c.g = e->vec[ABIPGPU_VEC_G];
+    c.rho_y = stgs->rho_y;
+    c.alpha = stgs->alpha;
+    c.cg_rate = stgs->cg_rate;
+    c.g_th = 0.0;
+    c.p = e->p;
+    c.r = e->r;
+    c.Gp = e->Gp;
+    c.tmp = e->tmp;
+    c.partials = e->partials;
+    c.sc = e->dsc;
+
+    k_precond<<<(unsigned)((m + 255) / 256), 256, 0, e->stream>>>(c.A, e->dM);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+
+    const double V = 8, I = 4;
+    e->B_A = (double)nnz * (V + I) + (m + 1.0) * I + n * V + m * V;
+    e->B_AT = (double)nnz * (V + I) + (n + 1.0) * I + m * V + n * V;
+    snprintf(e->desc, sizeof(e->desc),
+             "device %d (%s, %d SMs) block=%d grid(admm/bb/solve)=%d/%d/%d | CSR(A): %d rows mean-short %.1f -> %d "
+             "lanes/row, %zu long rows (>%d, warp-per-row 128-bit) | CSR(A'): %d rows mean-short %.1f -> %d lanes/row, "
+             "%zu long rows | nnz=%ld",
+             device, prop.name, e->num_sms, kBlock, e->grid_admm, e->grid_bb, e->grid_solve, (int)m, meanA, 1 << lgA,
+             a_long.size(), thrA, (int)n, meanAT, 1 << lgAT, at_long.size(), nnz);
+    return 0;
+}
+
+static void account_solve(abipgpu_lp* e, double cg_its, bool warm) {
+    // (c + 2 [+1 warm-start residual]) operator halves; 12 m-vector passes per CG iteration
+    e->stats.n_solves++;
+    e->stats.n_cg_iters += (abip_int)cg_its;
+    const double nA = cg_its + 1 + (warm ? 1 : 0), nAT = cg_its + 1 + (warm ? 1 : 0);
+    e->stats.n_spmv_A += (abip_int)nA;
+    e->stats.n_spmv_AT += (abip_int)nAT;
+    e->stats.alg_bytes += nA * e->B_A + nAT * e->B_AT + 12.0 * cg_its * e->m * 8.0;
+}
+
+extern "C" {
+
+abipgpu_lp* abipgpu_lp_create(abip_int m, abip_int n, const abip_int* Ap, const abip_int* Ai, const abip_float* Ax,
+                              const ABIPSettings* stgs, int device) {
+    if (!Ap || !Ai || !Ax || !stgs) return nullptr;
+    abipgpu_lp* e = new abipgpu_lp();
+    if (create_impl(e, m, n, Ap, Ai, Ax, stgs, device) != 0) {
+        abipgpu_lp_destroy(e);
+        return nullptr;
+    }
+    return e;
+}
+
+void abipgpu_lp_destroy(abipgpu_lp* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->A_ptr); cudaFree(e->A_idx); cudaFree(e->A_val);
+    cudaFree(e->AT_ptr); cudaFree(e->AT_idx); cudaFree(e->AT_val);
+    cudaFree(e->A_long); cudaFree(e->AT_long);
+    cudaFree(e->slab);
+    if (e->hsc) cudaFreeHost(e->hsc);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int abipgpu_lp_set_problem(abipgpu_lp* e, const abip_float* b, const abip_float* c, const abip_float* D,
+                           const abip_float* E) {
+    CK(cudaSetDevice(e->device));
+    const int m = e->m, n = e->n;
+    CK(cudaMemcpyAsync(e->db, b, sizeof(double) * m, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->dc, c, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    e->stats.h2d_bytes += 8.0 * (m + n);
+    e->have_scaling = (D && E);
+    if (e->have_scaling) {
+        CK(cudaMemcpyAsync(e->dD, D, sizeof(double) * m, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->dE, E, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+        e->stats.h2d_bytes += 8.0 * (m + n);
+    }
+    e->ctx.D = e->have_scaling ? e->dD : nullptr;
+    e->ctx.E = e->have_scaling ? e->dE : nullptr;
+    k_build_h<<<(m + n + 255) / 256, 256, 0, e->stream>>>(e->db, e->dc, e->vec[ABIPGPU_VEC_H], e->vec[ABIPGPU_VEC_G], m, n);
+    CK(cudaGetLastError());
+    if (launch_coop(e, (const void*)k_solve_vec, e->grid_solve, e->ctx, e->vec[ABIPGPU_VEC_G], (const double*)nullptr,
+                    (long)-1, 1))
+        return -1;
+    if (read_sc(e, nullptr)) return -1;
+    e->ctx.g_th = e->hsc[ABIPGPU_SC_VEC_NORM2];
+    account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], false);
+    return 0;
+}
+
+abip_float abipgpu_lp_g_th(const abipgpu_lp* e) { return e->ctx.g_th; }
+
+int abipgpu_lp_cold_start(abipgpu_lp* e, abip_float mu, abip_float beta) {
+    CK(cudaSetDevice(e->device));
+    k_cold_start<<<(e->l + 255) / 256, 256, 0, e->stream>>>(e->vec[ABIPGPU_VEC_U], e->vec[ABIPGPU_VEC_V], e->m, e->l,
+                                                             sqrt(mu / beta));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int abipgpu_lp_outer_prologue(abipgpu_lp* e, int avg_criterion) {
+    CK(cudaSetDevice(e->device));
+    const size_t bytes = sizeof(double) * e->l;
+    CK(cudaMemsetAsync(e->vec[ABIPGPU_VEC_USUM], 0, bytes, e->stream));
+    CK(cudaMemsetAsync(e->vec[ABIPGPU_VEC_VSUM], 0, bytes, e->stream));
+    CK(cudaMemsetAsync(e->vec[ABIPGPU_VEC_UAVG], 0, bytes, e->stream));
+    CK(cudaMemsetAsync(e->vec[ABIPGPU_VEC_VAVG], 0, bytes, e->stream));
+    e->restart_synced = true;  // u_avg == u_sum == 0 at the start of an outer iteration
+    if (avg_criterion) {
+        CK(cudaMemcpyAsync(e->vec[ABIPGPU_VEC_U], e->vec[ABIPGPU_VEC_UAVGC], bytes, cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->vec[ABIPGPU_VEC_V], e->vec[ABIPGPU_VEC_VAVGC], bytes, cudaMemcpyDeviceToDevice, e->stream));
+    }
+    return 0;
+}
+
+int abipgpu_lp_admm_iter(abipgpu_lp* e, abip_int j, abip_int k, abip_float mu, abip_float beta, abip_float* sc) {
+    CK(cudaSetDevice(e->device));
+    IterArgs a;
+    a.u = e->vec[ABIPGPU_VEC_U];
+    a.v = e->vec[ABIPGPU_VEC_V];
+    a.ut = e->vec[ABIPGPU_VEC_UT];
+    a.u_prev = e->vec[ABIPGPU_VEC_UPREV];
+    a.u_sum = e->vec[ABIPGPU_VEC_USUM];
+    a.v_sum = e->vec[ABIPGPU_VEC_VSUM];
+    a.u_avgc = e->vec[ABIPGPU_VEC_UAVGC];
+    a.v_avgc = e->vec[ABIPGPU_VEC_VAVGC];
+    a.u_avg = e->vec[ABIPGPU_VEC_UAVG];
+    a.v_avg = e->vec[ABIPGPU_VEC_VAVG];
+    a.j = j;
+    a.k = k;
+    a.mu = mu;
+    a.beta = beta;
+    a.half_update = (int)e->stgs.half_update;
+    // restart_vars (abip.c:587-630): u_avg/v_avg equal u_sumcon/v_sumcon until the first restart of an outer
+    // iteration fires, and are only read once k >= restart_thresh, so they are materialised lazily.
+    a.restart_active = (k >= e->stgs.restart_thresh) ? 1 : 0;
+    a.restart_fire = 0;
+    a.restart_fre = (double)e->stgs.restart_fre;
+    if (a.restart_active) {
+        if (e->restart_synced && j > 0) {
+            const size_t bytes = sizeof(double) * e->l;
+            CK(cudaMemcpyAsync(a.u_avg, a.u_sum, bytes, cudaMemcpyDeviceToDevice, e->stream));
+            CK(cudaMemcpyAsync(a.v_avg, a.v_sum, bytes, cudaMemcpyDeviceToDevice, e->stream));
+        }
+        e->restart_synced = false;
+    }
+    // fre_old is 0 until the first restart of this outer iteration and fre afterwards (abip.c:628, 2116):
+    // both give the same residue class, so the firing rule reduces to (j+1) % fre == 0
+    if (a.restart_active && e->stgs.restart_fre > 0 && (j + 1) % e->stgs.restart_fre == 0) a.restart_fire = 1;
+    CK(cudaEventRecord(e->ev0, e->stream));
+    if (launch_coop(e, (const void*)k_admm_iter, e->grid_admm, e->ctx, a)) return -1;
+    CK(cudaEventRecord(e->ev1, e->stream));
+    if (read_sc(e, sc)) return -1;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->stats.admm_kernel_ms += ms;
+    e->stats.n_admm_launch++;
+    account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], true);
+    const double nq = e->hsc[ABIPGPU_SC_HAS_AVG] != 0 ? 2.0 : 1.0;
+    e->stats.n_spmv_A += (abip_int)nq;
+    e->stats.n_spmv_AT += (abip_int)nq;
+    // rhs (6 l) + prox/dual/avg (9 l) + Q-norm extra vectors (b, c, D, E, s, y: ~3 l) per pair
+    e->stats.alg_bytes += nq * (e->B_A + e->B_AT) + (15.0 + 3.0 * nq) * e->l * 8.0;
+    return 0;
+}
+
+int abipgpu_lp_mu_stats(abipgpu_lp* e, int avg_criterion, abip_float* sc) {
+    CK(cudaSetDevice(e->device));
+    const double* u = e->vec[avg_criterion ? ABIPGPU_VEC_UAVGC : ABIPGPU_VEC_U];
+    const double* v = e->vec[avg_criterion ? ABIPGPU_VEC_VAVGC : ABIPGPU_VEC_V];
+    if (launch_coop(e, (const void*)k_mu_stats, e->grid_mu, u, v, e->m, e->l, e->partials, e->dsc)) return -1;
+    return read_sc(e, sc);
+}
+
+int abipgpu_lp_reinit(abipgpu_lp* e, int indx, abip_float sigma, int avg_criterion) {
+    CK(cudaSetDevice(e->device));
+    double* u = e->vec[avg_criterion ? ABIPGPU_VEC_UAVGC : ABIPGPU_VEC_U];
+    double* v = e->vec[avg_criterion ? ABIPGPU_VEC_VAVGC : ABIPGPU_VEC_V];
+    k_reinit<<<(e->n + 1 + 255) / 256, 256, 0, e->stream>>>(u, v, e->m, e->l, indx, sigma);
+    CK(cudaGetLastError());
+    e->stats.n_kernel_launches++;
+    return 0;
+}
+
+int abipgpu_lp_bb_begin(abipgpu_lp* e) {
+    CK(cudaSetDevice(e->device));
+    const size_t bytes = sizeof(double) * e->l;
+    CK(cudaMemcpyAsync(e->vec[ABIPGPU_VEC_BB_UPREV], e->vec[ABIPGPU_VEC_U], bytes, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->vec[ABIPGPU_VEC_BB_VPREV], e->vec[ABIPGPU_VEC_V], bytes, cudaMemcpyDeviceToDevice, e->stream));
+    return 0;
+}
+
+int abipgpu_lp_bb_round(abipgpu_lp* e, int carry, abip_int k, abip_float mu, abip_float beta_prev, abip_float* sc) {
+    CK(cudaSetDevice(e->device));
+    BBArgs a;
+    a.u_prev = e->vec[ABIPGPU_VEC_BB_UPREV];
+    a.v_prev = e->vec[ABIPGPU_VEC_BB_VPREV];
+    a.ut = e->vec[ABIPGPU_VEC_BB_UT];
+    a.u = e->vec[ABIPGPU_VEC_BB_U];
+    a.v = e->vec[ABIPGPU_VEC_BB_V];
+    a.ut_next = e->vec[ABIPGPU_VEC_BB_UTNEXT];
+    a.u_next = e->vec[ABIPGPU_VEC_BB_UNEXT];
+    a.v_next = e->vec[ABIPGPU_VEC_BB_VNEXT];
+    a.carry = carry;
+    a.k = k;
+    a.mu = mu;
+    a.beta_prev = beta_prev;
+    CK(cudaEventRecord(e->ev0, e->stream));
+    if (launch_coop(e, (const void*)k_bb_round, e->grid_bb, e->ctx, a)) return -1;
+    CK(cudaEventRecord(e->ev1, e->stream));
+    if (read_sc(e, sc)) return -1;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->stats.bb_kernel_ms += ms;
+    e->stats.n_bb_launch++;
+    account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], true);
+    account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS2], true);
+    e->stats.alg_bytes += (2 * 6.0 + 2 * 6.0 + (carry ? 4.0 : 0.0)) * e->l * 8.0;
+    return 0;
+}
+
+int abipgpu_lp_solve_vec(abipgpu_lp* e, int rhs_id, int warm_id, abip_int iter, abip_float* sc) {
+    CK(cudaSetDevice(e->device));
+    if (rhs_id < 0 || rhs_id > 20 || warm_id > 20) return -1;
+    const double* s = warm_id >= 0 ? e->vec[warm_id] : nullptr;
+    if (launch_coop(e, (const void*)k_solve_vec, e->grid_solve, e->ctx, e->vec[rhs_id], s, (long)iter, 0)) return -1;
+    if (read_sc(e, sc)) return -1;
+    account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], s != nullptr);
+    return 0;
+}
+
+int abipgpu_lp_get_vec(abipgpu_lp* e, int id, abip_float* host, abip_int len) {
+    CK(cudaSetDevice(e->device));
+    if (id < 0 || id > 20 || len > e->vec_len[id]) return -1;
+    CK(cudaMemcpyAsync(host, e->vec[id], sizeof(double) * len, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->stats.d2h_bytes += 8.0 * len;
+    return 0;
+}
+
+int abipgpu_lp_set_vec(abipgpu_lp* e, int id, const abip_float* host, abip_int len) {
+    CK(cudaSetDevice(e->device));
+    if (id < 0 || id > 20 || len > e->vec_len[id]) return -1;
+    CK(cudaMemcpyAsync(e->vec[id], host, sizeof(double) * len, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->stats.h2d_bytes += 8.0 * len;
+    return 0;
+}
+
+int abipgpu_lp_spmv(abipgpu_lp* e, int trans, const abip_float* x, abip_float* y) {
+    return abipgpu_lp_spmv_host(e, trans, x, y, 0);
+}
+
+void abipgpu_lp_describe(const abipgpu_lp* e, char* buf, abip_int buflen) {
+    if (buflen > 0) snprintf(buf, (size_t)buflen, "%s", e->desc);
+}
+
+}  // extern "C"
+
+// ---- internal helpers shared with lp_host.cpp -------------------------------------------------------------
+int abipgpu_lp_spmv_host(abipgpu_lp* e, int trans, const double* x, double* y, int accumulate) {
+    CK(cudaSetDevice(e->device));
+    const int nin = trans ? e->m : e->n, nout = trans ? e->n : e->m;
+    CK(cudaMemcpyAsync(e->xin, x, sizeof(double) * nin, cudaMemcpyHostToDevice, e->stream));
+    if (accumulate) CK(cudaMemcpyAsync(e->yout, y, sizeof(double) * nout, cudaMemcpyHostToDevice, e->stream));
+    k_spmv<<<e->grid_spmv, kBlock, 0, e->stream>>>(trans ? e->ctx.AT : e->ctx.A, e->xin, e->yout, accumulate);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(y, e->yout, sizeof(double) * nout, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->stats.n_kernel_launches++;
+    e->stats.h2d_bytes += 8.0 * (nin + (accumulate ? nout : 0));
+    e->stats.d2h_bytes += 8.0 * nout;
+    if (trans) e->stats.n_spmv_AT++; else e->stats.n_spmv_A++;
+    return 0;
+}
+
+// solve_lin_sys with host pointers (plugin path): b [m+n] in/out, s [m] or NULL
+int abipgpu_lp_solve_host(abipgpu_lp* e, double* b, const double* s, long iter, int* cg_its) {
+    CK(cudaSetDevice(e->device));
+    const int mn = e->m + e->n;
+    CK(cudaMemcpyAsync(e->xin, b, sizeof(double) * mn, cudaMemcpyHostToDevice, e->stream));
+    if (s) CK(cudaMemcpyAsync(e->yout, s, sizeof(double) * e->m, cudaMemcpyHostToDevice, e->stream));
+    if (launch_coop(e, (const void*)k_solve_vec, e->grid_solve, e->ctx, e->xin, (const double*)(s ? e->yout : nullptr),
+                    iter, 0))
+        return -1;
+    CK(cudaMemcpyAsync(b, e->xin, sizeof(double) * mn, cudaMemcpyDeviceToHost, e->stream));
+    if (read_sc(e, nullptr)) return -1;
+    e->stats.h2d_bytes += 8.0 * (mn + (s ? e->m : 0));
+    e->stats.d2h_bytes += 8.0 * mn;
+    account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], s != nullptr);
+    if (cg_its) *cg_its = (int)e->hsc[ABIPGPU_SC_CG_ITS];
+    return 0;
+}
+
+ABIPGpuStats* abipgpu_lp_stats(abipgpu_lp* e) { return &e->stats; }
+int abipgpu_lp_dims(const abipgpu_lp* e, int* m, int* n) { *m = e->m; *n = e->n; return 0; }
+int abipgpu_lp_sync(abipgpu_lp* e) {
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}

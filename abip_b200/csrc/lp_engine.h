@@ -1,0 +1,13 @@
+// lp_engine.h -- internal interface between the CUDA engine (lp_engine.cu) and the host solver (lp_host.cpp).
+#pragma once
+#include "../../include/abip_gpu.h"
+#ifdef __CUDACC__
+#include "lp_device.cuh"
+#endif
+
+// host-pointer helpers used by the linsys plugin symbols
+int abipgpu_lp_spmv_host(abipgpu_lp* e, int trans, const double* x, double* y, int accumulate);
+int abipgpu_lp_solve_host(abipgpu_lp* e, double* b, const double* s, long iter, int* cg_its);
+ABIPGpuStats* abipgpu_lp_stats(abipgpu_lp* e);
+int abipgpu_lp_dims(const abipgpu_lp* e, int* m, int* n);
+int abipgpu_lp_sync(abipgpu_lp* e);

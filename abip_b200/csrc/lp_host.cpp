@@ -1,0 +1,864 @@
+// lp_host.cpp -- host side of the ABIP-LP engine: the reference's linsys plugin symbols (group (1) of
+// include/abip_gpu.h) and the outer IPM / inner ADMM / Barzilai-Borwein control flow of the solver entry
+// (group (2)).  Only scalar decisions happen here; every vector operation is a CUDA kernel in lp_engine.cu.
+// Each function cites the reference lines whose behaviour it reproduces (paths under src/abip-lp/).
+#include "lp_engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <csignal>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <vector>
+
+namespace {
+
+constexpr double kMinScale = 1e-3, kMaxScale = 1e3;  // linsys/common.c:4-5, src/normalize.c:5-6
+constexpr double kEpsTol = 1e-18;                    // include/glbopts.h:157
+constexpr double kIndeterminateTol = 1e-9;           // include/glbopts.h:161
+
+inline double safediv_pos(double x, double y) { return y < kEpsTol ? x / kEpsTol : x / y; }  // glbopts.h:158
+
+double now_ms() {  // src/util.c:73-102 (CLOCK_MONOTONIC, milliseconds)
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+}
+
+// ---- SIGINT polling, same contract as src/ctrlc.c:62-93 -------------------------------------------------
+volatile sig_atomic_t g_interrupted = 0;
+struct sigaction g_old_action;
+void on_sigint(int) { g_interrupted = 1; }
+void start_interrupt_listener() {
+    struct sigaction act;
+    g_interrupted = 0;
+    act.sa_flags = 0;
+    sigemptyset(&act.sa_mask);
+    act.sa_handler = on_sigint;
+    sigaction(SIGINT, &act, &g_old_action);
+}
+void end_interrupt_listener() {
+    struct sigaction cur;
+    sigaction(SIGINT, &g_old_action, &cur);
+}
+
+double norm2(const double* a, long n) {
+    double s = 0;
+    for (long i = 0; i < n; ++i) s += a[i] * a[i];
+    return std::sqrt(s);
+}
+
+}  // namespace
+
+// =========================================================================================================
+// (1) linsys plugin
+// =========================================================================================================
+struct ABIP_LIN_SYS_WORK {
+    abipgpu_lp* eng;
+    abip_int tot_cg_its;        // linsys/indirect.h:26-28
+    abip_float total_solve_time;
+};
+
+extern "C" {
+
+abip_int abip_copy_A_matrix(ABIPMatrix** dstp, const ABIPMatrix* src) {  // common.c:10-41 (1 = ok, 0 = fail)
+    const abip_int nnz = src->p[src->n];
+    ABIPMatrix* A = (ABIPMatrix*)calloc(1, sizeof(ABIPMatrix));
+    if (!A) return 0;
+    A->m = src->m;
+    A->n = src->n;
+    A->x = (abip_float*)malloc(sizeof(abip_float) * nnz);
+    A->i = (abip_int*)malloc(sizeof(abip_int) * nnz);
+    A->p = (abip_int*)malloc(sizeof(abip_int) * (src->n + 1));
+    if (!A->x || !A->i || !A->p) {
+        free(A->x); free(A->i); free(A->p); free(A);
+        return 0;
+    }
+    std::copy(src->x, src->x + nnz, A->x);
+    std::copy(src->i, src->i + nnz, A->i);
+    std::copy(src->p, src->p + src->n + 1, A->p);
+    *dstp = A;
+    return 1;
+}
+
+void abip_free_A_matrix(ABIPMatrix* A) {  // common.c:100-118
+    if (!A) return;
+    free(A->x); free(A->i); free(A->p); free(A);
+}
+
+abip_int abip_validate_lin_sys(const ABIPMatrix* A) {  // common.c:44-96
+    if (!A->x || !A->i || !A->p) {
+        printf("ERROR: incomplete data!\n");
+        return -1;
+    }
+    for (abip_int j = 0; j < A->n; ++j) {
+        if (A->p[j] == A->p[j + 1]) printf("WARN: the %li-th column empty!\n", (long)j);
+        else if (A->p[j] > A->p[j + 1]) {
+            printf("ERROR: the column pointers decreases!\n");
+            return -1;
+        }
+    }
+    const abip_int nnz = A->p[A->n];
+    if (((abip_float)nnz / A->m > A->n) || nnz <= 0) {
+        printf("ERROR: the number of nonzeros in A = %li, outside of valid range!\n", (long)nnz);
+        return -1;
+    }
+    abip_int rmax = 0;
+    for (abip_int k = 0; k < nnz; ++k) rmax = std::max(rmax, A->i[k]);
+    if (rmax > A->m - 1) {
+        printf("ERROR: the number of rows in A is inconsistent with input dimension!\n");
+        return -1;
+    }
+    return 0;
+}
+
+// Equilibration of A (common.c:150-565).  One generic sweep -- "scale columns by f(column), then rows by
+// f(row)" -- instantiated for the pc (sqrt of 1-norm), origin (2-norm), ruiz (sqrt of inf-norm, repeated) and qp
+// (sqrt(min*max)) variants; D and E accumulate the products (:524-532).
+void abip_normalize_A(ABIPMatrix* A, const ABIPSettings* stgs, ABIPScaling* scal) {
+    const abip_int m = A->m, n = A->n, nnz = A->p[n];
+    double* D = (double*)malloc(sizeof(double) * m);
+    double* E = (double*)malloc(sizeof(double) * n);
+    std::fill(D, D + m, 1.0);
+    std::fill(E, E + n, 1.0);
+    const double min_row = kMinScale * std::sqrt((double)n), max_row = kMaxScale * std::sqrt((double)n);
+    const double min_col = kMinScale * std::sqrt((double)m), max_col = kMaxScale * std::sqrt((double)m);
+    std::vector<double> dt(m), dt2(m);
+    enum Kind { PC, ORIGIN, RUIZ, QP };
+    auto clamp = [](double v, double lo, double hi) { return v < lo ? 1.0 : (v > hi ? hi : v); };
+    auto sweep = [&](Kind kind) {
+        for (abip_int j = 0; j < n; ++j) {  // column factor, applied immediately
+            double acc = 0, mn = 0;
+            const abip_int c1 = A->p[j], c2 = A->p[j + 1];
+            for (abip_int k = c1; k < c2; ++k) {
+                const double a = std::fabs(A->x[k]);
+                if (kind == PC) acc += a;
+                else if (kind == ORIGIN) acc += a * a;
+                else acc = std::max(acc, a);
+            }
+            double e;
+            if (kind == QP) {  // sqrt(min nonzero) * sqrt(max), :423-428
+                mn = acc;
+                for (abip_int k = c1; k < c2; ++k) {
+                    const double a = std::fabs(A->x[k]);
+                    if (a <= mn && a > 0) mn = a;
+                }
+                e = std::sqrt(mn) * std::sqrt(acc);
+            } else {
+                e = std::sqrt(acc);
+            }
+            e = clamp(e, min_col, max_col);
+            const double inv = 1.0 / e;
+            for (abip_int k = c1; k < c2; ++k) A->x[k] *= inv;
+            E[j] *= e;
+        }
+        std::fill(dt.begin(), dt.end(), 0.0);
+        for (abip_int k = 0; k < nnz; ++k) {  // row statistic
+            const double a = std::fabs(A->x[k]);
+            double& d = dt[A->i[k]];
+            if (kind == PC) d += a;
+            else if (kind == ORIGIN) d += a * a;
+            else if (a >= d) d = a;
+        }
+        if (kind == QP) {
+            dt2 = dt;
+            for (abip_int k = 0; k < nnz; ++k) {
+                const double a = std::fabs(A->x[k]);
+                if (a <= dt2[A->i[k]] && a > 0) dt2[A->i[k]] = a;
+            }
+        }
+        for (abip_int i = 0; i < m; ++i) {
+            const double v = (kind == QP) ? std::sqrt(dt[i] * dt2[i]) : std::sqrt(dt[i]);
+            dt[i] = clamp(v, min_row, max_row);
+            D[i] *= dt[i];
+        }
+        for (abip_int k = 0; k < nnz; ++k) A->x[k] /= dt[A->i[k]];
+    };
+    const bool say = stgs->verbose != 0;  // the reference prints these unconditionally
+    if (stgs->pc_ruiz_rescale) { sweep(PC); if (say) printf("Done the pc rescaling!\n"); }
+    if (stgs->origin_rescale) { sweep(ORIGIN); if (say) printf("Done the origin rescaling!\n"); }
+    if (stgs->pc_ruiz_rescale) {
+        for (abip_int it = 0; it < stgs->ruiz_iter; ++it) sweep(RUIZ);
+        if (say) printf("Done the ruiz rescaling!\n");
+    }
+    if (stgs->qp_rescale) { sweep(QP); if (say) printf("Done the QP rescaling\n"); }
+    // mean row / column 2-norms of the scaled matrix (:535-557)
+    std::fill(dt.begin(), dt.end(), 0.0);
+    for (abip_int k = 0; k < nnz; ++k) dt[A->i[k]] += A->x[k] * A->x[k];
+    scal->mean_norm_row_A = 0.0;
+    for (abip_int i = 0; i < m; ++i) scal->mean_norm_row_A += std::sqrt(dt[i]) / m;
+    scal->mean_norm_col_A = 0.0;
+    for (abip_int j = 0; j < n; ++j)
+        scal->mean_norm_col_A += norm2(A->x + A->p[j], A->p[j + 1] - A->p[j]) / n;
+    if (stgs->scale != 1)
+        for (abip_int k = 0; k < nnz; ++k) A->x[k] *= stgs->scale;
+    scal->D = D;
+    scal->E = E;
+}
+
+void abip_un_normalize_A(ABIPMatrix* A, const ABIPSettings* stgs, const ABIPScaling* scal) {  // common.c:570-594
+    for (abip_int j = 0; j < A->n; ++j)
+        for (abip_int k = A->p[j]; k < A->p[j + 1]; ++k) A->x[k] *= scal->D[A->i[k]] * (scal->E[j] / stgs->scale);
+}
+
+char* abip_get_lin_sys_method(const ABIPMatrix* A, const ABIPSettings* stgs) {  // indirect.c:8-18
+    char* str = (char*)malloc(128);
+    snprintf(str, 128, "sparse-indirect (B200 CUDA PCG), nnz in A = %li, CG tol ~ 1/iter^(%2.2f)", (long)A->p[A->n],
+             stgs->cg_rate);
+    return str;
+}
+
+char* abip_get_lin_sys_summary(ABIPLinSysWork* p, const ABIPInfo* info) {  // indirect.c:20-33
+    char* str = (char*)malloc(128);
+    snprintf(str, 128, "\tLin-sys: avg # CG iterations: %2.2f, avg solve time: %1.2es\n",
+             (abip_float)p->tot_cg_its / (info->admm_iter + 1), p->total_solve_time / (info->admm_iter + 1) / 1e3);
+    p->tot_cg_its = 0;
+    p->total_solve_time = 0;
+    return str;
+}
+
+ABIPLinSysWork* abip_init_lin_sys_work(const ABIPMatrix* A, const ABIPSettings* stgs) {  // indirect.c:282-318
+    ABIPLinSysWork* p = (ABIPLinSysWork*)calloc(1, sizeof(ABIPLinSysWork));
+    if (!p) return nullptr;
+    const char* dev = getenv("ABIP_GPU_DEVICE");
+    p->eng = abipgpu_lp_create(A->m, A->n, A->p, A->i, A->x, stgs, dev ? atoi(dev) : 0);
+    if (!p->eng) {
+        free(p);
+        return nullptr;
+    }
+    return p;
+}
+
+void abip_free_lin_sys_work(ABIPLinSysWork* p) {  // indirect.c:141-203
+    if (!p) return;
+    abipgpu_lp_destroy(p->eng);
+    free(p);
+}
+
+abip_int abip_solve_lin_sys(const ABIPMatrix* A, const ABIPSettings* stgs, ABIPLinSysWork* p, abip_float* b,
+                            const abip_float* s, abip_int iter) {  // indirect.c:393-434
+    (void)A;
+    (void)stgs;
+    const double t0 = now_ms();
+    int its = 0;
+    if (abipgpu_lp_solve_host(p->eng, b, s, (long)iter, &its) != 0) return -1;
+    if (iter >= 0) p->tot_cg_its += its;
+    p->total_solve_time += now_ms() - t0;
+    return 0;
+}
+
+void abip_accum_by_Atrans(const ABIPMatrix* A, ABIPLinSysWork* p, const abip_float* x, abip_float* y) {
+    (void)A;
+    if (abipgpu_lp_spmv_host(p->eng, 1, x, y, 1) != 0) {  // the reference signature has no error channel
+        fprintf(stderr, "[abip_gpu] accum_by_Atrans failed\n");
+        abort();
+    }
+}
+
+void abip_accum_by_A(const ABIPMatrix* A, ABIPLinSysWork* p, const abip_float* x, abip_float* y) {
+    (void)A;
+    if (abipgpu_lp_spmv_host(p->eng, 0, x, y, 1) != 0) {
+        fprintf(stderr, "[abip_gpu] accum_by_A failed\n");
+        abort();
+    }
+}
+
+}  // extern "C"
+
+// =========================================================================================================
+// (2) solver entry
+// =========================================================================================================
+struct Resid {  // struct ABIP_RESIDUALS, include/abip.h:178-196
+    abip_int last_ipm_iter = -1, last_admm_iter = -1;
+    double res_pri = NAN, res_dual = NAN, rel_gap = NAN, res_infeas = NAN, res_unbdd = NAN;
+    double ct_x_by_tau = NAN, bt_y_by_tau = NAN, tau = NAN, kap = NAN;
+};
+
+struct ABIP_GPU_WORK {  // device-resident replacement of struct ABIP_WORK (include/abip.h:126-176)
+    abip_int m = 0, n = 0;
+    ABIPMatrix* A = nullptr;  // scaled private copy (COPYAMATRIX behaviour, abip.c:1799-1810)
+    ABIPScaling scal{nullptr, nullptr, 0, 0};
+    bool have_scal = false;
+    ABIPSettings stgs;  // private copy: the reference mutates the caller's struct (avg_criterion, dynamic_sigma,
+                        // max_admm_iters; SURVEY.md parity trap 5) -- we mutate this copy instead
+    double sp = 0;
+    abipgpu_lp* eng = nullptr;
+    std::vector<double> b, c;  // scaled
+    double sigma = 0, gamma = 0, mu = 1, beta = 1;
+    int final_check = 0, double_check = 0;
+    double sc_b = 1, sc_c = 1, nm_b = 0, nm_c = 0;
+    double sc[ABIPGPU_SC_COUNT];  // last scalar block of an ADMM iteration
+    abip_int tot_cg_its = 0;
+    double total_solve_ms = 0, total_adapt_ms = 0;
+    ABIPGpuStats last_stats;
+    FILE* trace = nullptr;
+};
+
+namespace {
+
+int validate(const ABIPData* d) {  // src/abip.c:1646-1734
+    const ABIPSettings* s = d->stgs;
+    if (d->m <= 0 || d->n <= 0) {
+        printf("m and n must both be greater than 0; m = %li, n = %li\n", (long)d->m, (long)d->n);
+        return -1;
+    }
+    if (d->m > d->n) {
+        printf("WARN: m larger than n, problem likely degenerate\n");
+        return -1;
+    }
+    if (abip_validate_lin_sys(d->A) < 0) {
+        printf("invalid linear system input data\n");
+        return -1;
+    }
+    struct { bool bad; const char* msg; } checks[] = {
+        {s->max_ipm_iters <= 0, "max_ipm_iters must be positive"},
+        {s->max_admm_iters <= 0, "max_admm_iters must be positive"},
+        {s->eps <= 0, "eps tolerance must be positive"},
+        {s->alpha <= 0 || s->alpha >= 2, "alpha must be in (0,2)"},
+        {s->rho_y <= 0, "rho_y must be positive (1e-3 works well)."},
+        {s->scale <= 0, "scale must be positive (1 works well)."},
+        {s->eps_cor <= 0, "eps_cor tolerance must be positive."},
+        {s->eps_pen <= 0, "eps_pen tolerance must be positive."},
+        {s->adaptive_lookback <= 0, "adaptive_lookback must be positive."},
+        {s->hybrid_mu > 0 && s->dynamic_sigma >= 0, "when use hybrid mu strategy, dynamic_sigma must be negative."},
+    };
+    for (auto& ck : checks)
+        if (ck.bad) {
+            printf("%s\n", ck.msg);
+            return -1;
+        }
+    return 0;
+}
+
+void fill_nan(double* a, abip_int n) {
+    for (abip_int i = 0; i < n; ++i) a[i] = NAN;
+}
+
+abip_int failure(abip_int m, abip_int n, ABIPSolution* sol, ABIPInfo* info, abip_int status, const char* msg,
+                 const char* ststr) {  // src/abip.c:219-303
+    if (info) {
+        info->res_pri = info->res_dual = info->rel_gap = info->res_infeas = info->res_unbdd = NAN;
+        info->pobj = info->dobj = NAN;
+        info->ipm_iter = info->admm_iter = -1;
+        info->status_val = status;
+        info->solve_time = NAN;
+        snprintf(info->status, sizeof(info->status), "%s", ststr);
+    }
+    if (sol) {
+        if (n > 0) {
+            if (!sol->x) sol->x = (double*)malloc(sizeof(double) * n);
+            if (!sol->s) sol->s = (double*)malloc(sizeof(double) * n);
+            fill_nan(sol->x, n);
+            fill_nan(sol->s, n);
+        }
+        if (m > 0) {
+            if (!sol->y) sol->y = (double*)malloc(sizeof(double) * m);
+            fill_nan(sol->y, m);
+        }
+    }
+    printf("Failure:%s\n", msg);
+    end_interrupt_listener();
+    return status;
+}
+
+// Q-norm criterion from one 13-scalar group (src/abip.c:1972-1992)
+double qnorm_value(const double* g) {
+    const double S_PR = g[0], BTY = g[3], UU_Y = g[4], S_DR = g[5], CTX = g[8], UU_X = g[9], VV = g[10];
+    const double tau = g[11], kap = g[12];
+    const double gap = BTY - CTX - kap;
+    const double Q = S_PR + S_DR + gap * gap;
+    const double nrm = 1 + std::sqrt((UU_Y + UU_X + tau * tau) + (VV + kap * kap));
+    return std::sqrt(Q) / nrm;
+}
+
+// calc_residuals (src/abip.c:458-535) evaluated from the sums the ADMM kernel already reduced
+void calc_residuals(ABIP_GPU_WORK* w, Resid* r, abip_int ipm_iter, abip_int admm_iter) {
+    if (admm_iter && r->last_admm_iter == admm_iter) return;
+    r->last_ipm_iter = ipm_iter;
+    r->last_admm_iter = admm_iter;
+    const double* g = w->sc + (w->stgs.avg_criterion ? ABIPGPU_SC_AVG_BASE : ABIPGPU_SC_S_PR);
+    const double W_AX = g[1], W_PR = g[2], BTY = g[3], W_ATYS = g[6], W_DR = g[7], CTX = g[8];
+    const bool nz = w->stgs.normalize != 0;
+    const double nrm = nz ? (w->stgs.scale * w->sc_c * w->sc_b) : 1.0;
+    const double sb = nz ? (w->sc_b * w->stgs.scale) : 1.0, scn = nz ? (w->sc_c * w->stgs.scale) : 1.0;
+    r->tau = std::fabs(g[11]);
+    r->kap = std::fabs(g[12]) / nrm;
+    const double nmpr_tau = std::sqrt(W_PR) / sb, nm_A_x_tau = std::sqrt(W_AX) / sb;
+    const double nmdr_tau = std::sqrt(W_DR) / scn, nm_At_ys_tau = std::sqrt(W_ATYS) / scn;
+    r->bt_y_by_tau = BTY / nrm;
+    r->ct_x_by_tau = CTX / nrm;
+    r->res_infeas = r->bt_y_by_tau > 0 ? w->nm_b * nm_At_ys_tau / r->bt_y_by_tau : NAN;
+    r->res_unbdd = r->ct_x_by_tau < 0 ? w->nm_c * nm_A_x_tau / -r->ct_x_by_tau : NAN;
+    const double bt_y = safediv_pos(r->bt_y_by_tau, r->tau), ct_x = safediv_pos(r->ct_x_by_tau, r->tau);
+    r->res_pri = safediv_pos(nmpr_tau / (1 + w->nm_b), r->tau);
+    r->res_dual = safediv_pos(nmdr_tau / (1 + w->nm_c), r->tau);
+    r->rel_gap = std::fabs(ct_x - bt_y) / (1 + std::fabs(ct_x) + std::fabs(bt_y));
+}
+
+abip_int has_converged(const ABIP_GPU_WORK* w, const Resid* r, abip_int ipm_iter, abip_int admm_iter) {  // :1613-1641
+    const double eps = w->stgs.eps;
+    if (r->res_pri < eps && (r->res_dual < eps || w->stgs.pfeasopt) && r->rel_gap < eps) return ABIP_SOLVED;
+    if (r->res_unbdd < eps && ipm_iter > 0 && admm_iter > 0) return ABIP_UNBOUNDED;
+    if (r->res_infeas < eps && ipm_iter > 0 && admm_iter > 0) return ABIP_INFEASIBLE;
+    return 0;
+}
+
+// table-driven mu rule (src/abip.c:753-921)
+void update_barrier(ABIP_GPU_WORK* w, const Resid* r) {
+    const ABIPSettings& s = w->stgs;
+    const double ratio = w->mu / s.eps;
+    const double err = std::max(std::max(r->res_pri, r->res_dual), r->rel_gap) / s.eps;
+    const bool dense = std::max(w->sp, s.sparsity_ratio) > 0.4 || std::min(w->sp, s.sparsity_ratio) > 0.1;
+    static const double lo[] = {10.0, 1.0, 0.5, 0.1, 0.05, 0.01, 0.005, 0.001};
+    const double gam[] = {dense ? 2.0 : 3.0, 1.0, 0.9, 0.8, 0.7, 0.6, 0.5, 0.4};
+    double gamma = 0.3, sigma = w->sigma;
+    for (int q = 0; q < 8; ++q)
+        if (ratio > lo[q]) { gamma = gam[q]; break; }
+    if (dense) {
+        if (err > 6 && err <= 10) sigma = 0.5;
+        else if (err > 3 && err <= 6) { sigma = 0.6; gamma *= 0.8; }
+        else if (err > 1 && err <= 3) { w->final_check = 1; gamma *= 0.4; sigma = ratio < 0.1 ? 0.8 : 0.7; }
+    } else {
+        if (err > 6 && err <= 10) { sigma = 0.82; gamma *= 0.8; }
+        else if (err > 4 && err <= 6) { sigma = 0.84; gamma *= 0.6; }
+        else if (err > 3 && err <= 4) { sigma = 0.85; gamma *= 0.5; w->final_check = 1; }
+        else if (err > 1 && err <= 3) {
+            w->final_check = 1;
+            if (ratio < 0.1) {
+                if (w->double_check) { sigma = 0.9; gamma *= 0.4; w->double_check = 0; }
+                else { sigma = 1.0; gamma *= 0.1; w->double_check = 1; }
+            } else { sigma = 0.88; gamma *= 0.4; }
+        }
+    }
+    w->mu *= sigma;
+    w->sigma = sigma;
+    w->gamma = gamma;
+}
+
+// LOQO rule (src/abip.c:930-977); min / sum of u_i v_i are reduced on the device
+int update_barrier_dynamic(ABIP_GPU_WORK* w) {
+    double sc[ABIPGPU_SC_COUNT];
+    if (abipgpu_lp_mu_stats(w->eng, (int)w->stgs.avg_criterion, sc) != 0) return -1;
+    const double minxs = sc[ABIPGPU_SC_MIN_XS];
+    if (!(minxs > 0.0)) {  // the reference assert(0)s here (:962-965)
+        printf("Invalid xisi < 0 \n");
+        return -1;
+    }
+    const double xs = sc[ABIPGPU_SC_SUM_XS] / (w->n + 1);
+    const double ksi = minxs / xs;
+    double sigma = std::min(0.05 * (1 - ksi) / ksi, 2.0);
+    sigma = std::max(0.1 * sigma * sigma * sigma, w->stgs.dynamic_sigma);
+    w->mu *= sigma;
+    return 0;
+}
+
+void update_barrier_dynamic_2(ABIP_GPU_WORK* w) {  // src/abip.c:982-992; eta = dynamic_sigma (parity trap 6)
+    w->mu *= std::min(w->stgs.dynamic_x * w->mu, std::pow(w->mu, w->stgs.dynamic_sigma));
+}
+
+int update_mu(ABIP_GPU_WORK* w, const Resid* r) {  // selection logic, src/abip.c:2251-2277
+    ABIPSettings& s = w->stgs;
+    if (s.hybrid_mu) {
+        if (s.dynamic_sigma_second > 0.0 && w->mu < s.hybrid_thresh * s.eps) {
+            s.dynamic_sigma = s.dynamic_sigma_second;
+            return update_barrier_dynamic(w);
+        } else if (s.dynamic_sigma_second == 0.0 && w->mu < s.hybrid_thresh * s.eps) {
+            s.dynamic_sigma = s.dynamic_sigma_second;
+            update_barrier(w, r);
+        } else if (s.dynamic_sigma < 0.0) {
+            update_barrier_dynamic_2(w);
+        }
+    } else {
+        if (s.dynamic_sigma == 0.0) update_barrier(w, r);
+        else if (s.dynamic_sigma < 0.0) update_barrier_dynamic_2(w);
+        else return update_barrier_dynamic(w);
+    }
+    return 0;
+}
+
+// Barzilai-Borwein search for beta (src/adaptive.c:34-256): the two ADMM steps and the five inner products of a
+// lookback round are one kernel launch; the safeguarded spectral step below is scalar work.
+int adaptive_search(ABIP_GPU_WORK* w, abip_int iter) {
+    const ABIPSettings& s = w->stgs;
+    if (s.adaptive_lookback <= 0) return -1;
+    const double t0 = now_ms();
+    if (abipgpu_lp_bb_begin(w->eng) != 0) return -1;
+    double beta_prev = 1.0, beta = 0.0;
+    int carry = 0;
+    double sc[ABIPGPU_SC_COUNT];
+    for (abip_int i = 0; i < s.adaptive_lookback; ++i) {
+        if (abipgpu_lp_bb_round(w->eng, carry, iter, w->mu, beta_prev, sc) != 0) return -1;
+        w->tot_cg_its += (abip_int)(sc[ABIPGPU_SC_CG_ITS] + sc[ABIPGPU_SC_CG_ITS2]);
+        const double utut = sc[ABIPGPU_SC_BB_UTUT], utv = sc[ABIPGPU_SC_BB_UTV], uu = sc[ABIPGPU_SC_BB_UU],
+                     vv = sc[ABIPGPU_SC_BB_VV], uv = sc[ABIPGPU_SC_BB_UV];
+        const double norm_ut = std::sqrt(utut), norm_u = std::sqrt(uu), norm_v = std::sqrt(vv);
+        const double alpha_SD = vv / utv, alpha_MG = utv / utut, gamma_SD = vv / uv, gamma_MG = uv / uu;
+        const double alpha_ss = (2 * alpha_MG > alpha_SD) ? alpha_MG : alpha_SD - 0.5 * alpha_MG;
+        const double gamma_ss = (2 * gamma_MG > gamma_SD) ? gamma_MG : gamma_SD - 0.5 * gamma_MG;
+        const double alpha_cor = utv / (norm_v * norm_ut), gamma_cor = uv / (norm_v * norm_u);
+        if (alpha_cor > s.eps_cor && gamma_cor > s.eps_cor) beta = std::sqrt(alpha_ss * gamma_ss);
+        else if (alpha_cor > s.eps_cor && gamma_cor <= s.eps_cor) beta = alpha_ss;
+        else if (alpha_cor <= s.eps_cor && gamma_cor > s.eps_cor) beta = gamma_ss;
+        else beta = beta_prev;
+        const double diff = std::fabs(beta - beta_prev);
+        if (w->trace)
+            fprintf(w->trace, "bbround %ld carry %d beta_prev %.17g beta %.17g dots %.10e %.10e %.10e %.10e %.10e cg %d %d\n",
+                    (long)i, carry, beta_prev, beta, utut, utv, uu, vv, uv, (int)sc[ABIPGPU_SC_CG_ITS],
+                    (int)sc[ABIPGPU_SC_CG_ITS2]);
+        if (diff > 0 && diff <= s.eps_pen) {
+            beta = (beta + beta_prev) / 2;
+            break;
+        } else if (diff > s.eps_pen) {
+            beta_prev = beta;
+            carry = 1;  // u_prev = u; v_prev = [v_y; (mu/beta)/u_x]   (:230-242), applied by the next launch
+        } else {
+            carry = 2;  // u_prev = u; v_prev = v                      (:243-247)
+        }
+    }
+    w->beta = beta;
+    w->total_adapt_ms += now_ms() - t0;
+    return 0;
+}
+
+void print_header_line(const ABIP_GPU_WORK* w) {
+    static const char* cols[] = {" ipm iter ", " admm iter ", "     mu ", " pri res ", " dua res ", " rel gap ",
+                                 " pri obj ", " dua obj ", " kap/tau ", " time (s)"};
+    (void)w;
+    for (int i = 0; i < 150; ++i) printf("-");
+    printf("\n");
+    for (int i = 0; i < 10; ++i) printf("%s%s", cols[i], i < 9 ? "|" : "\n");
+    for (int i = 0; i < 150; ++i) printf("=");
+    printf("\n");
+}
+
+void print_summary(const ABIP_GPU_WORK* w, abip_int i, abip_int k, const Resid* r, double t0) {  // abip.c:1418-1463
+    printf("%*i|", 10, (int)i);
+    printf("%*i|", 11, (int)k);
+    printf("%*.2e|", 8, w->mu);
+    printf("%*.2e|%*.2e|%*.2e|", 9, r->res_pri, 9, r->res_dual, 9, r->rel_gap);
+    printf("%*.2e|%*.2e|", 9, safediv_pos(r->ct_x_by_tau, r->tau), 9, safediv_pos(r->bt_y_by_tau, r->tau));
+    printf("%*.2e|%*.2e\n", 9, safediv_pos(r->kap, r->tau), 9, (now_ms() - t0) / 1e3);
+    fflush(stdout);
+}
+
+// get_solution + get_info (src/abip.c:1308-1414), un_normalize_sol (src/normalize.c:133-158)
+int get_solution(ABIP_GPU_WORK* w, ABIPSolution* sol, ABIPInfo* info, Resid* r, abip_int ipm_iter, abip_int admm_iter) {
+    const abip_int m = w->m, n = w->n, l = m + n + 1;
+    calc_residuals(w, r, ipm_iter, admm_iter);
+    if (!sol->x) sol->x = (double*)malloc(sizeof(double) * n);
+    if (!sol->y) sol->y = (double*)malloc(sizeof(double) * m);
+    if (!sol->s) sol->s = (double*)malloc(sizeof(double) * n);
+    std::vector<double> uu(l), vv(l);
+    const int avg = (int)w->stgs.avg_criterion;
+    if (abipgpu_lp_get_vec(w->eng, avg ? ABIPGPU_VEC_UAVGC : ABIPGPU_VEC_U, uu.data(), l) != 0 ||
+        abipgpu_lp_get_vec(w->eng, avg ? ABIPGPU_VEC_VAVGC : ABIPGPU_VEC_V, vv.data(), l) != 0)
+        return -1;
+    std::copy(uu.begin(), uu.begin() + m, sol->y);
+    std::copy(uu.begin() + m, uu.begin() + m + n, sol->x);
+    std::copy(vv.begin() + m, vv.begin() + m + n, sol->s);
+    enum { SOLVED, INDET, INFEAS, UNBDD } kind;
+    const abip_int sv = info->status_val;
+    if (sv == ABIP_UNFINISHED) {
+        if (r->tau > kIndeterminateTol && r->tau > r->kap) kind = SOLVED;
+        else if (norm2(uu.data(), l) < kIndeterminateTol * std::sqrt((double)l)) kind = INDET;
+        else if (-r->bt_y_by_tau < r->ct_x_by_tau) kind = INFEAS;
+        else kind = UNBDD;
+    } else if (sv == ABIP_SOLVED || sv == ABIP_SOLVED_INACCURATE) kind = SOLVED;
+    else if (sv == ABIP_INFEASIBLE || sv == ABIP_INFEASIBLE_INACCURATE) kind = INFEAS;
+    else kind = UNBDD;
+    const bool inacc = (sv == 0);
+    auto scale_all = [](double* a, abip_int len, double f) { for (abip_int i = 0; i < len; ++i) a[i] *= f; };
+    if (kind == SOLVED) {
+        const double f = safediv_pos(1.0, r->tau);
+        scale_all(sol->x, n, f); scale_all(sol->y, m, f); scale_all(sol->s, n, f);
+        info->status_val = inacc ? ABIP_SOLVED_INACCURATE : ABIP_SOLVED;
+        snprintf(info->status, sizeof(info->status), "%s", inacc ? "Solved/Inaccurate" : "Solved");
+    } else if (kind == INDET) {
+        fill_nan(sol->x, n); fill_nan(sol->y, m); fill_nan(sol->s, n);
+        info->status_val = ABIP_INDETERMINATE;
+        snprintf(info->status, sizeof(info->status), "Indeterminate");
+    } else if (kind == INFEAS) {
+        scale_all(sol->y, m, 1 / r->bt_y_by_tau); scale_all(sol->s, n, 1 / r->bt_y_by_tau);
+        fill_nan(sol->x, n);
+        info->status_val = inacc ? ABIP_INFEASIBLE_INACCURATE : ABIP_INFEASIBLE;
+        snprintf(info->status, sizeof(info->status), "%s", inacc ? "Infeasible/Inaccurate" : "Infeasible");
+    } else {
+        scale_all(sol->x, n, -1 / r->ct_x_by_tau);
+        fill_nan(sol->y, m); fill_nan(sol->s, n);
+        info->status_val = inacc ? ABIP_UNBOUNDED_INACCURATE : ABIP_UNBOUNDED;
+        snprintf(info->status, sizeof(info->status), "%s", inacc ? "Unbounded/Inaccurate" : "Unbounded");
+    }
+    if (w->stgs.normalize) {
+        const double* D = w->scal.D; const double* E = w->scal.E;
+        for (abip_int i = 0; i < n; ++i) sol->x[i] /= (E[i] * w->sc_b);
+        for (abip_int i = 0; i < m; ++i) sol->y[i] /= (D[i] * w->sc_c);
+        for (abip_int i = 0; i < n; ++i) sol->s[i] *= E[i] / (w->sc_c * w->stgs.scale);
+    }
+    info->ipm_iter = ipm_iter + 1;
+    info->admm_iter = admm_iter + 1;
+    info->res_infeas = r->res_infeas;
+    info->res_unbdd = r->res_unbdd;
+    if (kind == SOLVED) {
+        info->rel_gap = r->rel_gap; info->res_pri = r->res_pri; info->res_dual = r->res_dual;
+        info->pobj = r->ct_x_by_tau / r->tau; info->dobj = r->bt_y_by_tau / r->tau;
+    } else if (kind == UNBDD) {
+        info->rel_gap = info->res_pri = info->res_dual = NAN;
+        info->pobj = info->dobj = -INFINITY;
+    } else if (kind == INFEAS) {
+        info->rel_gap = info->res_pri = info->res_dual = NAN;
+        info->pobj = info->dobj = INFINITY;
+    }
+    return 0;
+}
+
+void print_footer(ABIP_GPU_WORK* w, const ABIPInfo* info) {  // src/abip.c:1465-1596 (abridged)
+    for (int i = 0; i < 150; ++i) printf("-");
+    printf("\nStatus: %s\n", info->status);
+    printf("Timing: Solve time: %1.2es\n", info->solve_time / 1e3);
+    printf("\tLin-sys: avg # CG iterations: %2.2f\n", (double)w->tot_cg_its / (info->admm_iter + 1));
+    printf("\tBarzilai-Borwein spectral method: avg step time: %1.2es\n",
+           w->total_adapt_ms / (info->admm_iter + 1) / 1e3);
+    printf("Error metrics:\nprimal res = %.4e, dual res = %.4e, rel gap = %.4e\n", info->res_pri, info->res_dual,
+           info->rel_gap);
+    printf("c'x = %.4f, b'y = %.4f\n", info->pobj, info->dobj);
+    for (int i = 0; i < 150; ++i) printf("=");
+    printf("\n");
+}
+
+}  // namespace
+
+extern "C" {
+
+void abip_gpu_set_default_settings(ABIPData* d) {  // src/util.c:288-329, mexfile/abip_mex.c:320-341
+    ABIPSettings* s = d->stgs;
+    s->max_ipm_iters = 500; s->max_admm_iters = 1000000; s->eps = 1e-3; s->alpha = 1.8; s->cg_rate = 2.0;
+    s->normalize = 1; s->scale = 1.0; s->rho_y = 1e-3; s->sparsity_ratio = 0.01;
+    s->adaptive = 1; s->eps_cor = 0.2; s->eps_pen = 0.1; s->adaptive_lookback = 20;
+    s->dynamic_x = 0.8; s->dynamic_eta = 1.1;
+    s->restart_fre = 1000; s->restart_thresh = 100000;
+    s->origin_rescale = 0; s->pc_ruiz_rescale = 1; s->qp_rescale = 0; s->ruiz_iter = 10;
+    s->hybrid_mu = 1; s->dynamic_sigma = -1.0; s->hybrid_thresh = 1000; s->dynamic_sigma_second = 0.5;
+    s->half_update = 0; s->avg_criterion = 0;
+    s->verbose = 1; s->warm_start = 0;
+    s->max_time = 3600; s->pfeasopt = 0;
+}
+
+ABIPGpuWork* abip_gpu_init(const ABIPData* d, ABIPInfo* info) {  // ABIP(init) + init_work, abip.c:1739-1841, 2341-2389
+    if (!d || !info) {
+        printf("ERROR: Missing ABIPData or ABIPInfo input\n");
+        return nullptr;
+    }
+    if (validate(d) < 0) {
+        printf("ERROR: Validation returned failure\n");
+        return nullptr;
+    }
+    const double t0 = now_ms();
+    ABIPGpuWork* w = new ABIPGpuWork();
+    w->m = d->m;
+    w->n = d->n;
+    w->stgs = *d->stgs;
+    w->sp = d->sp;
+    if (d->stgs->verbose) {
+        char* meth = abip_get_lin_sys_method(d->A, d->stgs);
+        for (int i = 0; i < 150; ++i) printf("-");
+        printf("\n\tABIP-B200 - First-Order Interior-Point Solver, device-resident ADMM engine (sm_100a)\n");
+        for (int i = 0; i < 150; ++i) printf("-");
+        printf("\nLin-sys: %s\n", meth);
+        free(meth);
+        printf("eps = %.2e, alpha = %.2f, max_ipm_iters = %i, max_admm_iters = %i, normalize = %i\n"
+               "scale = %2.2f, adaptive = %i, adaptive_lookback = %i, rho_y = %.2e\n",
+               d->stgs->eps, d->stgs->alpha, (int)d->stgs->max_ipm_iters, (int)d->stgs->max_admm_iters,
+               (int)d->stgs->normalize, d->stgs->scale, (int)d->stgs->adaptive, (int)d->stgs->adaptive_lookback,
+               d->stgs->rho_y);
+        printf("Variables n = %i, constraints m = %i\n", (int)d->n, (int)d->m);
+    }
+    if (!abip_copy_A_matrix(&w->A, d->A)) {
+        printf("ERROR: copy A matrix failed\n");
+        delete w;
+        return nullptr;
+    }
+    if (w->stgs.normalize) {
+        abip_normalize_A(w->A, &w->stgs, &w->scal);
+        w->have_scal = true;
+    }
+    const char* dev = getenv("ABIP_GPU_DEVICE");
+    w->eng = abipgpu_lp_create(w->m, w->n, w->A->p, w->A->i, w->A->x, &w->stgs, dev ? atoi(dev) : 0);
+    if (!w->eng) {
+        printf("ERROR: init_lin_sys_work failure\n");
+        abip_gpu_finish(w);
+        return nullptr;
+    }
+    if (d->stgs->verbose) {
+        char buf[512];
+        abipgpu_lp_describe(w->eng, buf, sizeof(buf));
+        printf("Engine: %s\n", buf);
+    }
+    info->setup_time = now_ms() - t0;
+    if (d->stgs->verbose) printf("Setup time: %1.2es\n", info->setup_time / 1e3);
+    return w;
+}
+
+abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, ABIPInfo* info) {  // abip.c:2056-2297
+    if (!d || !sol || !info || !w || !d->b || !d->c) {
+        printf("ERROR: ABIP_NULL input\n");
+        return ABIP_FAILED;
+    }
+    const abip_int m = w->m, n = w->n;
+    ABIPSettings& s = w->stgs;
+    const double t0 = now_ms();
+    const double max_time = s.max_time;
+    start_interrupt_listener();
+    info->status_val = ABIP_UNFINISHED;
+    Resid r;
+    ABIPGpuStats* st = abipgpu_lp_stats(w->eng);
+    memset(st, 0, sizeof(*st));
+    w->tot_cg_its = 0;
+    w->total_adapt_ms = 0;
+
+    // ---- update_work (abip.c:1843-1927) ----
+    w->nm_b = norm2(d->b, m);
+    w->nm_c = norm2(d->c, n);
+    w->b.assign(d->b, d->b + m);
+    w->c.assign(d->c, d->c + n);
+    w->sc_b = w->sc_c = 1.0;
+    if (s.normalize) {  // normalize_b_c, src/normalize.c:11-40
+        for (abip_int i = 0; i < n; ++i) w->c[i] /= w->scal.E[i];
+        w->sc_c = w->scal.mean_norm_row_A / std::max(norm2(w->c.data(), n), kMinScale);
+        for (abip_int i = 0; i < m; ++i) w->b[i] /= w->scal.D[i];
+        w->sc_b = w->scal.mean_norm_col_A / std::max(norm2(w->b.data(), m), kMinScale);
+        for (abip_int i = 0; i < n; ++i) w->c[i] *= w->sc_c * s.scale;
+        for (abip_int i = 0; i < m; ++i) w->b[i] *= w->sc_b * s.scale;
+    }
+    const double spmin = std::min(w->sp, s.sparsity_ratio), spmax = std::max(w->sp, s.sparsity_ratio);
+    if (spmax > 0.4 || (spmin > 0.1 && spmin < 0.2)) { w->sigma = 0.3; w->gamma = 2.0; }
+    else if (spmin > 0.2) { w->sigma = 0.5; w->gamma = 3.0; }
+    else { w->sigma = 0.8; w->gamma = 3.0; }
+    w->final_check = 0;
+    w->double_check = 0;
+    w->mu = 1.0;
+    w->beta = 1.0;
+    if (s.warm_start) {
+        // The reference's warm_start_vars (abip.c:307-357) overwrites every non-NaN entry with sqrt(mu/beta)
+        // unless built with NOVALIDATE, i.e. it degenerates to the cold start.
+        printf("WARN: warm_start behaves as in the reference build: iterates restart from sqrt(mu/beta)\n");
+    }
+    if (abipgpu_lp_cold_start(w->eng, w->mu, w->beta) != 0 ||
+        abipgpu_lp_set_problem(w->eng, w->b.data(), w->c.data(), s.normalize ? w->scal.D : nullptr,
+                               s.normalize ? w->scal.E : nullptr) != 0)
+        return failure(m, n, sol, info, ABIP_FAILED, "error in update_work", "Failure");
+
+    if (s.verbose) print_header_line(w);
+
+    FILE* trace = nullptr;  // ABIP_GPU_TRACE=<file>: one line per ADMM iteration / BB search (debug + parity tests)
+    if (const char* tf = getenv("ABIP_GPU_TRACE")) trace = fopen(tf, "w");
+    w->trace = trace;
+    struct TraceCloser { FILE* f; ABIP_GPU_WORK* w; ~TraceCloser() { if (f) fclose(f); w->trace = nullptr; } } trace_closer{trace, w};
+
+    abip_int k = 0;
+    for (abip_int i = 0; i < s.max_ipm_iters; ++i) {  // outer loop
+        abip_int inner_stopper;
+        if (spmin > 0.5) inner_stopper = (abip_int)std::round(std::pow(w->mu, -0.35));
+        else if (spmin > 0.2) inner_stopper = (abip_int)std::round(std::pow(w->mu, -1));
+        else inner_stopper = s.max_admm_iters;
+        if (abipgpu_lp_outer_prologue(w->eng, (int)s.avg_criterion) != 0)
+            return failure(m, n, sol, info, ABIP_FAILED, "error in outer prologue", "Failure");
+
+        for (abip_int j = 0; j < inner_stopper; ++j) {  // inner loop: one kernel launch per iteration
+            if (abipgpu_lp_admm_iter(w->eng, j, k, w->mu, w->beta, w->sc) != 0)
+                return failure(m, n, sol, info, ABIP_FAILED, "error in project_lin_sys", "Failure");
+            w->tot_cg_its += (abip_int)w->sc[ABIPGPU_SC_CG_ITS];
+            if (g_interrupted) return failure(m, n, sol, info, ABIP_SIGINT, "Interrupted", "Interrupted");
+            k += 1;
+            // iterate_Q_norm_resd decision (abip.c:2040-2050)
+            const double q_cur = qnorm_value(w->sc + ABIPGPU_SC_S_PR);
+            const double q_avg = w->sc[ABIPGPU_SC_HAS_AVG] != 0 ? qnorm_value(w->sc + ABIPGPU_SC_AVG_BASE)
+                                                                 : std::sqrt((double)s.max_admm_iters) / 1.0;
+            double q;
+            if (q_avg < q_cur) { s.avg_criterion = 1; q = q_avg; }
+            else { s.avg_criterion = 0; q = q_cur; }
+            if (trace)
+                fprintf(trace, "it %ld %ld %ld %.17g %.17g %d %.17g %d\n", (long)i, (long)j, (long)k, w->mu, w->beta,
+                        (int)w->sc[ABIPGPU_SC_CG_ITS], q, (int)s.avg_criterion);
+            if (q < w->gamma * w->mu) {
+                // (half_update: the reference clamps negative v to 1e-6 here, abip.c:2175-2186; v >= 0 on the
+                //  (x,tau) tail by construction of the prox step, and v_y is free, so this is a no-op there)
+                break;
+            }
+            if (w->final_check) {
+                calc_residuals(w, &r, i, k);
+                info->status_val = has_converged(w, &r, i, k);
+                if (info->status_val != 0 || k + 1 >= s.max_admm_iters || i + 1 >= s.max_ipm_iters) {
+                    if (s.verbose && k > 0) print_summary(w, i, k, &r, t0);
+                    if (get_solution(w, sol, info, &r, i, k) != 0)
+                        return failure(m, n, sol, info, ABIP_FAILED, "error in get_solution", "Failure");
+                    info->solve_time = now_ms() - t0;
+                    if (s.verbose) print_footer(w, info);
+                    end_interrupt_listener();
+                    w->last_stats = *st;
+                    return info->status_val;
+                }
+            }
+        }
+        if ((now_ms() - t0) / 1e3 > max_time) {  // wall clock; the reference uses clock() CPU time (trap 9)
+            printf("Timelimit reached. \n");
+            s.max_admm_iters = (abip_int)(k * 1.05);
+        }
+        if (w->mu < s.eps) w->final_check = 1;
+        calc_residuals(w, &r, i, k);
+        if (s.verbose) print_summary(w, i, k, &r, t0);
+        info->status_val = has_converged(w, &r, i, k);
+        if (info->status_val != 0 || k + 1 >= s.max_admm_iters) {
+            if (get_solution(w, sol, info, &r, i, k) != 0)
+                return failure(m, n, sol, info, ABIP_FAILED, "error in get_solution", "Failure");
+            info->solve_time = now_ms() - t0;
+            if (s.verbose) print_footer(w, info);
+            end_interrupt_listener();
+            w->last_stats = *st;
+            return info->status_val;
+        }
+        if (update_mu(w, &r) != 0) return failure(m, n, sol, info, ABIP_FAILED, "error in mu update", "Failure");
+        const int avg = (int)s.avg_criterion;
+        if (abipgpu_lp_reinit(w->eng, 0, w->sigma, avg) != 0)
+            return failure(m, n, sol, info, ABIP_FAILED, "error in reinitialize_vars", "Failure");
+        if (s.adaptive) {
+            if (abipgpu_lp_reinit(w->eng, 1, w->sigma, avg) != 0)
+                return failure(m, n, sol, info, ABIP_FAILED, "error in reinitialize_vars", "Failure");
+            w->beta = 1;
+            if (adaptive_search(w, k) < 0) return failure(m, n, sol, info, ABIP_FAILED, "error in adaptive", "Failure");
+            if (trace) fprintf(trace, "bb %ld %.17g %.17g %.17g\n", (long)i, w->mu, w->sigma, w->beta);
+            if (abipgpu_lp_reinit(w->eng, 2, w->sigma, avg) != 0)
+                return failure(m, n, sol, info, ABIP_FAILED, "error in reinitialize_vars", "Failure");
+        }
+    }
+    end_interrupt_listener();
+    w->last_stats = *st;
+    return info->status_val;
+}
+
+void abip_gpu_finish(ABIPGpuWork* w) {  // abip.c:2301-2336
+    if (!w) return;
+    abipgpu_lp_destroy(w->eng);
+    abip_free_A_matrix(w->A);
+    free(w->scal.D);
+    free(w->scal.E);
+    delete w;
+}
+
+abip_int abip_gpu_main(const ABIPData* d, ABIPSolution* sol, ABIPInfo* info) {  // abip.c:2393-2422
+    abip_int status;
+    ABIPGpuWork* w = abip_gpu_init(d, info);
+    if (w) {
+        abip_gpu_solve(w, d, sol, info);
+        status = info->status_val;
+    } else {
+        status = failure(d ? d->m : -1, d ? d->n : -1, sol, info, ABIP_FAILED, "could not initialize work", "Failure");
+    }
+    abip_gpu_finish(w);
+    return status;
+}
+
+void abip_gpu_get_stats(const ABIPGpuWork* w, ABIPGpuStats* out) { *out = w->last_stats; }
+
+}  // extern "C"

@@ -1,0 +1,276 @@
+"""GPU parity tests (through the C ABI) of the ABIP-LP engine against the oracle (oracle/lp_oracle.py, a numpy
+restatement pinned to the compiled reference) and the golden fixtures produced by the reference itself.
+
+Tolerances: FP64 everywhere; kernels differ from the oracle only by summation order, so single steps agree to
+~1e-10 relative; whole solves follow north_star: same status, residuals <= eps, objective within 1e-6 relative,
+ADMM iteration count within 5%.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from abip_b200 import problems
+from abip_b200.api import LinSysPlugin, LpEngine, SC, lp_solve, abip
+from oracle import lp_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "lp_golden.json")
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / (np.max(np.abs(b)) + 1e-300))
+
+
+def make_work(p, **kw):
+    st = O.Settings(**kw)
+    return O.Work(p.csc(), p.b, p.c, st), st
+
+
+def make_engine(w, **kw):
+    A = w.A.tocsc()
+    A.sort_indices()
+    e = LpEngine(A, **kw)
+    e.set_problem(w.b, w.c, w.D, w.E)
+    return e
+
+
+PROBLEMS = {
+    "rand_200x700": lambda: problems.random_lp(200, 700, 4, seed=3),
+    "rand_1x9": lambda: problems.random_lp(1, 9, 1, seed=4),
+    "rand_37x1000_dense_rows": lambda: problems.random_lp(37, 1000, 20, seed=5),     # rows ~540 nnz -> long-row path
+    "mcf_small": lambda: problems.mcf_lp(4, 40, 200, 6, 300, seed=6),               # mixed short/long rows
+}
+
+
+@pytest.mark.parametrize("name", list(PROBLEMS))
+def test_spmv_and_adjoint(name):
+    p = PROBLEMS[name]()
+    A = p.csc()
+    e = LpEngine(A)
+    rng = np.random.default_rng(0)
+    x, y = rng.standard_normal(p.n), rng.standard_normal(p.m)
+    ax, aty = e.spmv(x), e.spmv(y, trans=True)
+    assert rel(ax, A @ x) < 1e-13
+    assert rel(aty, A.T @ y) < 1e-13
+    # adjoint identity between the two stored CSR copies, linearity
+    assert abs(np.dot(ax, y) - np.dot(x, aty)) <= 1e-11 * (np.linalg.norm(ax) * np.linalg.norm(y) + 1)
+    assert rel(e.spmv(2.5 * x), 2.5 * ax) < 1e-14
+    # determinism: bit-identical on repeat
+    assert np.array_equal(ax, e.spmv(x))
+    e.close()
+
+
+@pytest.mark.parametrize("name", list(PROBLEMS))
+def test_plugin_accum_and_solve(name):
+    """linsys plugin symbols with host pointers vs oracle LinSys (indirect.c:222-242, 393-434)."""
+    p = PROBLEMS[name]()
+    w, st = make_work(p)
+    A = w.A.tocsc(); A.sort_indices()
+    plug = LinSysPlugin(A)
+    rng = np.random.default_rng(1)
+    x, y0 = rng.standard_normal(p.n), rng.standard_normal(p.m)
+    assert rel(plug.accum_by_A(x, y0), y0 + A @ x) < 1e-13
+    x0 = rng.standard_normal(p.n)
+    assert rel(plug.accum_by_Atrans(y0, x0), x0 + A.T @ y0) < 1e-13
+    for it, warm in ((-1, None), (0, rng.standard_normal(p.m)), (7, rng.standard_normal(p.m)), (400, np.zeros(p.m))):
+        b = rng.standard_normal(p.m + p.n)
+        ref = b.copy()
+        its = w.p.solve(ref, warm, it)
+        got = plug.solve(b, warm, it)
+        # both stop on |r| < tol: compare through the KKT residual instead of elementwise when its differ
+        K_res = np.concatenate([st.rho_y * got[:p.m] + A @ got[p.m:], A.T @ got[:p.m] - got[p.m:]]) - b
+        tol = max(np.linalg.norm(b[:p.m]) * (1e-9 if it < 0 else 0.1 / (it + 1.0) ** 2), 1e-7)
+        assert np.linalg.norm(K_res[:p.m]) < 1.5 * tol + 1e-12
+        assert np.linalg.norm(K_res[p.m:]) < 1e-9 * (1 + np.linalg.norm(got))
+        assert rel(got, ref) < 50 * tol / (np.linalg.norm(ref) + 1e-300) + 1e-9
+    plug.close()
+
+
+@pytest.mark.parametrize("name", ["rand_200x700", "mcf_small", "rand_37x1000_dense_rows"])
+def test_set_problem_g(name):
+    p = PROBLEMS[name]()
+    w, _ = make_work(p)
+    e = make_engine(w)
+    assert rel(e.get("H"), w.h) < 1e-15
+    assert rel(e.get("G"), w.g) < 1e-7
+    assert abs(e.g_th() - w.g_th) < 1e-7 * abs(w.g_th)
+    assert rel(e.get("M"), w.p.M) < 1e-14
+    e.close()
+
+
+@pytest.mark.parametrize("half", [0, 1])
+@pytest.mark.parametrize("name", ["rand_200x700", "mcf_small"])
+def test_admm_iterations_stepwise(name, half):
+    """30 inner iterations, same (mu, beta): every vector and every reduced scalar against the oracle."""
+    p = PROBLEMS[name]()
+    w, st = make_work(p, half_update=half)
+    e = make_engine(w, half_update=half)
+    e.cold_start(1.0, 1.0)
+    e.outer_prologue(0)
+    mu, beta = 0.37, 1.3
+    w.mu, w.beta = mu, beta
+    for j in range(30):
+        w.u_prev[:] = w.u
+        its = O.project_lin_sys(w, j + 5)
+        if half:
+            O.half_update_dual_vars(w); O.project_barrier_dual(w)
+        else:
+            O.project_barrier(w); O.update_dual_vars(w)
+        O.restart_vars(w, j, j + 5)
+        O.compute_avg(w, j)
+        sc = e.admm_iter(j, j + 5, mu, beta)
+        assert abs(sc[SC["CG_ITS"]] - its) <= 1
+        for nm, ref in (("UT", w.u_t), ("U", w.u), ("V", w.v), ("UAVGC", w.u_avgcon), ("VAVGC", w.v_avgcon)):
+            assert rel(e.get(nm), ref) < 2e-6, (j, nm)   # CG stops at a tolerance, not at machine precision
+        q, nrm = O.q_norm_parts(w, w.u, w.v)
+        g = sc[SC["S_PR"]:SC["S_PR"] + 13]
+        q_gpu = g[0] + g[5] + (g[3] - g[8] - g[12]) ** 2
+        n_gpu = 1 + math.sqrt(g[4] + g[9] + g[11] ** 2 + g[10] + g[12] ** 2)
+        assert abs(math.sqrt(q_gpu) / n_gpu - math.sqrt(q) / nrm) < 1e-5 * (math.sqrt(q) / nrm) + 1e-9
+        assert bool(sc[SC["HAS_AVG"]]) == ((j + 1) % 10 == 0)
+        if (j + 1) % 10 == 0:
+            qa, na = O.q_norm_parts(w, w.u_avgcon, w.v_avgcon)
+            g = sc[SC["AVG_BASE"]:SC["AVG_BASE"] + 13]
+            qa_gpu = g[0] + g[5] + (g[3] - g[8] - g[12]) ** 2
+            assert abs(qa_gpu - qa) < 1e-5 * qa + 1e-12
+        # re-synchronise so that stopping-rule jitter of CG cannot accumulate
+        e.set("U", w.u); e.set("V", w.v); e.set("USUM", w.u_sumcon); e.set("VSUM", w.v_sumcon)
+    # weighted residual sums against calc_residuals
+    r = O.Residuals()
+    O.calc_residuals(w, r, 0, 30)
+    g = sc[SC["S_PR"]:SC["S_PR"] + 13]
+    nrm = st.scale * w.sc_c * w.sc_b
+    res_pri = math.sqrt(g[2]) / (w.sc_b * st.scale) / (1 + w.nm_b) / abs(g[11])
+    res_dual = math.sqrt(g[7]) / (w.sc_c * st.scale) / (1 + w.nm_c) / abs(g[11])
+    assert abs(res_pri - r.res_pri) < 1e-5 * r.res_pri
+    assert abs(res_dual - r.res_dual) < 1e-5 * r.res_dual
+    assert abs(g[3] / nrm - r.bt_y_by_tau) < 1e-6 * abs(r.bt_y_by_tau) + 1e-12
+    e.close()
+
+
+def test_restart_path():
+    """restart_vars firing (abip.c:601-628) with a tiny threshold/frequency."""
+    p = PROBLEMS["rand_200x700"]()
+    kw = dict(restart_thresh=3, restart_fre=4)
+    w, st = make_work(p, **kw)
+    e = make_engine(w, **kw)
+    e.cold_start(1.0, 1.0)
+    e.outer_prologue(0)
+    w.mu, w.beta = 0.5, 1.0
+    for j in range(13):
+        w.u_prev[:] = w.u
+        O.project_lin_sys(w, j)
+        O.project_barrier(w); O.update_dual_vars(w)
+        O.restart_vars(w, j, j)
+        O.compute_avg(w, j)
+        e.admm_iter(j, j, w.mu, w.beta)
+        for nm, ref in (("U", w.u), ("V", w.v), ("UAVGC", w.u_avgcon)):
+            assert rel(e.get(nm), ref) < 1e-5, (j, nm)
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["rand_200x700", "mcf_small"])
+def test_reinit_mu_stats_bb(name):
+    p = PROBLEMS[name]()
+    w, st = make_work(p)
+    e = make_engine(w)
+    e.cold_start(1.0, 1.0)
+    e.outer_prologue(0)
+    w.mu, w.beta = 0.8, 1.0
+    for j in range(6):
+        w.u_prev[:] = w.u
+        O.project_lin_sys(w, j); O.project_barrier(w); O.update_dual_vars(w); O.compute_avg(w, j)
+        e.admm_iter(j, j, w.mu, w.beta)
+    e.set("U", w.u); e.set("V", w.v)
+    sc = e.mu_stats(0)
+    xs = w.u[w.m:] * w.v[w.m:]
+    assert abs(sc[SC["MIN_XS"]] - xs.min()) < 1e-14 and abs(sc[SC["SUM_XS"]] - xs.sum()) < 1e-9 * xs.sum()
+    w.sigma = 0.64
+    for idx in (0, 1):
+        O.reinitialize_vars(w, idx); e.reinit(idx, w.sigma, 0)
+    assert rel(e.get("U"), w.u) < 1e-15 and rel(e.get("V"), w.v) < 1e-15
+    # Barzilai-Borwein rounds: the 5 inner products per round and the resulting beta sequence
+    tr = []
+    O.update_adapt_params(w, 6, trace=tr)
+    e.bb_begin()
+    beta_prev, carry, betas = 1.0, 0, []
+    for _ in range(len(tr)):
+        sc = e.bb_round(carry, 6, w.mu, beta_prev)
+        beta = O.bb_beta_from_scalars(st, sc[SC["BB_UTUT"]], sc[SC["BB_UTV"]], sc[SC["BB_UU"]], sc[SC["BB_VV"]],
+                                      sc[SC["BB_UV"]], beta_prev)
+        betas.append(beta)
+        d = abs(beta - beta_prev)
+        if 0 < d <= st.eps_pen:
+            break
+        elif d > st.eps_pen:
+            beta_prev, carry = beta, 1
+        else:
+            carry = 2
+    assert len(betas) == len(tr)
+    assert np.allclose(betas, tr, rtol=2e-3), (betas, tr)
+    e.close()
+
+
+def _check_solution(p, x, y, s, info, eps):
+    """size-independent properties: residuals of the returned point recomputed on the CPU from the ORIGINAL data"""
+    A = p.csc()
+    pres = np.linalg.norm(A @ x - p.b) / (1 + np.linalg.norm(p.b))
+    dres = np.linalg.norm(A.T @ y + s - p.c) / (1 + np.linalg.norm(p.c))
+    pobj, dobj = float(p.c @ x), float(p.b @ y)
+    gap = abs(pobj - dobj) / (1 + abs(pobj) + abs(dobj))
+    assert pres < 1.5 * eps and dres < 1.5 * eps and gap < 1.5 * eps, (pres, dres, gap)
+    assert x.min() > -1e-9 and s.min() > -1e-9
+    assert abs(pobj - info["pobj"]) < 1e-8 * (1 + abs(pobj))
+
+
+@pytest.mark.parametrize("name,eps", [("rand_200x700", 1e-4), ("mcf_small", 1e-4), ("rand_1x9", 1e-3),
+                                      ("rand_37x1000_dense_rows", 1e-4)])
+def test_full_solve_vs_oracle(name, eps):
+    p = PROBLEMS[name]()
+    o = O.solve(p.csc(), p.b, p.c, O.Settings(eps=eps))
+    x, y, s, info = lp_solve(p.csc(), p.b, p.c, dict(tol=eps, verbose=0))
+    assert info["status_val"] == o.status_val == 1
+    assert abs(info["admm_iter"] - o.admm_iter) <= max(2, 0.05 * o.admm_iter), (info["admm_iter"], o.admm_iter)
+    assert abs(info["pobj"] - o.pobj) <= 1e-6 * (1 + abs(o.pobj)) + 2 * eps * eps
+    assert max(info["pres"], info["dres"], info["gap"]) < eps
+    _check_solution(p, x, y, s, info, eps)
+
+
+def test_cfg1_against_reference_golden():
+    """BASELINE.json configs[0] against the numbers the compiled reference produced (tests/golden/make_golden.py)."""
+    gold = json.load(open(GOLD))["cfg1"]
+    p = problems.cfg1()
+    x, y, s, info = abip({"A": p.csc(), "b": p.b, "c": p.c}, {"l": p.n}, dict(tol=1e-4, verbose=0, pcg=1))
+    assert info["status"] == gold["status"]
+    assert abs(info["admm_iter"] - gold["admm_iter"]) <= 0.05 * gold["admm_iter"]
+    assert abs(info["pobj"] - gold["pobj"]) <= 1e-6 * abs(gold["pobj"]) + 1e-8
+    assert max(info["pres"], info["dres"], info["gap"]) < 1e-4
+    assert rel(x[:16], np.array(gold["x_head"])) < 1e-3
+    _check_solution(p, x, y, s, info, 1e-4)
+
+
+def test_infeasible_and_validation():
+    """error behaviour of the entry: m > n is rejected like the reference's validate (abip.c:1661-1665)."""
+    p = problems.random_lp(30, 20, 3, seed=9) if False else None
+    import scipy.sparse as sp
+    A = sp.random(8, 5, density=0.6, random_state=1, format="csc")
+    x, y, s, info = lp_solve(A, np.ones(8), np.ones(5), dict(verbose=0))
+    assert info["status_val"] == -4 and np.isnan(x).all()
+
+
+def test_dropin_reference_core_with_gpu_plugin():
+    """The UNMODIFIED reference solver core (abip.c, adaptive.c, ...) linked against our linsys plugin instead of
+    linsys/indirect.c + common.c (oracle/Makefile target libabip_gpuplug_ref.so): host-pointer drop-in."""
+    from oracle import ref_lp
+    if not ref_lp.available("gpuplug"):
+        pytest.skip("oracle/_ref/libabip_gpuplug_ref.so not built")
+    gold = json.load(open(GOLD))["rand_200x700"]
+    p = PROBLEMS["rand_200x700"]()
+    r = ref_lp.solve(p, which="gpuplug", eps=1e-4)
+    assert r["status"] == gold["status"]
+    assert abs(r["admm_iter"] - gold["admm_iter"]) <= max(2, 0.05 * gold["admm_iter"])
+    assert abs(r["pobj"] - gold["pobj"]) <= 1e-6 * abs(gold["pobj"]) + 1e-7
+    assert max(r["res_pri"], r["res_dual"], r["rel_gap"]) < 1e-4
