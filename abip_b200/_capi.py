@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libabip_gpu.so")
+LIB_PATH = os.environ.get("ABIP_GPU_LIB") or os.path.join(_HERE, "csrc", "libabip_gpu.so")  # env override: tuning builds
 
 c_int = C.c_long      # abip_int  (-DDLONG layout)
 c_float = C.c_double  # abip_float
@@ -59,7 +59,8 @@ class ABIPGpuStats(C.Structure):
     _fields_ = [("n_admm_launch", c_int), ("n_bb_launch", c_int), ("n_solves", c_int),
                 ("n_cg_iters", c_int), ("n_spmv_A", c_int), ("n_spmv_AT", c_int),
                 ("n_kernel_launches", c_int), ("admm_kernel_ms", c_float), ("bb_kernel_ms", c_float),
-                ("alg_bytes", c_float), ("h2d_bytes", c_float), ("d2h_bytes", c_float)]
+                ("alg_bytes", c_float), ("h2d_bytes", c_float), ("d2h_bytes", c_float),
+                ("alg_bytes_admm", c_float), ("alg_bytes_bb", c_float), ("solve_event_ms", c_float)]
 
 
 # every symbol include/abip_gpu.h declares (checked by tests/test_capi_symbols.py)

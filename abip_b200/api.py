@@ -124,6 +124,58 @@ def lp_solve(A, b, c, params: dict | None = None, want_stats: bool = False, **ra
     return out["x"], out["y"], out["s"], res
 
 
+class LpSolver:
+    """ABIP(init) / ABIP(solve) / ABIP(finish) life cycle (src/abip-lp/include/abip.h:116-124): A is scaled and
+    uploaded once, solve() may be called repeatedly with the data resident in HBM."""
+
+    def __init__(self, A, params: dict | None = None, **raw_settings):
+        self.L = _capi.lib()
+        self.p, self.st = _lp_settings(params, **raw_settings)
+        self.H = CscHolder(A)
+        self.info = _capi.ABIPInfo()
+        self._b = np.zeros(self.H.m)
+        self._c = np.zeros(self.H.n)
+        self.d = _capi.ABIPData(self.H.m, self.H.n, C.pointer(self.H.c), _fp(self._b), _fp(self._c),
+                                float(self.H.nnz) / (float(self.H.m) * float(self.H.n)), C.pointer(self.st))
+        self.w = self.L.abip_gpu_init(C.byref(self.d), C.byref(self.info))
+        if not self.w:
+            raise RuntimeError("abip_gpu_init failed")
+        self.setup_time_ms = self.info.setup_time
+        self._libc = C.CDLL(None)
+        self._libc.free.argtypes = [C.c_void_p]
+
+    def solve(self, b, c):
+        self._b[:] = b
+        self._c[:] = c
+        sol = _capi.ABIPSolution()
+        info = _capi.ABIPInfo()
+        self.L.abip_gpu_solve(self.w, C.byref(self.d), C.byref(sol), C.byref(info))
+        stats = _capi.ABIPGpuStats()
+        self.L.abip_gpu_get_stats(self.w, C.byref(stats))
+        out = {}
+        for name, ln in (("x", self.H.n), ("y", self.H.m), ("s", self.H.n)):
+            ptr = getattr(sol, name)
+            out[name] = np.ctypeslib.as_array(ptr, shape=(ln,)).copy() if ptr else np.full(ln, np.nan)
+            if ptr:
+                self._libc.free(C.cast(ptr, C.c_void_p))
+        res = dict(status=info.status.decode(), status_val=int(info.status_val), ipm_iter=int(info.ipm_iter),
+                   admm_iter=int(info.admm_iter), pres=info.res_pri, dres=info.res_dual, gap=info.rel_gap,
+                   pobj=info.pobj, dobj=info.dobj, solve_time_ms=info.solve_time,
+                   stats={f: getattr(stats, f) for f, _ in stats._fields_})
+        return out["x"], out["y"], out["s"], res
+
+    def close(self):
+        if self.w:
+            self.L.abip_gpu_finish(self.w)
+            self.w = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def abip(data: dict, K: dict, params: dict | None = None):
     """[x, y, s, info] = abip(data, K, params) -- scripts/matlab/abip.m:1-30.
 

@@ -15,53 +15,112 @@
 
 namespace cg = cooperative_groups;
 
+// Geometry chosen by measurement on B200 at cfg2 (profiles/r01_spmv_variants.md): one 1024-thread CTA per SM,
+// 256-nonzero chunks, single-stage cp.async ring (deeper rings cost L1 capacity, which the gathers need more).
 #ifndef ABIP_BLOCK
-#define ABIP_BLOCK 512
+#define ABIP_BLOCK 1024
 #endif
 #ifndef ABIP_MIN_BLOCKS_PER_SM
-#define ABIP_MIN_BLOCKS_PER_SM 2
+#define ABIP_MIN_BLOCKS_PER_SM 1
+#endif
+#ifndef ABIP_STAGES
+#define ABIP_STAGES 1
 #endif
 constexpr int kBlock = ABIP_BLOCK;
 constexpr int kWarps = kBlock / 32;
 constexpr int kMaxRed = 24;  // max scalars reduced between two grid barriers
 
 // ---------------------------------------------------------------------------------------------------------
-// Streaming loads for the matrix arrays: read-only path, do not allocate in L1 (keeps L1 for the gathered
-// vector), default L2 policy (A and A' together are ~L2-sized at cfg2, so we want them retained in L2).
+// Asynchronous global -> shared staging of the matrix arrays (cp.async 16 B per lane, SASS LDGSTS, L2-only
+// caching so the stream does not evict the gathered vector from L1).  No registers are tied up by the loads in
+// flight, so the persistent grid can run 32 warps per SM with a kStages-deep ring per warp.
+// (A TMA bulk-copy ring -- cp.async.bulk + mbarrier, three small 1-2 KB copies per chunk -- was measured slower
+//  on this access pattern: 40.6 us vs 24.5 us per A' pass at cfg2; see profiles/ and DESIGN.md.)
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double ld_stream(const double* p) {
-    double v;
-    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ int ld_stream(const int* p) {
-    int v;
-    asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int4 ld_stream4(const int* p) {  // 16-byte aligned
-    int4 v;
-    asm("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ double2 ld_stream2(const double* p) {  // 16-byte aligned
-    double2 v;
-    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// CSR matrix + the SpMV variant chosen from its row-length statistics (host: choose_spmv_plan()).
+// CSR matrix + the SpMV plan built on the host from its row-length statistics (lp_engine.cu: build_spmv_plan()).
+//   * every warp of the persistent grid owns a contiguous range of rows with (nearly) equal cost, cut into
+//     "chunks" of <= kChunk nonzeros and <= kChunk rows; descriptor = {first row, first nnz, #rows, #nnz};
+//   * a row longer than kChunk is cut into pieces of <= kChunk nonzeros, all owned by the same warp:
+//     #rows = 0 marks "row continues", #rows = -1 its last piece.
+// The device arrays are padded by 8 elements so that 16-byte aligned copy windows may over-read.
+#ifndef ABIP_CHUNK
+#define ABIP_CHUNK 256
+#endif
+constexpr int kChunk = ABIP_CHUNK;
+constexpr int kStages = ABIP_STAGES;
 struct Csr {
-    const int* ptr;        // [nrows+1]
-    const int* idx;        // [nnz] column indices
-    const double* val;     // [nnz]
+    const int* ptr;         // [nrows+1 (+8)]
+    const int* idx;         // [nnz (+8)] column indices
+    const double* val;      // [nnz (+8)]
     int nrows;
-    int lanes_log2;        // vector-per-row width L = 1<<lanes_log2 lanes (1..32) for rows <= long_thresh
-    int long_thresh;       // rows longer than this go to the warp-per-row 128-bit path
-    const int* long_rows;  // [n_long] their indices
-    int n_long;
+    const int* warp_chunk;  // [W+1] chunk range of each warp of the persistent grid
+    const int4* chunk;      // [nchunks] {row0, nnz0, nrows | 0 | -1, nnz}
+    int lanes_log2;         // lanes per row in the shared-memory row reduction (1 => reference summation order)
 };
+
+// Per-warp staging ring in shared memory.  Stage layout (bytes): [val window][idx window][row-ptr window].
+constexpr int kValWin = (kChunk + 2) * 8;                 // 16-byte aligned window may start 1 element early
+constexpr int kIdxWin = ((kChunk + 6 + 3) / 4) * 16;      // up to 3 elements early, rounded to 16 bytes
+constexpr int kPtrWin = ((kChunk + 1 + 6 + 3) / 4) * 16;  // kChunk + 1 row pointers
+constexpr int kStageBytes = ((kValWin + kIdxWin + kPtrWin + 127) / 128) * 128;
+constexpr int kWarpSmemBytes = kStages * kStageBytes;
+struct WarpSmem {
+    unsigned char* base;  // generic pointer to this warp's slice
+    unsigned base_s;      // same, shared-space address
+    int head;             // stage of the oldest chunk in flight
+    int inflight;         // chunks (= cp.async groups) in flight, <= kStages
+    const int4* cur;      // matrix (identified by its chunk array) whose chunks are in flight
+    int next_c;           // next chunk of `cur` to issue
+
+    // all lanes: 16-byte cp.async copies of the chunk's three windows into stage (head + inflight) % kStages
+    __device__ __forceinline__ void issue(const Csr& A, int c) {
+        const int lane = threadIdx.x & 31;
+        const int stage = (head + inflight) % kStages;
+        const int4 d = __ldg(A.chunk + c);
+        const int s = d.y, n = d.w, row0 = d.x;
+        const int nr = d.z > 0 ? d.z : 0;
+        const unsigned st_s = base_s + stage * kStageBytes;
+        const int sv = s & ~1, nv = (((s + n + 1) & ~1) - sv) >> 1;            // 16-byte units of values
+        const int si = s & ~3, ni = (((s + n + 3) & ~3) - si) >> 2;            // ... of column indices
+        const int sr = row0 & ~3, np = nr > 0 ? ((((row0 + nr + 4) & ~3) - sr) >> 2) : 0;  // ... of row pointers
+        for (int i = lane; i < nv; i += 32) cp_async16(st_s + 16 * i, A.val + sv + 2 * i);
+        for (int i = lane; i < ni; i += 32) cp_async16(st_s + kValWin + 16 * i, A.idx + si + 4 * i);
+        for (int i = lane; i < np; i += 32) cp_async16(st_s + kValWin + kIdxWin + 16 * i, A.ptr + sr + 4 * i);
+        cp_async_commit();
+        ++inflight;
+    }
+    // wait until the oldest group has landed (groups complete in order) and make it visible to the whole warp
+    __device__ __forceinline__ void wait_head() {
+        if (inflight <= 1) cp_async_wait<0>();
+        else if (inflight == 2) cp_async_wait<1>();
+        else if (inflight == 3) cp_async_wait<2>();
+        else cp_async_wait<3>();
+        __syncwarp();
+    }
+    __device__ __forceinline__ void release_head() {
+        __syncwarp();  // every lane is done reading the stage before it is overwritten
+        head = (head + 1) % kStages;
+        --inflight;
+    }
+    __device__ __forceinline__ void drain() {
+        cp_async_wait<0>();
+        __syncwarp();
+        head = 0;
+        inflight = 0;
+        cur = nullptr;
+    }
+};
+static_assert(kStages >= 1 && kStages <= 4, "cp.async ring depth");
 
 // Deterministic grid-wide reduction helper (see file header).  partials is double-buffered so that a fast
 // block starting reduction t+1 can never overwrite values a slow block is still reading for reduction t.
@@ -70,6 +129,7 @@ struct Reducer {
     double* sm;        // shared scratch [kMaxRed * kWarps]
     int G;
     int parity;
+    WarpSmem ws;       // this warp's SpMV staging slice
 
     // adds this block's contribution for slots [slot0, slot0+K); several calls (distinct slots) may precede one
     // grid barrier + finish()
@@ -115,61 +175,177 @@ struct Reducer {
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// K1: CSR SpMV phase.  fn(row, dot) is called once per row by one lane with dot = A[row,:] * x.
-//   * rows of length <= long_thresh: vector-per-row, L = 2^lanes_log2 lanes per row, warp-coalesced scalar
-//     loads (adjacent sub-warps read adjacent rows, so a warp streams one contiguous span of val/idx);
-//   * longer rows: warp-per-row with 128-bit loads (int4 indices, 2 x double2 values) after an alignment peel.
+// K1: CSR SpMV phase ("CSR-stream" per warp, cp.async-staged).  fn(row, dot) is called once per row by one lane with
+// dot = A[row,:] * x.  For each chunk the warp
+//   1. waits for the chunk's cp.async copies (issued kStages chunks ahead, also across grid barriers and across
+//      the switch to the matrix of the next phase, `next`), gathers x and multiplies in shared memory;
+//   2. reduces the rows of the chunk out of shared memory, L lanes per row (L = 1 reproduces the serial
+//      summation order of the reference, linsys/common.c:624-634);
+//   long rows arrive as consecutive pieces and are accumulated per lane, then tree-reduced.
 // x may have been written earlier in the same kernel (ordinary coherent loads; L1 is invalidated by the grid
 // barrier's fence).  Replaces _accum_by_Atrans (reference linsys/common.c:598-639) for both A and A'.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void spmv_prefetch(const Csr& A, WarpSmem& ws) {
+    const int gwarp = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const int c0 = __ldg(A.warp_chunk + gwarp), c1 = __ldg(A.warp_chunk + gwarp + 1);
+    if (ws.cur == A.chunk) return;
+    ws.drain();
+    ws.cur = A.chunk;
+    ws.next_c = c0;
+    while (ws.inflight < kStages && ws.next_c < c1) ws.issue(A, ws.next_c++);
+}
+
 template <class RowFn>
-__device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, RowFn fn) {
+__device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, WarpSmem& ws, const Csr* next, RowFn fn) {
+    constexpr int U = kChunk / 32;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * kWarps + (threadIdx.x >> 5);
     const int lg = A.lanes_log2;
     const int L = 1 << lg;
-    const int lane = threadIdx.x & 31;
     const int sl = lane & (L - 1);
     const int sub = lane >> lg;
     const int rpw = 32 >> lg;
-    const int gwarp = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    const int nwarps = gridDim.x * kWarps;
-    const int nrows = A.nrows;
-    for (int base = gwarp * rpw; base < nrows; base += nwarps * rpw) {
-        const int row = base + sub;
-        int s = 0, e = 0;
-        bool ok = row < nrows;
-        if (ok) {
-            s = __ldg(A.ptr + row);
-            e = __ldg(A.ptr + row + 1);
-            if (e - s > A.long_thresh) { ok = false; e = s; }
-        }
-        double acc = 0.0;
-        for (int k = s + sl; k < e; k += L) acc = fma(ld_stream(A.val + k), x[ld_stream(A.idx + k)], acc);
-        for (int off = L >> 1; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off, L);
-        if (ok && sl == 0) fn(row, acc);
+    const int c0 = __ldg(A.warp_chunk + gwarp), c1 = __ldg(A.warp_chunk + gwarp + 1);
+    int nx_c = 0, nx_c1 = 0;
+    if (next) {
+        nx_c = __ldg(next->warp_chunk + gwarp);
+        nx_c1 = __ldg(next->warp_chunk + gwarp + 1);
     }
-    for (int li = gwarp; li < A.n_long; li += nwarps) {
-        const int row = __ldg(A.long_rows + li);
-        const int s = __ldg(A.ptr + row), e = __ldg(A.ptr + row + 1);
-        double acc = 0.0;
-        int s4 = (s + 3) & ~3;
-        if (s4 > e) s4 = e;
-        if (s + lane < s4) acc = ld_stream(A.val + s + lane) * x[ld_stream(A.idx + s + lane)];
-        const int e4 = s4 + ((e - s4) & ~3);
-        for (int k = s4 + lane * 4; k < e4; k += 128) {
-            const int4 c = ld_stream4(A.idx + k);
-            const double2 v0 = ld_stream2(A.val + k), v1 = ld_stream2(A.val + k + 2);
-            const double x0 = x[c.x], x1 = x[c.y], x2 = x[c.z], x3 = x[c.w];
-            acc = fma(v0.x, x0, acc);
-            acc = fma(v0.y, x1, acc);
-            acc = fma(v1.x, x2, acc);
-            acc = fma(v1.y, x3, acc);
+    if (ws.cur != A.chunk) {  // nothing useful in flight
+        ws.drain();
+        ws.cur = A.chunk;
+        ws.next_c = c0;
+    }
+    double acc_long = 0.0;
+    for (int c = c0; c < c1; ++c) {
+        // keep the ring full: first our own chunks, then the first chunks of the next phase's matrix
+        while (ws.inflight < kStages) {
+            if (ws.next_c < c1) ws.issue(A, ws.next_c++);
+            else if (next && nx_c < nx_c1) ws.issue(*next, nx_c++);
+            else break;
         }
-        if (e4 + lane < e) acc = fma(ld_stream(A.val + e4 + lane), x[ld_stream(A.idx + e4 + lane)], acc);
+        ws.wait_head();
+        unsigned char* st = ws.base + ws.head * kStageBytes;
+        const int4 d = __ldg(A.chunk + c);  // loaded by issue() a moment ago: L1 hit
+        const int row0 = d.x, s = d.y, nr = d.z, n = d.w;
+        double* vs = reinterpret_cast<double*>(st) + (s & 1);
+        const int* is = reinterpret_cast<const int*>(st + kValWin) + (s & 3);
+        if (nr <= 0) {  // piece of a long row
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (lane == 0) fn(row, acc);
+            for (int u = 0; u < U; ++u) {
+                const int k = lane + 32 * u;
+                if (k < n) acc_long = fma(vs[k], x[is[k]], acc_long);
+            }
+            if (nr < 0) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) acc_long += __shfl_xor_sync(0xffffffffu, acc_long, off);
+                if (lane == 0) fn(row0, acc_long);
+                acc_long = 0.0;
+            }
+            ws.release_head();
+            continue;
+        }
+        // 1. gather x (U independent loads per lane) and multiply in place
+        double xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = lane + 32 * u;
+            xv[u] = (k < n) ? x[is[k]] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = lane + 32 * u;
+            if (k < n) vs[k] *= xv[u];
+        }
+        __syncwarp();
+        // 2. row sums out of shared memory, L lanes per row; each sum is parked in the row's first product slot
+        const int* rp = reinterpret_cast<const int*>(st + kValWin + kIdxWin) + (row0 & 3);
+        if (L == 1) {
+            for (int rr = lane; rr < nr; rr += 32) {
+                const int a = rp[rr] - s, b = rp[rr + 1] - s;
+                double acc = 0.0;
+                for (int k = a; k < b; ++k) acc += vs[k];
+                fn(row0 + rr, acc);
+            }
+        } else {
+            for (int base = 0; base < nr; base += rpw) {
+                const int rr = base + sub;
+                const bool ok = rr < nr;
+                double acc = 0.0;
+                int a = 0, b = 0;
+                if (ok) {
+                    a = rp[rr] - s;
+                    b = rp[rr + 1] - s;
+                    for (int k = a + sl; k < b; k += L) acc += vs[k];
+                }
+                for (int off = L >> 1; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off, L);
+                __syncwarp();  // every lane of the group has read its products before slot a is overwritten
+                if (ok && sl == 0 && a < b) vs[a] = acc;
+            }
+            __syncwarp();
+            // 3. epilogue for all rows of the chunk at once (one lane per row: the epilogue's own global loads
+            //    overlap instead of serialising per pass)
+            for (int rr = lane; rr < nr; rr += 32) {
+                const int a = rp[rr] - s, b = rp[rr + 1] - s;
+                fn(row0 + rr, a < b ? vs[a] : 0.0);
+            }
+        }
+        ws.release_head();
+    }
+    if (next) {  // whatever is in flight now belongs to `next`
+        if (ws.inflight == 0 && nx_c < nx_c1) {
+            while (ws.inflight < kStages && nx_c < nx_c1) ws.issue(*next, nx_c++);
+        }
+        ws.cur = next->chunk;
+        ws.next_c = nx_c;
+    } else {
+        ws.cur = nullptr;
     }
 }
+
+// Dynamic shared memory of every persistent kernel: [reducer scratch][per-warp staging rings]
+constexpr size_t kRedBytes = sizeof(double) * kMaxRed * kWarps;
+constexpr size_t kSmemBytes = ((kRedBytes + 127) / 128) * 128 + (size_t)kWarps * kWarpSmemBytes;
+__device__ __forceinline__ Reducer make_reducer(unsigned char* smem_raw, double* partials) {
+    const int w = threadIdx.x >> 5;
+    Reducer R;
+    R.partials = partials;
+    R.sm = reinterpret_cast<double*>(smem_raw);
+    R.G = (int)gridDim.x;
+    R.parity = 0;
+    unsigned char* wbase = smem_raw + ((kRedBytes + 127) / 128) * 128 + (size_t)w * kWarpSmemBytes;
+    R.ws.base = wbase;
+    R.ws.base_s = smem_u32(wbase);
+    R.ws.head = 0;
+    R.ws.inflight = 0;
+    R.ws.cur = nullptr;
+    R.ws.next_c = 0;
+    return R;
+}
+
+// Optional per-phase timing (build with -DABIP_PHASE_TIMING): block 0 / thread 0 accumulates globaltimer deltas per
+// phase id into LpCtx::phase_ns (it leaves a barrier only when every block has arrived, so its deltas are the
+// critical path of each phase including the barrier).
+#ifdef ABIP_PHASE_TIMING
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define PHASE_MARK(c, last, id)                                    \
+    do {                                                           \
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (c).phase_ns) { \
+            const unsigned long long _t = gtimer();                \
+            (c).phase_ns[(id)] += (double)(_t - (last));           \
+            (c).phase_ns[16 + (id)] += 1.0;                        \
+            (last) = _t;                                           \
+        }                                                          \
+    } while (0)
+#define PHASE_START(last) unsigned long long last = gtimer()
+#else
+#define PHASE_MARK(c, last, id) do { } while (0)
+#define PHASE_START(last) do { } while (0)
+#endif
 
 // Constant problem data + PCG workspace (kernel parameter, passed by value).
 struct LpCtx {
@@ -187,6 +363,7 @@ struct LpCtx {
     double *p, *r, *Gp, *tmp;  // PCG: direction, residual, G p [m]; A'p scratch [n]
     double* partials;
     double* sc;  // scalar block [ABIPGPU_SC_COUNT]
+    double* phase_ns;  // [32] debug phase timing or nullptr
 };
 
 struct SolveOut {
@@ -210,24 +387,26 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
     const int m = c.m;
     double* by = b;
     double* bx = b + m;
+    PHASE_START(tl);
     // S1: by += A bx, accumulating |by|^2 of the *incoming* by for the tolerance (indirect.c:406-409, trap 2);
     //     independent of that, tmp = A' s for the warm-start residual.
     double a1[1] = {0.0};
-    spmv_rows(c.A, bx, [&](int row, double a) {
+    spmv_rows(c.A, bx, R.ws, &c.AT, [&](int row, double a) {
         const double o = by[row];
         a1[0] = fma(o, o, a1[0]);
         by[row] = o + a;
     });
-    if (s) spmv_rows(c.AT, s, [&](int row, double a) { c.tmp[row] = a; });
+    if (s) spmv_rows(c.AT, s, R.ws, &c.A, [&](int row, double a) { c.tmp[row] = a; });
     R.block_store<1>(a1);
     grid.sync();
     R.finish<1>(a1);
+    PHASE_MARK(c, tl, 2);
     double tol = sqrt(a1[0]) * (iter < 0 ? 1e-9 : 0.1 / pow((double)iter + 1.0, c.cg_rate));
     tol = fmax(fmax(tol, 1e-7), 1e-9);
     // S2: r = by - (rho s + A tmp), x = s (stored in by), z = M r, p = z   (indirect.c:343-365)
     double a2[2] = {0.0, 0.0};
     if (s) {
-        spmv_rows(c.A, c.tmp, [&](int row, double a) {
+        spmv_rows(c.A, c.tmp, R.ws, &c.AT, [&](int row, double a) {
             const double si = s[row];
             const double ri = by[row] - fma(c.rho_y, si, a);
             const double zi = __ldg(c.M + row) * ri;
@@ -251,17 +430,19 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
     R.block_store<2>(a2);
     grid.sync();
     R.finish<2>(a2);
+    PHASE_MARK(c, tl, 3);
     double rn = sqrt(a2[0]);
     double ipzr = a2[1];
     int its = 0;
     if (!(rn < fmin(tol, 1e-18))) {
         for (int it = 0; it < m; ++it) {
             // L1: tmp = A' p
-            spmv_rows(c.AT, c.p, [&](int row, double a) { c.tmp[row] = a; });
+            spmv_rows(c.AT, c.p, R.ws, &c.A, [&](int row, double a) { c.tmp[row] = a; });
             grid.sync();
+            PHASE_MARK(c, tl, 4);
             // L2: Gp = A tmp + rho p ; p.Gp
             double d1[1] = {0.0};
-            spmv_rows(c.A, c.tmp, [&](int row, double a) {
+            spmv_rows(c.A, c.tmp, R.ws, &c.AT, [&](int row, double a) {
                 const double pi = c.p[row];
                 const double gp = fma(c.rho_y, pi, a);
                 c.Gp[row] = gp;
@@ -270,6 +451,7 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
             R.block_store<1>(d1);
             grid.sync();
             R.finish<1>(d1);
+            PHASE_MARK(c, tl, 5);
             const double alpha = ipzr / d1[0];
             // L3: x += alpha p ; r -= alpha Gp ; |r|^2 ; (M r).r
             double d2[2] = {0.0, 0.0};
@@ -284,6 +466,7 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
             R.block_store<2>(d2);
             grid.sync();
             R.finish<2>(d2);
+            PHASE_MARK(c, tl, 6);
             its = it + 1;
             rn = sqrt(d2[0]);
             if (rn < tol) break;
@@ -292,11 +475,12 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
             // L4: p = beta p + M r
             GRID_STRIDE(i, m) c.p[i] = fma(beta, c.p[i], __ldg(c.M + i) * c.r[i]);
             grid.sync();
+            PHASE_MARK(c, tl, 7);
         }
     }
     // S4: bx = -bx + A' by   (indirect.c:419-420)
     double a3[1] = {0.0};
-    spmv_rows(c.AT, by, [&](int row, double a) {
+    spmv_rows(c.AT, by, R.ws, &c.A, [&](int row, double a) {
         const double nv = a - bx[row];
         bx[row] = nv;
         if (EPI) a3[0] = fma(nv, __ldg(c.h + m + row), a3[0]);
@@ -305,6 +489,7 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
         GRID_STRIDE(i, m) a3[0] = fma(by[i], __ldg(c.h + i), a3[0]);
         R.block_store<1>(a3);
     }
+    PHASE_MARK(c, tl, 8);
     out.its = its;
     out.tol = tol;
     out.res = rn;
@@ -319,6 +504,7 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
 __device__ __forceinline__ void dev_build_rhs(const LpCtx& c, Reducer& R, cg::grid_group& grid, const double* u,
                                               const double* v, double* ut, double* u_prev_out) {
     const int m = c.m, lm1 = c.m + c.n;
+    spmv_prefetch(c.A, R.ws);  // the solve that follows starts with A; its first chunks stream in meanwhile
     const double tt = u[lm1] + v[lm1];
     double a[1] = {0.0};
     GRID_STRIDE(i, lm1) {

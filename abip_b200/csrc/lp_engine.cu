@@ -25,14 +25,14 @@ struct IterArgs {
 // Q-norm / residual sums for one (u, v) pair: src/abip.c:1964-1992 (unweighted) and :385-456 (D/E weighted).
 // Writes 11 partial sums into reducer slots [slot0, slot0+11).
 __device__ __forceinline__ void dev_qnorm_sums(const LpCtx& c, Reducer& R, const double* u, const double* v,
-                                               int half, int slot0) {
+                                               int half, int slot0, bool more) {
     const int m = c.m, n = c.n;
     const double tau = u[m + n];
     const double* y = u;
     const double* x = u + m;
     const double* s = v + m;
     double a[5] = {0, 0, 0, 0, 0};  // S_PR, W_AX, W_PR, BTY, UU_Y
-    spmv_rows(c.A, x, [&](int row, double ax) {
+    spmv_rows(c.A, x, R.ws, &c.AT, [&](int row, double ax) {
         const double bi = __ldg(c.b + row);
         const double pr = fma(-bi, tau, ax);
         double d2 = 1.0;
@@ -46,7 +46,7 @@ __device__ __forceinline__ void dev_qnorm_sums(const LpCtx& c, Reducer& R, const
     });
     R.block_store<5>(a, slot0);
     double d[6] = {0, 0, 0, 0, 0, 0};  // S_DR, W_ATYS, W_DR, CTX, UU_X, VV
-    spmv_rows(c.AT, y, [&](int row, double aty) {
+    spmv_rows(c.AT, y, R.ws, more ? &c.A : nullptr, [&](int row, double aty) {
         const double cj = __ldg(c.c + row);
         const double sj = s[row];
         const double xj = x[row];
@@ -77,16 +77,19 @@ __device__ __forceinline__ void write_qnorm_sc(double* sc, int base, const doubl
 // One full inner ADMM iteration (src/abip.c:2133-2173).
 __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_admm_iter(LpCtx c, IterArgs a) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double sm[kMaxRed * kWarps];
-    Reducer R{c.partials, sm, (int)gridDim.x, 0};
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Reducer R = make_reducer(smem_raw, c.partials);
     const int m = c.m, lm1 = c.m + c.n, l = lm1 + 1;
 
+    PHASE_START(tk);
     dev_build_rhs(c, R, grid, a.u, a.v, a.ut, a.u_prev);
+    PHASE_MARK(c, tk, 0);
     SolveOut so;
     dev_solve_lin_sys<true>(c, R, grid, a.ut, a.u, a.k, so);
     grid.sync();
     double hd[1];
     R.finish<1>(hd);
+    PHASE_START(tk2);
     const double lam = a.mu / a.beta;
     const double al = c.alpha;
     const double dom = (double)(a.j + 1);
@@ -142,11 +145,13 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_admm_iter(Lp
         }
     }
     grid.sync();
+    PHASE_MARK(c, tk2, 9);
 
     // iterate_Q_norm_resd sums (abip.c:1951-2051); every 10th inner iteration also on the running average
     const int has_avg = ((a.j + 1) % 10 == 0) ? 1 : 0;
-    dev_qnorm_sums(c, R, a.u, a.v, a.half_update, 0);
-    if (has_avg) dev_qnorm_sums(c, R, a.u_avgc, a.v_avgc, a.half_update, 11);
+    dev_qnorm_sums(c, R, a.u, a.v, a.half_update, 0, has_avg != 0);
+    if (has_avg) dev_qnorm_sums(c, R, a.u_avgc, a.v_avgc, a.half_update, 11, false);
+    R.ws.drain();
     grid.sync();
     double t[22];
     if (has_avg) R.finish<22>(t);
@@ -155,6 +160,7 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_admm_iter(Lp
         R.finish<11>(t11);
         for (int q = 0; q < 11; ++q) t[q] = t11[q];
     }
+    PHASE_MARK(c, tk2, 10);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         c.sc[ABIPGPU_SC_CG_ITS] = (double)so.its;
         c.sc[ABIPGPU_SC_CG_TOL] = so.tol;
@@ -230,8 +236,8 @@ __device__ __forceinline__ void dev_bb_half(const LpCtx& c, Reducer& R, cg::grid
 // One lookback round of the Barzilai-Borwein search (src/adaptive.c:89-178).
 __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_bb_round(LpCtx c, BBArgs a) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double sm[kMaxRed * kWarps];
-    Reducer R{c.partials, sm, (int)gridDim.x, 0};
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Reducer R = make_reducer(smem_raw, c.partials);
     const int m = c.m, l = c.m + c.n + 1;
     const double lam = a.mu / a.beta_prev;
     if (a.carry) {  // state hand-over of the previous round (adaptive.c:230-247)
@@ -245,6 +251,7 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_bb_round(LpC
     int its1, its2;
     dev_bb_half(c, R, grid, a.u_prev, a.v_prev, a.ut, a.u, a.v, a.k, lam, nullptr, false, its1);
     dev_bb_half(c, R, grid, a.u, a.v, a.ut_next, a.u_next, a.v_next, a.k, lam, a.v_prev, true, its2);
+    R.ws.drain();  // no bulk copy may be outstanding when the CTA exits
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         c.sc[ABIPGPU_SC_CG_ITS] = (double)its1;
         c.sc[ABIPGPU_SC_CG_ITS2] = (double)its2;
@@ -255,10 +262,12 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_bb_round(LpC
 __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
     k_solve_vec(LpCtx c, double* b, const double* s, long iter, int post_g) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double sm[kMaxRed * kWarps];
-    Reducer R{c.partials, sm, (int)gridDim.x, 0};
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Reducer R = make_reducer(smem_raw, c.partials);
     SolveOut so;
+    spmv_prefetch(c.A, R.ws);
     dev_solve_lin_sys<false>(c, R, grid, b, s, iter, so);
+    R.ws.drain();
     if (post_g) {
         grid.sync();
         const int m = c.m, lm1 = c.m + c.n;
@@ -283,7 +292,10 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
 // y (+)= A x as a stand-alone launch (plugin accum_by_A / accum_by_Atrans and tests)
 __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
     k_spmv(Csr A, const double* x, double* y, int accumulate) {
-    spmv_rows(A, x, [&](int row, double a) { y[row] = accumulate ? y[row] + a : a; });
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Reducer R = make_reducer(smem_raw, nullptr);
+    spmv_rows(A, x, R.ws, nullptr, [&](int row, double a) { y[row] = accumulate ? y[row] + a : a; });
+    R.ws.drain();
 }
 
 // min / sum of u_i v_i over the (x, tau) tail: update_barrier_dynamic, src/abip.c:957-960
@@ -379,27 +391,66 @@ static int env_int(const char* name, int dflt) {
     return (s && *s) ? atoi(s) : dflt;
 }
 
-// Row-length statistics -> SpMV plan (lanes per row for the vector kernel, threshold + list for the
-// warp-per-row 128-bit kernel).
-static void choose_spmv_plan(const std::vector<int>& ptr, int nrows, const char* env_lanes, int* lanes_log2,
-                             int* long_thresh, std::vector<int>* long_rows, double* mean_short) {
-    const int thresh = env_int("ABIP_GPU_LONG_ROW", 192);
-    long_rows->clear();
-    double sum_short = 0;
-    long n_short = 0;
-    for (int r = 0; r < nrows; ++r) {
-        const int len = ptr[r + 1] - ptr[r];
-        if (len > thresh) long_rows->push_back(r);
-        else { sum_short += len; ++n_short; }
+// Row-length statistics -> SpMV plan for a persistent grid of W warps (see Csr in lp_device.cuh):
+// contiguous, cost-balanced row ranges per warp (cost = nnz + 2 per row), cut into chunks of <= kChunk nonzeros and
+// <= kChunk rows; rows longer than kChunk become single-row chunks (warp-per-row 128-bit path).  The lane count of
+// the shared-memory row reduction follows the mean row length: L ~ 16 * mean / kChunk rounded up to a power of two
+// (L = 1 for short rows, e.g. A' of an LP with ~5 nnz/column; L = 2 at ~25 nnz/row).
+struct SpmvPlan {
+    std::vector<int> warp_chunk;
+    std::vector<int4> chunk;
+    int lanes_log2 = 0;
+    double mean = 0;
+    int n_long = 0;
+    int max_len = 0;
+};
+
+static void build_spmv_plan(const std::vector<int>& ptr, int nrows, int W, const char* env_lanes, SpmvPlan* P) {
+    const long nnz = ptr[nrows];
+    const double total_cost = (double)nnz + 2.0 * nrows;
+    P->warp_chunk.assign(W + 1, 0);
+    P->chunk.clear();
+    P->n_long = 0;
+    P->max_len = 0;
+    int r = 0;
+    for (int w = 0; w < W; ++w) {
+        const double target = total_cost * (double)(w + 1) / (double)W;
+        const int ra = r;
+        while (r < nrows && ((double)ptr[r + 1] + 2.0 * (r + 1) <= target || w == W - 1)) ++r;
+        int q = ra;
+        while (q < r) {  // cut [ra, r) into chunks
+            int q1 = q;
+            int n = 0;
+            while (q1 < r && (q1 - q) < kChunk) {
+                const int len = ptr[q1 + 1] - ptr[q1];
+                if (n + len > kChunk) break;
+                n += len;
+                ++q1;
+            }
+            if (q1 == q) {  // a row longer than kChunk: consecutive pieces, all in this warp
+                const int len = ptr[q + 1] - ptr[q];
+                for (int off = 0; off < len; off += kChunk) {
+                    const int cnt = std::min(kChunk, len - off);
+                    P->chunk.push_back(make_int4(q, ptr[q] + off, (off + cnt == len) ? -1 : 0, cnt));
+                }
+                P->n_long++;
+                q = q + 1;
+                continue;
+            }
+            P->chunk.push_back(make_int4(q, ptr[q], q1 - q, n));
+            q = q1;
+        }
+        P->warp_chunk[w + 1] = (int)P->chunk.size();
     }
-    const double mean = n_short ? sum_short / n_short : 1.0;
+    for (int i = 0; i < nrows; ++i) P->max_len = std::max(P->max_len, ptr[i + 1] - ptr[i]);
+    P->mean = nrows ? (double)nnz / nrows : 1.0;
+    // measured at cfg2: fewer lanes per row win (each extra pass over the chunk costs more than a longer serial sum)
+    const double want = 16.0 * P->mean / kChunk;
     int lg = 0;
-    while (lg < 5 && (1 << lg) < mean) ++lg;  // smallest power of two >= mean short-row length
+    while (lg < 5 && (1 << lg) < want) ++lg;
     const int forced = env_int(env_lanes, -1);
     if (forced >= 0 && forced <= 5) lg = forced;
-    *lanes_log2 = lg;
-    *long_thresh = thresh;
-    *mean_short = mean;
+    P->lanes_log2 = lg;
 }
 
 struct ABIPGPU_LP {
@@ -407,11 +458,12 @@ struct ABIPGPU_LP {
     int m = 0, n = 0, l = 0;
     long nnz = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_solve0 = nullptr, ev_solve1 = nullptr;
     int num_sms = 0;
-    int grid_admm = 0, grid_bb = 0, grid_solve = 0, grid_spmv = 0, grid_mu = 0;
+    int grid = 0, grid_mu = 0;  // every SpMV-bearing kernel uses the same persistent grid (the plan is per warp)
     // matrix
-    int *A_ptr = nullptr, *A_idx = nullptr, *AT_ptr = nullptr, *AT_idx = nullptr, *A_long = nullptr, *AT_long = nullptr;
+    int *A_ptr = nullptr, *A_idx = nullptr, *AT_ptr = nullptr, *AT_idx = nullptr, *A_wc = nullptr, *AT_wc = nullptr;
+    int4 *A_chunk = nullptr, *AT_chunk = nullptr;
     double *A_val = nullptr, *AT_val = nullptr;
     // everything else lives in one slab
     double* slab = nullptr;
@@ -420,6 +472,7 @@ struct ABIPGPU_LP {
     long vec_len[32] = {0};
     double *dM = nullptr, *dD = nullptr, *dE = nullptr, *db = nullptr, *dc = nullptr;
     double *p = nullptr, *r = nullptr, *Gp = nullptr, *tmp = nullptr, *partials = nullptr, *dsc = nullptr;
+    double* dphase = nullptr;
     double *xin = nullptr, *yout = nullptr;  // staging for host-pointer plugin calls [l] each
     double* hsc = nullptr;                   // pinned host scalar block
     bool have_scaling = false;
@@ -431,9 +484,10 @@ struct ABIPGPU_LP {
     bool restart_synced = false;
 };
 
-static int coop_grid(const void* kernel, int num_sms, int* out) {
+static int coop_grid(const void* kernel, int num_sms, size_t smem, int* out) {
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, 0));
+    if (smem > 0) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, smem));
     if (occ < 1) {
         fprintf(stderr, "[abip_gpu] kernel cannot be made resident\n");
         return -1;
@@ -444,9 +498,9 @@ static int coop_grid(const void* kernel, int num_sms, int* out) {
 }
 
 template <class... Args>
-static int launch_coop(abipgpu_lp* e, const void* kernel, int grid, Args... args) {
+static int launch_coop(abipgpu_lp* e, const void* kernel, int grid, size_t smem, Args... args) {
     void* argv[] = {(void*)&args...};
-    CK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kBlock), argv, 0, e->stream));
+    CK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kBlock), argv, smem, e->stream));
     e->stats.n_kernel_launches++;
     return 0;
 }
@@ -461,8 +515,9 @@ static int read_sc(abipgpu_lp* e, abip_float* sc) {
 
 template <class T>
 static int upload(T** dst, const std::vector<T>& src, abipgpu_lp* e) {
-    const size_t bytes = std::max<size_t>(src.size(), 4) * sizeof(T);
+    const size_t bytes = (src.size() + 8) * sizeof(T);  // +8: 16-byte aligned TMA windows may over-read
     CK(cudaMalloc((void**)dst, bytes));
+    CK(cudaMemsetAsync(*dst, 0, bytes, e->stream));
     if (!src.empty()) CK(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, e->stream));
     e->stats.h2d_bytes += src.size() * sizeof(T);
     return 0;
@@ -494,6 +549,8 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
+    CK(cudaEventCreate(&e->ev_solve0));
+    CK(cudaEventCreate(&e->ev_solve1));
 
     // CSR(A') is the caller's CSC; CSR(A) by counting sort (the reference's transpose(), indirect.c:81-139)
     std::vector<int> at_ptr(n + 1), at_idx(nnz), a_ptr(m + 1, 0), a_idx(nnz);
@@ -518,31 +575,35 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
             }
     }
     std::vector<double> at_val(Ax, Ax + nnz);
-    std::vector<int> a_long, at_long;
-    int lgA, lgAT, thrA, thrAT;
-    double meanA, meanAT;
-    choose_spmv_plan(a_ptr, (int)m, "ABIP_GPU_LANES_A", &lgA, &thrA, &a_long, &meanA);
-    choose_spmv_plan(at_ptr, (int)n, "ABIP_GPU_LANES_AT", &lgAT, &thrAT, &at_long, &meanAT);
+    // persistent grid: a multiple of the SM count, common to all SpMV-bearing kernels
+    {
+        int g1, g2, g3, g4;
+        if (coop_grid((const void*)k_admm_iter, e->num_sms, kSmemBytes, &g1) ||
+            coop_grid((const void*)k_bb_round, e->num_sms, kSmemBytes, &g2) ||
+            coop_grid((const void*)k_solve_vec, e->num_sms, kSmemBytes, &g3) ||
+            coop_grid((const void*)k_mu_stats, e->num_sms, 0, &g4))
+            return -1;
+        CK(cudaFuncSetAttribute((const void*)k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        e->grid = std::min(g1, std::min(g2, g3));
+        e->grid_mu = g4;
+    }
+    const int W = e->grid * kWarps;
+    SpmvPlan planA, planAT;
+    build_spmv_plan(a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA);
+    build_spmv_plan(at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT);
 
     if (upload(&e->A_ptr, a_ptr, e) || upload(&e->A_idx, a_idx, e) || upload(&e->A_val, a_val, e) ||
         upload(&e->AT_ptr, at_ptr, e) || upload(&e->AT_idx, at_idx, e) || upload(&e->AT_val, at_val, e) ||
-        upload(&e->A_long, a_long, e) || upload(&e->AT_long, at_long, e))
+        upload(&e->A_wc, planA.warp_chunk, e) || upload(&e->AT_wc, planAT.warp_chunk, e) ||
+        upload(&e->A_chunk, planA.chunk, e) || upload(&e->AT_chunk, planAT.chunk, e))
         return -1;
-
-    // grids (persistent: a multiple of the SM count)
-    if (coop_grid((const void*)k_admm_iter, e->num_sms, &e->grid_admm) ||
-        coop_grid((const void*)k_bb_round, e->num_sms, &e->grid_bb) ||
-        coop_grid((const void*)k_solve_vec, e->num_sms, &e->grid_solve) ||
-        coop_grid((const void*)k_mu_stats, e->num_sms, &e->grid_mu))
-        return -1;
-    e->grid_spmv = e->num_sms * 4;
-    const int gmax = std::max(std::max(e->grid_admm, e->grid_bb), std::max(e->grid_solve, e->grid_mu));
+    const int gmax = std::max(e->grid, e->grid_mu);
 
     // one slab for all FP64 vectors, each 256-byte aligned
     const size_t L = ((size_t)e->l + 31) & ~(size_t)31;
     const size_t Mm = ((size_t)m + 31) & ~(size_t)31, Nn = ((size_t)n + 31) & ~(size_t)31;
     const size_t n_l_vecs = 21 + 2;  // ids 0..20 + xin + yout
-    const size_t total = n_l_vecs * L + 7 * Mm + 3 * Nn + (size_t)2 * kMaxRed * gmax + 64 + ABIPGPU_SC_COUNT;
+    const size_t total = n_l_vecs * L + 7 * Mm + 3 * Nn + (size_t)2 * kMaxRed * gmax + 64 + ABIPGPU_SC_COUNT + 32;
     CK(cudaMalloc((void**)&e->slab, total * sizeof(double)));
     CK(cudaMemsetAsync(e->slab, 0, total * sizeof(double), e->stream));
     e->slab_doubles = total;
@@ -569,14 +630,14 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     e->tmp = take(Nn);
     e->partials = take((size_t)2 * kMaxRed * gmax + 64);
     e->dsc = take(ABIPGPU_SC_COUNT);
+    e->dphase = take(32);
     CK(cudaMallocHost((void**)&e->hsc, sizeof(double) * ABIPGPU_SC_COUNT));
 
     LpCtx& c = e->ctx;
     c.m = (int)m;
     c.n = (int)n;
-    c.A = Csr{e->A_ptr, e->A_idx, e->A_val, (int)m, lgA, a_long.empty() ? 0x7fffffff : thrA, e->A_long, (int)a_long.size()};
-    c.AT = Csr{e->AT_ptr, e->AT_idx, e->AT_val, (int)n, lgAT, at_long.empty() ? 0x7fffffff : thrAT, e->AT_long,
-               (int)at_long.size()};
+    c.A = Csr{e->A_ptr, e->A_idx, e->A_val, (int)m, e->A_wc, e->A_chunk, planA.lanes_log2};
+    c.AT = Csr{e->AT_ptr, e->AT_idx, e->AT_val, (int)n, e->AT_wc, e->AT_chunk, planAT.lanes_log2};
     c.M = e->dM;
     c.D = nullptr;
     c.E = nullptr;
@@ -594,6 +655,11 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     c.tmp = e->tmp;
     c.partials = e->partials;
     c.sc = e->dsc;
+#ifdef ABIP_PHASE_TIMING
+    c.phase_ns = e->dphase;
+#else
+    c.phase_ns = nullptr;
+#endif
 
     k_precond<<<(unsigned)((m + 255) / 256), 256, 0, e->stream>>>(c.A, e->dM);
     CK(cudaGetLastError());
@@ -603,22 +669,25 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     e->B_A = (double)nnz * (V + I) + (m + 1.0) * I + n * V + m * V;
     e->B_AT = (double)nnz * (V + I) + (n + 1.0) * I + m * V + n * V;
     snprintf(e->desc, sizeof(e->desc),
-             "device %d (%s, %d SMs) block=%d grid(admm/bb/solve)=%d/%d/%d | CSR(A): %d rows mean-short %.1f -> %d "
-             "lanes/row, %zu long rows (>%d, warp-per-row 128-bit) | CSR(A'): %d rows mean-short %.1f -> %d lanes/row, "
-             "%zu long rows | nnz=%ld",
-             device, prop.name, e->num_sms, kBlock, e->grid_admm, e->grid_bb, e->grid_solve, (int)m, meanA, 1 << lgA,
-             a_long.size(), thrA, (int)n, meanAT, 1 << lgAT, at_long.size(), nnz);
+             "device %d (%s, %d SMs) persistent grid %d x %d threads, %zu B smem/block | CSR(A): %d rows, mean %.1f max %d "
+             "nnz/row, %zu chunks (%d long rows), %d lane(s)/row | CSR(A'): %d rows, mean %.1f max %d, %zu chunks (%d long), "
+             "%d lane(s)/row | nnz=%ld",
+             device, prop.name, e->num_sms, e->grid, kBlock, (size_t)kSmemBytes, (int)m, planA.mean, planA.max_len,
+             planA.chunk.size(), planA.n_long, 1 << planA.lanes_log2, (int)n, planAT.mean, planAT.max_len,
+             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz);
     return 0;
 }
 
-static void account_solve(abipgpu_lp* e, double cg_its, bool warm) {
+static double account_solve(abipgpu_lp* e, double cg_its, bool warm) {
     // (c + 2 [+1 warm-start residual]) operator halves; 12 m-vector passes per CG iteration
     e->stats.n_solves++;
     e->stats.n_cg_iters += (abip_int)cg_its;
     const double nA = cg_its + 1 + (warm ? 1 : 0), nAT = cg_its + 1 + (warm ? 1 : 0);
     e->stats.n_spmv_A += (abip_int)nA;
     e->stats.n_spmv_AT += (abip_int)nAT;
-    e->stats.alg_bytes += nA * e->B_A + nAT * e->B_AT + 12.0 * cg_its * e->m * 8.0;
+    const double bytes = nA * e->B_A + nAT * e->B_AT + 12.0 * cg_its * e->m * 8.0;
+    e->stats.alg_bytes += bytes;
+    return bytes;
 }
 
 extern "C" {
@@ -640,11 +709,13 @@ void abipgpu_lp_destroy(abipgpu_lp* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->A_ptr); cudaFree(e->A_idx); cudaFree(e->A_val);
     cudaFree(e->AT_ptr); cudaFree(e->AT_idx); cudaFree(e->AT_val);
-    cudaFree(e->A_long); cudaFree(e->AT_long);
+    cudaFree(e->A_wc); cudaFree(e->AT_wc); cudaFree(e->A_chunk); cudaFree(e->AT_chunk);
     cudaFree(e->slab);
     if (e->hsc) cudaFreeHost(e->hsc);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev_solve0) cudaEventDestroy(e->ev_solve0);
+    if (e->ev_solve1) cudaEventDestroy(e->ev_solve1);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -666,7 +737,7 @@ int abipgpu_lp_set_problem(abipgpu_lp* e, const abip_float* b, const abip_float*
     e->ctx.E = e->have_scaling ? e->dE : nullptr;
     k_build_h<<<(m + n + 255) / 256, 256, 0, e->stream>>>(e->db, e->dc, e->vec[ABIPGPU_VEC_H], e->vec[ABIPGPU_VEC_G], m, n);
     CK(cudaGetLastError());
-    if (launch_coop(e, (const void*)k_solve_vec, e->grid_solve, e->ctx, e->vec[ABIPGPU_VEC_G], (const double*)nullptr,
+    if (launch_coop(e, (const void*)k_solve_vec, e->grid, kSmemBytes, e->ctx, e->vec[ABIPGPU_VEC_G], (const double*)nullptr,
                     (long)-1, 1))
         return -1;
     if (read_sc(e, nullptr)) return -1;
@@ -735,19 +806,21 @@ int abipgpu_lp_admm_iter(abipgpu_lp* e, abip_int j, abip_int k, abip_float mu, a
     // both give the same residue class, so the firing rule reduces to (j+1) % fre == 0
     if (a.restart_active && e->stgs.restart_fre > 0 && (j + 1) % e->stgs.restart_fre == 0) a.restart_fire = 1;
     CK(cudaEventRecord(e->ev0, e->stream));
-    if (launch_coop(e, (const void*)k_admm_iter, e->grid_admm, e->ctx, a)) return -1;
+    if (launch_coop(e, (const void*)k_admm_iter, e->grid, kSmemBytes, e->ctx, a)) return -1;
     CK(cudaEventRecord(e->ev1, e->stream));
     if (read_sc(e, sc)) return -1;
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     e->stats.admm_kernel_ms += ms;
     e->stats.n_admm_launch++;
-    account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], true);
+    double bytes = account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], true);
     const double nq = e->hsc[ABIPGPU_SC_HAS_AVG] != 0 ? 2.0 : 1.0;
     e->stats.n_spmv_A += (abip_int)nq;
     e->stats.n_spmv_AT += (abip_int)nq;
     // rhs (6 l) + prox/dual/avg (9 l) + Q-norm extra vectors (b, c, D, E, s, y: ~3 l) per pair
-    e->stats.alg_bytes += nq * (e->B_A + e->B_AT) + (15.0 + 3.0 * nq) * e->l * 8.0;
+    const double extra = nq * (e->B_A + e->B_AT) + (15.0 + 3.0 * nq) * e->l * 8.0;
+    e->stats.alg_bytes += extra;
+    e->stats.alg_bytes_admm += bytes + extra;
     return 0;
 }
 
@@ -755,7 +828,7 @@ int abipgpu_lp_mu_stats(abipgpu_lp* e, int avg_criterion, abip_float* sc) {
     CK(cudaSetDevice(e->device));
     const double* u = e->vec[avg_criterion ? ABIPGPU_VEC_UAVGC : ABIPGPU_VEC_U];
     const double* v = e->vec[avg_criterion ? ABIPGPU_VEC_VAVGC : ABIPGPU_VEC_V];
-    if (launch_coop(e, (const void*)k_mu_stats, e->grid_mu, u, v, e->m, e->l, e->partials, e->dsc)) return -1;
+    if (launch_coop(e, (const void*)k_mu_stats, e->grid_mu, (size_t)0, u, v, e->m, e->l, e->partials, e->dsc)) return -1;
     return read_sc(e, sc);
 }
 
@@ -793,16 +866,18 @@ int abipgpu_lp_bb_round(abipgpu_lp* e, int carry, abip_int k, abip_float mu, abi
     a.mu = mu;
     a.beta_prev = beta_prev;
     CK(cudaEventRecord(e->ev0, e->stream));
-    if (launch_coop(e, (const void*)k_bb_round, e->grid_bb, e->ctx, a)) return -1;
+    if (launch_coop(e, (const void*)k_bb_round, e->grid, kSmemBytes, e->ctx, a)) return -1;
     CK(cudaEventRecord(e->ev1, e->stream));
     if (read_sc(e, sc)) return -1;
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     e->stats.bb_kernel_ms += ms;
     e->stats.n_bb_launch++;
-    account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], true);
-    account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS2], true);
-    e->stats.alg_bytes += (2 * 6.0 + 2 * 6.0 + (carry ? 4.0 : 0.0)) * e->l * 8.0;
+    double bytes = account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], true);
+    bytes += account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS2], true);
+    const double extra = (2 * 6.0 + 2 * 6.0 + (carry ? 4.0 : 0.0)) * e->l * 8.0;
+    e->stats.alg_bytes += extra;
+    e->stats.alg_bytes_bb += bytes + extra;
     return 0;
 }
 
@@ -810,7 +885,7 @@ int abipgpu_lp_solve_vec(abipgpu_lp* e, int rhs_id, int warm_id, abip_int iter, 
     CK(cudaSetDevice(e->device));
     if (rhs_id < 0 || rhs_id > 20 || warm_id > 20) return -1;
     const double* s = warm_id >= 0 ? e->vec[warm_id] : nullptr;
-    if (launch_coop(e, (const void*)k_solve_vec, e->grid_solve, e->ctx, e->vec[rhs_id], s, (long)iter, 0)) return -1;
+    if (launch_coop(e, (const void*)k_solve_vec, e->grid, kSmemBytes, e->ctx, e->vec[rhs_id], s, (long)iter, 0)) return -1;
     if (read_sc(e, sc)) return -1;
     account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], s != nullptr);
     return 0;
@@ -850,7 +925,7 @@ int abipgpu_lp_spmv_host(abipgpu_lp* e, int trans, const double* x, double* y, i
     const int nin = trans ? e->m : e->n, nout = trans ? e->n : e->m;
     CK(cudaMemcpyAsync(e->xin, x, sizeof(double) * nin, cudaMemcpyHostToDevice, e->stream));
     if (accumulate) CK(cudaMemcpyAsync(e->yout, y, sizeof(double) * nout, cudaMemcpyHostToDevice, e->stream));
-    k_spmv<<<e->grid_spmv, kBlock, 0, e->stream>>>(trans ? e->ctx.AT : e->ctx.A, e->xin, e->yout, accumulate);
+    k_spmv<<<e->grid, kBlock, kSmemBytes, e->stream>>>(trans ? e->ctx.AT : e->ctx.A, e->xin, e->yout, accumulate);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(y, e->yout, sizeof(double) * nout, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -867,7 +942,7 @@ int abipgpu_lp_solve_host(abipgpu_lp* e, double* b, const double* s, long iter, 
     const int mn = e->m + e->n;
     CK(cudaMemcpyAsync(e->xin, b, sizeof(double) * mn, cudaMemcpyHostToDevice, e->stream));
     if (s) CK(cudaMemcpyAsync(e->yout, s, sizeof(double) * e->m, cudaMemcpyHostToDevice, e->stream));
-    if (launch_coop(e, (const void*)k_solve_vec, e->grid_solve, e->ctx, e->xin, (const double*)(s ? e->yout : nullptr),
+    if (launch_coop(e, (const void*)k_solve_vec, e->grid, kSmemBytes, e->ctx, e->xin, (const double*)(s ? e->yout : nullptr),
                     iter, 0))
         return -1;
     CK(cudaMemcpyAsync(b, e->xin, sizeof(double) * mn, cudaMemcpyDeviceToHost, e->stream));
@@ -880,6 +955,26 @@ int abipgpu_lp_solve_host(abipgpu_lp* e, double* b, const double* s, long iter, 
 }
 
 ABIPGpuStats* abipgpu_lp_stats(abipgpu_lp* e) { return &e->stats; }
+extern "C" int abipgpu_lp_phase_times(abipgpu_lp* e, double* out32, int reset) {  // debug builds (-DABIP_PHASE_TIMING)
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(out32, e->dphase, sizeof(double) * 32, cudaMemcpyDeviceToHost, e->stream));
+    if (reset) CK(cudaMemsetAsync(e->dphase, 0, sizeof(double) * 32, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+int abipgpu_lp_solve_timer(abipgpu_lp* e, int stop) {  // CUDA events on the engine stream around a whole solve
+    CK(cudaSetDevice(e->device));
+    if (!stop) {
+        CK(cudaEventRecord(e->ev_solve0, e->stream));
+    } else {
+        CK(cudaEventRecord(e->ev_solve1, e->stream));
+        CK(cudaEventSynchronize(e->ev_solve1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e->ev_solve0, e->ev_solve1));
+        e->stats.solve_event_ms = ms;
+    }
+    return 0;
+}
 int abipgpu_lp_dims(const abipgpu_lp* e, int* m, int* n) { *m = e->m; *n = e->n; return 0; }
 int abipgpu_lp_sync(abipgpu_lp* e) {
     CK(cudaSetDevice(e->device));

@@ -11,3 +11,4 @@ int abipgpu_lp_solve_host(abipgpu_lp* e, double* b, const double* s, long iter, 
 ABIPGpuStats* abipgpu_lp_stats(abipgpu_lp* e);
 int abipgpu_lp_dims(const abipgpu_lp* e, int* m, int* n);
 int abipgpu_lp_sync(abipgpu_lp* e);
+int abipgpu_lp_solve_timer(abipgpu_lp* e, int stop);

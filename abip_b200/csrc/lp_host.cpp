@@ -283,6 +283,7 @@ struct ABIP_GPU_WORK {  // device-resident replacement of struct ABIP_WORK (incl
     bool have_scal = false;
     ABIPSettings stgs;  // private copy: the reference mutates the caller's struct (avg_criterion, dynamic_sigma,
                         // max_admm_iters; SURVEY.md parity trap 5) -- we mutate this copy instead
+    ABIPSettings stgs0; // as passed to init; every solve starts from it, so repeated solves are independent
     double sp = 0;
     abipgpu_lp* eng = nullptr;
     std::vector<double> b, c;  // scaled
@@ -659,6 +660,7 @@ ABIPGpuWork* abip_gpu_init(const ABIPData* d, ABIPInfo* info) {  // ABIP(init) +
     w->m = d->m;
     w->n = d->n;
     w->stgs = *d->stgs;
+    w->stgs0 = *d->stgs;
     w->sp = d->sp;
     if (d->stgs->verbose) {
         char* meth = abip_get_lin_sys_method(d->A, d->stgs);
@@ -706,6 +708,7 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
         return ABIP_FAILED;
     }
     const abip_int m = w->m, n = w->n;
+    w->stgs = w->stgs0;
     ABIPSettings& s = w->stgs;
     const double t0 = now_ms();
     const double max_time = s.max_time;
@@ -714,6 +717,7 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
     Resid r;
     ABIPGpuStats* st = abipgpu_lp_stats(w->eng);
     memset(st, 0, sizeof(*st));
+    abipgpu_lp_solve_timer(w->eng, 0);
     w->tot_cg_its = 0;
     w->total_adapt_ms = 0;
 
@@ -796,6 +800,7 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
                     info->solve_time = now_ms() - t0;
                     if (s.verbose) print_footer(w, info);
                     end_interrupt_listener();
+                    abipgpu_lp_solve_timer(w->eng, 1);
                     w->last_stats = *st;
                     return info->status_val;
                 }
@@ -815,6 +820,7 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
             info->solve_time = now_ms() - t0;
             if (s.verbose) print_footer(w, info);
             end_interrupt_listener();
+            abipgpu_lp_solve_timer(w->eng, 1);
             w->last_stats = *st;
             return info->status_val;
         }
@@ -832,7 +838,13 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
                 return failure(m, n, sol, info, ABIP_FAILED, "error in reinitialize_vars", "Failure");
         }
     }
+    // max_ipm_iters exhausted.  The reference returns here without filling sol/info (abip.c:2296); we report the
+    // last iterate instead (status Solved/Inaccurate or the certificate get_solution selects).
+    if (get_solution(w, sol, info, &r, s.max_ipm_iters - 1, k) != 0)
+        return failure(m, n, sol, info, ABIP_FAILED, "error in get_solution", "Failure");
+    info->solve_time = now_ms() - t0;
     end_interrupt_listener();
+    abipgpu_lp_solve_timer(w->eng, 1);
     w->last_stats = *st;
     return info->status_val;
 }

@@ -184,6 +184,9 @@ typedef struct ABIP_GPU_STATS {
     abip_float alg_bytes;      /* algorithmic bytes moved by all launches (formula in DESIGN.md) */
     abip_float h2d_bytes;
     abip_float d2h_bytes;
+    abip_float alg_bytes_admm; /* share of alg_bytes inside ADMM-iteration launches */
+    abip_float alg_bytes_bb;   /* share inside BB-round launches */
+    abip_float solve_event_ms; /* CUDA-event time (engine stream) around the whole abip_gpu_solve */
 } ABIPGpuStats;
 void abip_gpu_get_stats(const ABIPGpuWork *w, ABIPGpuStats *out);
 
