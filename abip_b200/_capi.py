@@ -72,7 +72,7 @@ DECLARED_SYMBOLS = [
     "abip_gpu_get_stats",
     "abipgpu_lp_create", "abipgpu_lp_destroy", "abipgpu_lp_set_problem", "abipgpu_lp_cold_start",
     "abipgpu_lp_outer_prologue", "abipgpu_lp_admm_iter", "abipgpu_lp_mu_stats", "abipgpu_lp_reinit",
-    "abipgpu_lp_bb_begin", "abipgpu_lp_bb_round", "abipgpu_lp_solve_vec", "abipgpu_lp_get_vec",
+    "abipgpu_lp_clamp_v", "abipgpu_lp_bb_begin", "abipgpu_lp_bb_round", "abipgpu_lp_solve_vec", "abipgpu_lp_get_vec",
     "abipgpu_lp_set_vec", "abipgpu_lp_g_th", "abipgpu_lp_spmv", "abipgpu_lp_describe",
 ]
 
@@ -119,6 +119,7 @@ def lib():
         "abipgpu_lp_admm_iter": (C.c_int, [vp, c_int, c_int, c_float, c_float, fp]),
         "abipgpu_lp_mu_stats": (C.c_int, [vp, C.c_int, fp]),
         "abipgpu_lp_reinit": (C.c_int, [vp, C.c_int, c_float, C.c_int]),
+        "abipgpu_lp_clamp_v": (C.c_int, [vp]),
         "abipgpu_lp_bb_begin": (C.c_int, [vp]),
         "abipgpu_lp_bb_round": (C.c_int, [vp, C.c_int, c_int, c_float, c_float, fp]),
         "abipgpu_lp_solve_vec": (C.c_int, [vp, C.c_int, C.c_int, c_int, fp]),

@@ -347,6 +347,12 @@ __global__ void k_reinit(double* u, double* v, int m, int l, int indx, double si
     }
 }
 
+// half_update inner-loop exit (src/abip.c:2175-2186): negative entries of v (rounding-level) are reset to 1e-6
+__global__ void k_clamp_v(double* v, int l) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < l && v[i] < 0) v[i] = 1e-6;
+}
+
 // cold_start_vars, src/abip.c:361-381
 __global__ void k_cold_start(double* u, double* v, int m, int l, double val) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -837,6 +843,14 @@ int abipgpu_lp_reinit(abipgpu_lp* e, int indx, abip_float sigma, int avg_criteri
     double* u = e->vec[avg_criterion ? ABIPGPU_VEC_UAVGC : ABIPGPU_VEC_U];
     double* v = e->vec[avg_criterion ? ABIPGPU_VEC_VAVGC : ABIPGPU_VEC_V];
     k_reinit<<<(e->n + 1 + 255) / 256, 256, 0, e->stream>>>(u, v, e->m, e->l, indx, sigma);
+    CK(cudaGetLastError());
+    e->stats.n_kernel_launches++;
+    return 0;
+}
+
+int abipgpu_lp_clamp_v(abipgpu_lp* e) {
+    CK(cudaSetDevice(e->device));
+    k_clamp_v<<<(e->l + 255) / 256, 256, 0, e->stream>>>(e->vec[ABIPGPU_VEC_V], e->l);
     CK(cudaGetLastError());
     e->stats.n_kernel_launches++;
     return 0;

@@ -786,8 +786,8 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
                 fprintf(trace, "it %ld %ld %ld %.17g %.17g %d %.17g %d\n", (long)i, (long)j, (long)k, w->mu, w->beta,
                         (int)w->sc[ABIPGPU_SC_CG_ITS], q, (int)s.avg_criterion);
             if (q < w->gamma * w->mu) {
-                // (half_update: the reference clamps negative v to 1e-6 here, abip.c:2175-2186; v >= 0 on the
-                //  (x,tau) tail by construction of the prox step, and v_y is free, so this is a no-op there)
+                if (s.half_update && abipgpu_lp_clamp_v(w->eng) != 0)  // abip.c:2175-2186
+                    return failure(m, n, sol, info, ABIP_FAILED, "error in clamp", "Failure");
                 break;
             }
             if (w->final_check) {

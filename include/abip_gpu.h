@@ -243,6 +243,7 @@ int abipgpu_lp_admm_iter(abipgpu_lp *e, abip_int j, abip_int k, abip_float mu, a
                          abip_float *sc);
 int abipgpu_lp_mu_stats(abipgpu_lp *e, int avg_criterion, abip_float *sc);              /* abip.c:957-960 */
 int abipgpu_lp_reinit(abipgpu_lp *e, int indx, abip_float sigma, int avg_criterion);    /* abip.c:996-1075 */
+int abipgpu_lp_clamp_v(abipgpu_lp *e);                                                  /* abip.c:2175-2186 */
 int abipgpu_lp_bb_begin(abipgpu_lp *e);                                                 /* adaptive.c:86-87 */
 /* one lookback round (adaptive.c:89-178).  carry: 0 = first round, 1 = beta changed (:230-242),
  * 2 = keep (u,v) (:243-247). */

@@ -1,0 +1,104 @@
+"""CPU tests of the C-ABI library: it loads, exports every symbol include/abip_gpu.h declares, its host-side
+functions (validate / copy / equilibration) match the oracle, and compute entry points fail loudly -- never fall
+back -- when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from abip_b200 import _capi, api, problems
+from oracle import lp_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    L = _capi.lib()
+    hdr = open(os.path.join(ROOT, "include", "abip_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(abip(?:gpu)?_[a-z_A-Z0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_capi.DECLARED_SYMBOLS), declared ^ set(_capi.DECLARED_SYMBOLS)
+    for s in declared:
+        assert hasattr(L, s), s
+
+
+def test_struct_layouts_match_reference_abi():
+    # -DDLONG layout of the shipped reference build: all fields 8 bytes (include/abip.h:36-105)
+    assert C.sizeof(_capi.ABIPSettings) == 31 * 8
+    assert C.sizeof(_capi.ABIPInfo) == 32 + 12 * 8
+    assert C.sizeof(_capi.ABIPMatrix) == 5 * 8
+    assert C.sizeof(_capi.ABIPData) == 7 * 8
+    st = _capi.default_settings()
+    assert (st.max_ipm_iters, st.max_admm_iters, st.alpha, st.rho_y, st.adaptive_lookback) == (500, 1000000, 1.8, 1e-3, 20)
+    assert (st.dynamic_sigma, st.hybrid_thresh, st.dynamic_sigma_second, st.restart_thresh) == (-1.0, 1000.0, 0.5, 100000)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(origin_rescale=1), dict(qp_rescale=1, pc_ruiz_rescale=0), dict(scale=2.0),
+                                dict(ruiz_iter=3)])
+def test_normalize_A_matches_oracle_and_roundtrips(kw):
+    L = _capi.lib()
+    p = problems.random_lp(200, 700, 4, seed=3)
+    H = api.CscHolder((p.m, p.n, p.Ap.copy(), p.Ai.copy(), p.Ax.copy()))
+    st = _capi.default_settings(verbose=0, **kw)
+    sc = _capi.ABIPScaling()
+    L.abip_normalize_A(C.byref(H.c), C.byref(st), C.byref(sc))
+    D = np.ctypeslib.as_array(sc.D, shape=(p.m,)).copy()
+    E = np.ctypeslib.as_array(sc.E, shape=(p.n,)).copy()
+    As, Do, Eo, mr, mc = O.normalize_A(p.csc(), O.Settings(**kw))
+    assert np.allclose(H.Ax, As.data, rtol=1e-13, atol=0)
+    assert np.allclose(D, Do, rtol=1e-13) and np.allclose(E, Eo, rtol=1e-13)
+    assert abs(sc.mean_norm_row_A - mr) < 1e-12 and abs(sc.mean_norm_col_A - mc) < 1e-12
+    L.abip_un_normalize_A(C.byref(H.c), C.byref(st), C.byref(sc))
+    assert np.allclose(H.Ax, p.Ax, rtol=1e-13)
+
+
+def test_validate_and_copy():
+    L = _capi.lib()
+    p = problems.random_lp(20, 50, 3, seed=1)
+    H = api.CscHolder(p.csc())
+    assert L.abip_validate_lin_sys(C.byref(H.c)) == 0
+    dst = C.POINTER(_capi.ABIPMatrix)()
+    assert L.abip_copy_A_matrix(C.byref(dst), C.byref(H.c)) == 1
+    assert dst.contents.m == p.m and dst.contents.n == p.n
+    assert np.array_equal(np.ctypeslib.as_array(dst.contents.x, shape=(p.nnz,)), H.Ax)
+    L.abip_free_A_matrix(dst)
+    bad = api.CscHolder((p.m, p.n, p.Ap.copy(), p.Ai.copy(), p.Ax.copy()))
+    bad.Ai[0] = p.m + 3   # row index out of range
+    assert L.abip_validate_lin_sys(C.byref(bad.c)) == -1
+    bad2 = api.CscHolder((p.m, p.n, p.Ap.copy(), p.Ai.copy(), p.Ax.copy()))
+    bad2.Ap[3] = bad2.Ap[4] + 1  # decreasing column pointers
+    assert L.abip_validate_lin_sys(C.byref(bad2.c)) == -1
+
+
+def test_entry_rejects_invalid_input_like_reference():
+    # validate(): m > n is rejected (src/abip.c:1661-1665) -> status ABIP_FAILED, NaN outputs; no GPU needed
+    import scipy.sparse as sp
+    A = sp.random(8, 5, density=0.6, random_state=1, format="csc")
+    x, y, s, info = api.lp_solve(A, np.ones(8), np.ones(5), dict(verbose=0))
+    assert info["status_val"] == -4 and np.isnan(x).all() and np.isnan(y).all()
+    with pytest.raises(ValueError):
+        api.lp_solve(A.T.tocsc(), np.ones(5), np.ones(8), dict(verbose=0, pcg=0))  # direct path: out of scope
+    with pytest.raises(ValueError):
+        api.abip({"A": A, "b": np.ones(8), "c": np.ones(5)}, {"s": 3})
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks behaviour without a CUDA device")
+def test_no_cpu_fallback_without_gpu():
+    p = problems.random_lp(20, 50, 3, seed=1)
+    x, y, s, info = api.lp_solve(p.csc(), p.b, p.c, dict(verbose=0))
+    assert info["status_val"] == -4 and np.isnan(x).all()      # ABIP_FAILED, like a failed init in the reference
+    with pytest.raises(RuntimeError):
+        api.LinSysPlugin(p.csc())
+    with pytest.raises(RuntimeError):
+        api.LpEngine(p.csc())

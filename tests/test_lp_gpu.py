@@ -274,3 +274,29 @@ def test_dropin_reference_core_with_gpu_plugin():
     assert abs(r["admm_iter"] - gold["admm_iter"]) <= max(2, 0.05 * gold["admm_iter"])
     assert abs(r["pobj"] - gold["pobj"]) <= 1e-6 * abs(gold["pobj"]) + 1e-7
     assert max(r["res_pri"], r["res_dual"], r["rel_gap"]) < 1e-4
+
+
+GOLD_CASES = {
+    "rand_200x700_eps1e-3": lambda: problems.random_lp(200, 700, 4, seed=3),
+    "rand_200x700_half": lambda: problems.random_lp(200, 700, 4, seed=3),
+    "rand_200x700_noadapt": lambda: problems.random_lp(200, 700, 4, seed=3),
+    "rand_200x700_nonorm": lambda: problems.random_lp(200, 700, 4, seed=3),
+    "rand_1x9": lambda: problems.random_lp(1, 9, 1, seed=4),
+    "cfg5_lp_0": lambda: problems.random_lp(500, 2000, 5, seed=5000),
+    "cfg2_scale0.01": lambda: problems.cfg2(scale=0.01),
+}
+
+
+@pytest.mark.parametrize("name", list(GOLD_CASES))
+def test_settings_variants_against_reference_golden(name):
+    """half_update / adaptive=0 / normalize=0 / eps variants and the cfg2 / cfg5 families against the outputs of the
+    compiled reference (tests/golden/lp_golden.json)."""
+    g = json.load(open(GOLD))[name]
+    p = GOLD_CASES[name]()
+    eps = g["settings"]["eps"]
+    x, y, s, info = lp_solve(p.csc(), p.b, p.c, dict(verbose=0), **g["settings"])
+    assert info["status"] == g["status"]
+    assert abs(info["admm_iter"] - g["admm_iter"]) <= max(2, 0.05 * g["admm_iter"]), (info["admm_iter"], g["admm_iter"])
+    assert abs(info["pobj"] - g["pobj"]) <= 1e-6 * abs(g["pobj"]) + 2 * eps * eps
+    assert max(info["pres"], info["dres"], info["gap"]) < eps
+    _check_solution(p, x, y, s, info, eps)
