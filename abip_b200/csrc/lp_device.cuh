@@ -154,16 +154,45 @@ struct Reducer {
         // the grid barrier that follows orders these writes before finish()
     }
 
-    // call after the grid barrier; every block computes the same totals in the same order
+    // same for max-reductions (inf-norms of the QCP residuals); values must be >= 0
     template <int K>
+    __device__ __forceinline__ void block_store_max(double (&v)[K], int slot0 = 0) {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double x = v[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) x = fmax(x, __shfl_down_sync(0xffffffffu, x, off));
+            if (lane == 0) sm[k * kWarps + w] = x;
+        }
+        __syncthreads();
+        if (threadIdx.x < K) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < kWarps; ++i) s = fmax(s, sm[threadIdx.x * kWarps + i]);
+            partials[(parity * kMaxRed + slot0 + threadIdx.x) * G + blockIdx.x] = s;
+        }
+        __syncthreads();
+    }
+
+    // call after the grid barrier; every block computes the same totals in the same order.
+    // MAXMASK: bit k set => slot k is a max-reduction
+    template <int K, unsigned MAXMASK = 0u>
     __device__ __forceinline__ void finish(double (&out)[K]) {
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
         for (int k = w; k < K; k += kWarps) {
             const double* src = partials + (parity * kMaxRed + k) * G;
+            const bool mx = (MAXMASK >> k) & 1u;
             double s = 0.0;
-            for (int i = lane; i < G; i += 32) s += __ldcg(src + i);
+            for (int i = lane; i < G; i += 32) {
+                const double t = __ldcg(src + i);
+                s = mx ? fmax(s, t) : s + t;
+            }
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            for (int off = 16; off > 0; off >>= 1) {
+                const double t = __shfl_xor_sync(0xffffffffu, s, off);
+                s = mx ? fmax(s, t) : s + t;
+            }
             if (lane == 0) sm[k] = s;
         }
         __syncthreads();

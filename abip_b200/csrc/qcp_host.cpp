@@ -1,0 +1,393 @@
+// qcp_host.cpp -- host side of the ABIP-QCP engine: data scaling (qcp_config.c:91-491), the outer/inner loop
+// control of ABIP(solve) (source/abip.c:1076-1249), has_converged (:750-777), adjust_barrier (:994-1071),
+// get_solution (:559-586) and the entry abip_qcp_gpu == abip() (:1335-1371).  Vector work is in qcp_engine.cu.
+#include "qcp_engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <vector>
+
+namespace {
+
+constexpr double kMinScale = 1e-3, kMaxScale = 1e3;  // qcp_config.c:2-3
+
+double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+}
+
+thread_local long g_n_iter = 0, g_n_cg = 0, g_n_inner = 0;
+thread_local double g_kernel_ms = 0;
+
+struct Resid {  // struct ABIP_RESIDUALS, include/abip.h:190-216
+    int last_admm_iter = -1;
+    double res_pri = 1e8, res_dual = 1e8, rel_gap = 1e8, error_ratio = 1e8;
+    double res_dif = NAN, res_infeas = NAN, res_unbdd = NAN, pobj = NAN, dobj = NAN, tau = NAN, kap = NAN;
+};
+
+void fill_nan(double* a, long n) {
+    for (long i = 0; i < n; ++i) a[i] = NAN;
+}
+
+int qcp_failure(int m, int n, ABIPSolution* sol, ABIPQcpInfo* info, const char* msg) {  // abip.c:129-184
+    if (info) {
+        info->res_pri = info->res_dual = info->rel_gap = info->res_infeas = info->res_unbdd = NAN;
+        info->pobj = info->dobj = NAN;
+        info->ipm_iter = info->admm_iter = -1;
+        info->status_val = ABIP_FAILED;
+        info->solve_time = NAN;
+        snprintf(info->status, sizeof(info->status), "Failure");
+    }
+    if (sol) {
+        if (n > 0) {
+            if (!sol->x) sol->x = (double*)malloc(sizeof(double) * n);
+            if (!sol->s) sol->s = (double*)malloc(sizeof(double) * n);
+            fill_nan(sol->x, n);
+            fill_nan(sol->s, n);
+        }
+        if (m > 0) {
+            if (!sol->y) sol->y = (double*)malloc(sizeof(double) * m);
+            fill_nan(sol->y, m);
+        }
+    }
+    printf("Failure:%s\n", msg);
+    return ABIP_FAILED;
+}
+
+}  // namespace
+
+extern "C" {
+
+void abip_qcp_gpu_set_default_settings(ABIPQcpData* d) {  // source/util.c:203-255
+    ABIPQcpSettings* s = d->stgs;
+    s->normalize = 1; s->scale_E = 1; s->scale_bc = 1;
+    s->max_ipm_iters = 500; s->max_admm_iters = 1000000;
+    s->eps = s->eps_p = s->eps_d = s->eps_g = s->eps_inf = s->eps_unb = 1e-3;
+    s->alpha = 1.8; s->cg_rate = 2.0; s->use_indirect = 0;
+    s->scale = 1.0; s->rho_y = 1e-6; s->rho_x = 1; s->rho_tau = 1; s->verbose = 1;
+    s->err_dif = 0; s->inner_check_period = 500; s->outer_check_period = 1;
+    s->linsys_solver = 3; s->prob_type = 3; s->time_limit = INFINITY; s->psi = 1;
+    s->origin_scaling = 1; s->ruiz_scaling = 1; s->pc_scaling = 0;
+}
+
+// Scaling of (A, Q, b, c): 10 Ruiz sweeps, one "origin" (2-norm) sweep, optionally one pc sweep; the column factor
+// E is the max of A's and Q's column statistic, averaged over every SOC / RSOC block so that cones stay cones.
+void abip_qcp_scale_data(ABIPQcpMatrix* A, ABIPQcpMatrix* Q, double* b, double* c, const ABIPQcpCone* K,
+                         const ABIPQcpSettings* stgs, double* D_hat, double* E_hat, double* sc_b, double* sc_c) {
+    const int m = A->m, n = A->n;
+    const int nnzA = A->p[n], nnzQ = Q ? Q->p[n] : 0;
+    std::fill(D_hat, D_hat + m, 1.0);
+    std::fill(E_hat, E_hat + n, 1.0);
+    const double min_row = kMinScale * std::sqrt((double)n), max_row = kMaxScale * std::sqrt((double)n);
+    const double min_col = kMinScale * std::sqrt((double)m), max_col = kMaxScale * std::sqrt((double)m);
+    std::vector<double> E(n), D(m);
+    enum Kind { RUIZ, ORIGIN, PC };
+    auto col_stat = [&](const ABIPQcpMatrix* M, int j, Kind kind) {
+        double acc = 0;
+        for (int k = M->p[j]; k < M->p[j + 1]; ++k) {
+            const double a = std::fabs(M->x[k]);
+            if (kind == RUIZ) acc = std::max(acc, a);
+            else if (kind == ORIGIN) acc += a * a;
+            else acc += a;
+        }
+        return kind == ORIGIN ? std::sqrt(acc) : acc;  // ORIGIN: 2-norm; RUIZ: inf-norm; PC: 1-norm
+    };
+    auto sweep = [&](Kind kind) {
+        for (int j = 0; j < n; ++j) {
+            double e1 = col_stat(A, j, kind), e2 = Q ? col_stat(Q, j, kind) : 0.0;
+            E[j] = std::sqrt(std::max(e1, e2));  // sqrt of the (larger) column statistic, for all three kinds
+        }
+        int pos = 0;  // cone averaging (:207-225)
+        auto avg_blocks = [&](const int* dims, int cnt) {
+            for (int i = 0; i < cnt; ++i) {
+                const int d = dims[i];
+                if (d > 0) {
+                    double s = 0;
+                    for (int j = 0; j < d; ++j) s += E[pos + j];
+                    s /= d;
+                    for (int j = 0; j < d; ++j) E[pos + j] = s;
+                }
+                pos += d;
+            }
+        };
+        if (K->q) avg_blocks(K->q, K->qsize);
+        if (K->rq) avg_blocks(K->rq, K->rqsize);
+        std::fill(D.begin(), D.end(), 0.0);
+        for (int k = 0; k < nnzA; ++k) {
+            const double a = std::fabs(A->x[k]);
+            double& d = D[A->i[k]];
+            if (kind == RUIZ) { if (d < a) d = a; }
+            else if (kind == ORIGIN) d += a * a;
+            else d += a;
+        }
+        for (int i = 0; i < m; ++i) {
+            double d = kind == ORIGIN ? std::sqrt(std::sqrt(D[i])) : std::sqrt(D[i]);
+            if (d < min_row) d = 1; else if (d > max_row) d = max_row;
+            D[i] = d;
+        }
+        for (int j = 0; j < n; ++j) {
+            if (E[j] < min_col) E[j] = 1; else if (E[j] > max_col) E[j] = max_col;
+            for (int k = A->p[j]; k < A->p[j + 1]; ++k) A->x[k] /= E[j];
+        }
+        if (Q) {
+            for (int j = 0; j < n; ++j)
+                for (int k = Q->p[j]; k < Q->p[j + 1]; ++k) Q->x[k] /= E[j];
+            for (int k = 0; k < nnzQ; ++k) Q->x[k] /= E[Q->i[k]];
+        }
+        for (int k = 0; k < nnzA; ++k) A->x[k] /= D[A->i[k]];
+        for (int j = 0; j < n; ++j) E_hat[j] *= E[j];
+        for (int i = 0; i < m; ++i) D_hat[i] *= D[i];
+    };
+    if (stgs->ruiz_scaling)
+        for (int it = 0; it < 10; ++it) sweep(RUIZ);
+    if (stgs->origin_scaling) sweep(ORIGIN);
+    if (stgs->pc_scaling) sweep(PC);
+    double nsq = 0;
+    for (int j = 0; j < n; ++j) nsq += c[j] * c[j];
+    for (int i = 0; i < m; ++i) nsq += b[i] * b[i];
+    double sc = std::sqrt(std::sqrt(nsq));
+    for (int i = 0; i < m; ++i) b[i] /= D_hat[i];
+    for (int j = 0; j < n; ++j) c[j] /= E_hat[j];
+    if (sc < kMinScale) sc = 1; else if (sc > kMaxScale) sc = kMaxScale;
+    *sc_b = 1 / sc;
+    *sc_c = 1 / sc;
+    for (int i = 0; i < m; ++i) b[i] *= *sc_b * stgs->scale;
+    for (int j = 0; j < n; ++j) c[j] *= *sc_c * stgs->scale;
+}
+
+void abip_qcp_gpu_last_counters(long* n_iter, long* n_cg, long* n_inner, double* kernel_ms) {
+    *n_iter = g_n_iter; *n_cg = g_n_cg; *n_inner = g_n_inner; *kernel_ms = g_kernel_ms;
+}
+
+int abip_qcp_gpu(const ABIPQcpData* d, ABIPSolution* sol, ABIPQcpInfo* info, ABIPQcpCone* K) {
+    if (!d || !sol || !info || !K || !d->A || !d->stgs || !d->b || !d->c) {
+        printf("ERROR: ABIP_NULL input\n");
+        return ABIP_FAILED;
+    }
+    const ABIPQcpSettings st = *d->stgs;
+    const int m = d->m, n = d->n;
+    const double t_init = now_ms();
+    // ---- validate (abip.c:779-832, cones.c:37-83)
+    int dims = K->f + K->z + K->l;
+    bool bad = n <= 0 || m > n || K->f < 0 || K->z < 0 || K->l < 0;
+    for (int i = 0; K->q && i < K->qsize; ++i) { bad |= K->q[i] < 0; dims += K->q[i]; }
+    for (int i = 0; K->rq && i < K->rqsize; ++i) { bad |= K->rq[i] < 0; dims += K->rq[i]; }
+    if (dims != n) { printf("cone dimensions %d not equal to num rows in A = n = %d\n", dims, n); bad = true; }
+    bad |= st.max_ipm_iters <= 0 || st.max_admm_iters <= 0 || st.eps_p <= 0 || st.eps_d <= 0 || st.eps_g <= 0 ||
+           st.eps_inf <= 0 || st.eps_unb <= 0 || st.alpha <= 0 || st.alpha >= 2 || st.rho_y <= 0;
+    if (bad) {
+        printf("ERROR: Validation returned failure\n");
+        return qcp_failure(m, n, sol, info, "could not initialize work");
+    }
+    // ---- init_work: norms of the original data, scaled private copies (abip.c:873-878)
+    double nm_inf_b = 0, nm_inf_c = 0;
+    for (int i = 0; i < m; ++i) nm_inf_b = std::max(nm_inf_b, std::fabs(d->b[i]));
+    for (int j = 0; j < n; ++j) nm_inf_c = std::max(nm_inf_c, std::fabs(d->c[j]));
+    const int nnzA = d->A->p[n];
+    std::vector<double> Ax(d->A->x, d->A->x + nnzA), b(d->b, d->b + m), c(d->c, d->c + n), D(m), E(n);
+    std::vector<int> Ai(d->A->i, d->A->i + nnzA), Ap(d->A->p, d->A->p + n + 1);
+    ABIPQcpMatrix As{Ax.data(), Ai.data(), Ap.data(), m, n};
+    std::vector<double> Qx;
+    std::vector<int> Qi, Qp;
+    ABIPQcpMatrix Qs{nullptr, nullptr, nullptr, n, n};
+    const bool has_q = d->Q && d->Q->p && d->Q->p[n] > 0;
+    if (has_q) {
+        Qx.assign(d->Q->x, d->Q->x + d->Q->p[n]);
+        Qi.assign(d->Q->i, d->Q->i + d->Q->p[n]);
+        Qp.assign(d->Q->p, d->Q->p + n + 1);
+        Qs = ABIPQcpMatrix{Qx.data(), Qi.data(), Qp.data(), n, n};
+    }
+    double sc_b = 1, sc_c = 1;
+    abip_qcp_scale_data(&As, has_q ? &Qs : nullptr, b.data(), c.data(), K, &st, D.data(), E.data(), &sc_b, &sc_c);
+    const char* dev = getenv("ABIP_GPU_DEVICE");
+    const char* rt = getenv("ABIP_GPU_QCP_RTOL");
+    const double rtol = rt ? atof(rt) : 1e-8;
+    abipgpu_qcp* e = abipgpu_qcp_create(m, n, Ap.data(), Ai.data(), Ax.data(), has_q ? Qp.data() : nullptr,
+                                        has_q ? Qi.data() : nullptr, has_q ? Qx.data() : nullptr, b.data(), c.data(),
+                                        D.data(), E.data(), K->q, K->q ? K->qsize : 0, K->rq, K->rq ? K->rqsize : 0, K->f,
+                                        K->z, K->l, st.rho_x, st.rho_y, st.rho_tau, st.alpha, rtol, dev ? atoi(dev) : 0);
+    if (!e) return qcp_failure(m, n, sol, info, "could not initialize work");
+    info->setup_time = now_ms() - t_init;
+    if (st.verbose) printf("ABIP-QCP B200 engine: m = %d, n = %d, setup %.2es\n", m, n, info->setup_time / 1e3);
+
+    // ---- ABIP(solve), abip.c:1076-1249
+    const double t0 = now_ms();
+    const double time_limit_left = 1e3 * st.time_limit - info->setup_time;
+    info->status_val = ABIP_UNFINISHED;
+    Resid r;
+    double mu = 1.0, beta = 1.0;
+    double tol_inner = 4 * std::pow(mu, st.psi);
+    double sc[ABIPGPU_QSC_COUNT];
+    const int sparsity = 1;  // qcp_config.c:19-23: integer division nnz/(m*n) is 0 < 0.05 for every sparse input
+    long k = 0;
+    int i = 0, status = 0;
+    bool done = false;
+
+    auto calc_residuals = [&](long admm_iter) {  // qcp_config.c:562-691 from the sums reduced by the kernel
+        if (admm_iter && r.last_admm_iter == admm_iter) return;
+        r.last_admm_iter = (int)admm_iter;
+        const double tau = std::fabs(sc[ABIPGPU_QSC_TAU]);
+        r.tau = tau;
+        r.kap = std::fabs(sc[ABIPGPU_QSC_VO_TAU]) / (st.normalize ? (st.scale * sc_c * sc_b) : 1);
+        const double this_pr = sc[ABIPGPU_QSC_AXB_D_INF] / (sc_b + std::max(sc[ABIPGPU_QSC_AX_D_INF], sc_b * nm_inf_b));
+        const double xQx_2 = has_q ? (sc[ABIPGPU_QSC_XQX] / (tau * tau)) / (2 * sc_b * sc_c) : 0.0;
+        const double this_dr =
+            sc[ABIPGPU_QSC_RESD_E_INF] / (sc_c + std::max(sc_c * nm_inf_c, sc[ABIPGPU_QSC_QX_E_INF]));
+        const double cTx = (sc[ABIPGPU_QSC_XC] / tau) / (sc_b * sc_c), bTy = (sc[ABIPGPU_QSC_YB] / tau) / (sc_b * sc_c);
+        const double this_gap =
+            std::fabs(2 * xQx_2 + cTx - bTy) / (1 + std::max(2 * xQx_2, std::max(std::fabs(cTx), std::fabs(bTy))));
+        r.pobj = xQx_2 + cTx;
+        r.dobj = -xQx_2 + bTy;
+        r.res_dif = std::max(std::max(std::fabs(this_pr - r.res_pri), std::fabs(this_dr - r.res_dual)),
+                             std::fabs(this_gap - r.rel_gap));
+        r.res_pri = this_pr;
+        r.res_dual = this_dr;
+        r.rel_gap = this_gap;
+        r.error_ratio = std::max(r.res_pri / st.eps_p, std::max(r.res_dual / st.eps_d, r.rel_gap / st.eps_g));
+        r.res_unbdd = sc[ABIPGPU_QSC_XC] < 0
+                          ? std::max(std::sqrt(sc[ABIPGPU_QSC_QXE2]), std::sqrt(sc[ABIPGPU_QSC_AXD2])) / (-sc[ABIPGPU_QSC_XC])
+                          : INFINITY;
+        r.res_infeas = sc[ABIPGPU_QSC_YB] > 0 ? std::sqrt(sc[ABIPGPU_QSC_ATYS_E2]) / sc[ABIPGPU_QSC_YB] : INFINITY;
+    };
+    auto has_converged = [&](int ipm_iter, long admm_iter) {  // abip.c:750-777
+        if (r.res_pri < st.eps_p && r.res_dual < st.eps_d && r.rel_gap < st.eps_g) return (int)ABIP_SOLVED;
+        if (r.res_dif < st.err_dif * std::max(std::max(st.eps_p, st.eps_d), st.eps_g)) return (int)ABIP_SOLVED_INACCURATE;
+        if (r.res_unbdd < st.eps_unb && ipm_iter > 0 && admm_iter > 0) return (int)ABIP_UNBOUNDED;
+        if (r.res_infeas < st.eps_inf && ipm_iter > 0 && admm_iter > 0) return (int)ABIP_INFEASIBLE;
+        return 0;
+    };
+    auto adjust_barrier = [&]() {  // abip.c:994-1071
+        double sigma = 0.8, gamma = 0.5;
+        const double ratio = mu / std::min(std::min(st.eps_p, st.eps_d), st.eps_g);
+        static const double lo[] = {50, 10, 5, 1, 0.5, 0.1, 0.05, 0.01, 0.005, 0.001, 0.0005, 0.0001, 0.00005};
+        static const double hi[] = {100, 50, 10, 5, 1, 0.5, 0.1, 0.05, 0.01, 0.005, 0.001, 0.0005, 0.0001};
+        static const double gm[] = {1.5, 1.3, 1.2, 1.1, 1.0, 0.9, 0.9, 0.8, 0.8, 0.7, 0.7, 0.6, 0.6};
+        for (int q = 0; q < 13; ++q)
+            if (ratio > lo[q] && ratio <= hi[q]) { gamma = gm[q]; break; }
+        const double er = r.error_ratio;
+        if (er > 22) gamma *= 4.4;
+        else if (er > 18) gamma *= 4.2;
+        else if (er > 15) gamma *= 4;
+        else if (er > 12) gamma *= 3.8;
+        else if (er > 8) gamma *= 3.6;
+        else if (er > 6) { sigma = 0.81; gamma *= 3.4; }
+        else if (er > 4) { sigma = 0.82; gamma *= 3.4; }
+        else if (er > 3) { sigma = 0.83; gamma *= 3.2; }
+        else if (er > 2) { sigma = 0.85; gamma *= 2.8; }
+        else if (er > 1.5) { sigma = 0.85; gamma *= 2.6; }
+        else if (er < 1.5) { sigma = 0.85; gamma *= 2.4; }
+        sigma *= 0.2;
+        mu = sigma * mu;
+        return gamma * std::pow(mu, st.psi);
+    };
+
+    for (i = 0; i < st.max_ipm_iters && !done; ++i) {
+        for (long j = 0; j < st.max_admm_iters; ++j) {
+            if (abipgpu_qcp_iter(e, k, mu, beta, sc) != 0) {
+                abipgpu_qcp_destroy(e);
+                return qcp_failure(m, n, sol, info, "error in project_lin_sys");
+            }
+            k += 1;
+            // inner_conv_check (qcp_config.c:518-557)
+            const double tau = sc[ABIPGPU_QSC_TAU];
+            const double qu_tau = -sc[ABIPGPU_QSC_UMU] / tau + sc[ABIPGPU_QSC_YB] - sc[ABIPGPU_QSC_XC];
+            const double vo_tau = sc[ABIPGPU_QSC_VO_TAU];
+            const double dt = qu_tau - vo_tau;
+            const double err_inner = std::sqrt(sc[ABIPGPU_QSC_S_DIFF] + dt * dt) /
+                                     (1 + std::sqrt(sc[ABIPGPU_QSC_S_QU] + qu_tau * qu_tau) +
+                                      std::sqrt(sc[ABIPGPU_QSC_S_VO] + vo_tau * vo_tau));
+            const bool timeout = (now_ms() - t0) > time_limit_left;
+            if (err_inner < tol_inner || timeout) break;
+            if ((j + 1) % st.inner_check_period == 0 || r.error_ratio <= 8) {
+                calc_residuals(k);
+                status = has_converged(i, k);
+                if (status != 0 || k + 1 >= (long)st.max_admm_iters * st.max_ipm_iters || i + 1 >= st.max_ipm_iters ||
+                    (now_ms() - t0) > time_limit_left) {
+                    done = true;
+                    break;
+                }
+            }
+        }
+        if (done) break;
+        if (sparsity || (i + 1) % st.outer_check_period == 0) {
+            calc_residuals(k);
+            if (st.verbose)
+                printf("%4d | %7ld | mu %.2e | pres %.2e dres %.2e gap %.2e | pobj %.6e dobj %.6e | %.2fs\n", i + 1, k, mu,
+                       r.res_pri, r.res_dual, r.rel_gap, r.pobj, r.dobj, (now_ms() - t0) / 1e3);
+            status = has_converged(i, k);
+            if (status != 0 || k + 1 >= (long)st.max_admm_iters * st.max_ipm_iters || i + 1 >= st.max_ipm_iters ||
+                (now_ms() - t0) > time_limit_left) {
+                done = true;
+                break;
+            }
+        }
+        tol_inner = adjust_barrier();
+    }
+    // ---- get_solution (abip.c:559-586) + un_scaling_qcp_sol (qcp_config.c:496-513)
+    if (!done) {  // loop ran out without a verdict: the reference returns garbage here; report the last iterate
+        calc_residuals(k);
+        i = st.max_ipm_iters - 1;
+    }
+    const int l = m + n + 1;
+    std::vector<double> u(l), v(l);
+    if (abipgpu_qcp_get_vec(e, 0, u.data(), l) != 0 || abipgpu_qcp_get_vec(e, 1, v.data(), l) != 0) {
+        abipgpu_qcp_destroy(e);
+        return qcp_failure(m, n, sol, info, "error in get_solution");
+    }
+    if (!sol->x) sol->x = (double*)malloc(sizeof(double) * n);
+    if (!sol->y) sol->y = (double*)malloc(sizeof(double) * std::max(m, 1));
+    if (!sol->s) sol->s = (double*)malloc(sizeof(double) * n);
+    std::copy(u.begin(), u.begin() + m, sol->y);
+    std::copy(u.begin() + m, u.begin() + m + n, sol->x);
+    std::copy(v.begin() + m, v.begin() + m + n, sol->s);
+    auto scale_all = [](double* a, int len, double f) { for (int q = 0; q < len; ++q) a[q] *= f; };
+    info->status_val = status;
+    if (status == 0 || status == ABIP_SOLVED || status == ABIP_SOLVED_INACCURATE) {
+        const double f = r.tau < 1e-18 ? 1.0 / 1e-18 : 1.0 / r.tau;
+        scale_all(sol->x, n, f); scale_all(sol->y, m, f); scale_all(sol->s, n, f);
+        const bool inacc = status == 0 || status == ABIP_SOLVED_INACCURATE;
+        info->status_val = inacc ? ABIP_SOLVED_INACCURATE : ABIP_SOLVED;
+        snprintf(info->status, sizeof(info->status), "%s", inacc ? "Solved/Inaccurate" : "Solved");
+    } else if (status == ABIP_INFEASIBLE) {
+        scale_all(sol->y, m, 1 / (r.dobj * r.tau)); scale_all(sol->s, n, 1 / (r.dobj * r.tau));
+        fill_nan(sol->x, n);
+        snprintf(info->status, sizeof(info->status), "Infeasible");
+    } else {
+        scale_all(sol->x, n, -1 / (r.pobj * r.tau));
+        fill_nan(sol->y, m); fill_nan(sol->s, n);
+        snprintf(info->status, sizeof(info->status), "Unbounded");
+    }
+    if (st.normalize) {
+        for (int j = 0; j < n; ++j) sol->x[j] /= (E[j] * sc_b);
+        for (int q = 0; q < m; ++q) sol->y[q] /= (D[q] * sc_c);
+        for (int j = 0; j < n; ++j) sol->s[j] *= E[j] / (sc_c * st.scale);
+    }
+    info->ipm_iter = i + 1;
+    info->admm_iter = (int)k;
+    info->res_infeas = r.res_infeas;
+    info->res_unbdd = r.res_unbdd;
+    if (info->status_val == ABIP_SOLVED || info->status_val == ABIP_SOLVED_INACCURATE) {
+        info->rel_gap = r.rel_gap; info->res_pri = r.res_pri; info->res_dual = r.res_dual;
+        info->pobj = r.pobj; info->dobj = r.dobj;
+    } else if (info->status_val == ABIP_UNBOUNDED) {
+        info->rel_gap = info->res_pri = info->res_dual = NAN; info->pobj = info->dobj = -INFINITY;
+    } else {
+        info->rel_gap = info->res_pri = info->res_dual = NAN; info->pobj = info->dobj = INFINITY;
+    }
+    info->solve_time = now_ms() - t0;
+    abipgpu_qcp_counters(e, &g_n_iter, &g_n_cg, &g_n_inner, &g_kernel_ms);
+    info->avg_cg_iters = k > 0 ? (double)g_n_cg / k : 0.0;
+    info->avg_linsys_time = 0.0;
+    if (st.verbose)
+        printf("Status: %s | ipm %d admm %ld | pobj %.6e dobj %.6e | solve %.3fs | avg CG its %.1f\n", info->status,
+               info->ipm_iter, k, info->pobj, info->dobj, info->solve_time / 1e3, info->avg_cg_iters);
+    abipgpu_qcp_destroy(e);
+    return info->status_val;
+}
+
+}  // extern "C"

@@ -167,3 +167,106 @@ def cfg5_batch(count: int = 4096, base_seed: int = 5000, m: int = 500, n: int = 
                nnz_per_col: int = 5):
     """BASELINE.json configs[4]: independent small LPs (density 1% -> 5 nnz per column)."""
     return [random_lp(m, n, nnz_per_col, seed=base_seed + i, name=f"cfg5_lp_{i}") for i in range(count)]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ABIP-QCP:  min 1/2 x'Qx + c'x  s.t. Ax = b, x in K,  K = SOC^q x RSOC^rq x free x zero x R+   (column order
+# q -> rq -> f -> z -> l, reference README.md:121 and src/abip-qcp/include/abip.h:63-76)
+# ---------------------------------------------------------------------------------------------------------
+@dataclass
+class QCPProblem:
+    m: int
+    n: int
+    A: sp.csc_matrix
+    Q: sp.csc_matrix | None
+    b: np.ndarray
+    c: np.ndarray
+    K: dict
+    name: str = "qcp"
+
+
+def toy_qcp() -> QCPProblem:
+    """The explicit 2 x 8 QCP of the reference's only test (test/test_abip_install.m:32-43)."""
+    A = sp.csc_matrix(np.array([[1, 2, 3, 4, 5, 6, 7, 8], [0, 1, 2, 1, 2, 3, 1, 2]], dtype=np.float64))
+    return QCPProblem(2, 8, A, sp.identity(8, format="csc", dtype=np.float64), np.array([4.0, 3.0]),
+                      np.array([1.0, 0, 2, 1, 4, 2, 3, 0]), {"q": [3], "rq": [3], "f": 1, "l": 1}, "toy_qcp")
+
+
+def _cone_interior_point(K: dict, n: int, rng: np.random.Generator):
+    """A point strictly inside K (primal) / K* (dual; all cones here are self-dual except free<->zero)."""
+    x = np.zeros(n)
+    pos = 0
+    for d in K.get("q", []):
+        if d > 0:
+            t = rng.standard_normal(d - 1) if d > 1 else np.zeros(0)
+            x[pos] = np.linalg.norm(t) + rng.uniform(0.5, 1.5)
+            x[pos + 1:pos + d] = t
+            pos += d
+    for d in K.get("rq", []):
+        t = rng.standard_normal(d - 2)
+        a = rng.uniform(0.5, 1.5)
+        bb = (t @ t) / (2 * a) + rng.uniform(0.5, 1.5)
+        x[pos], x[pos + 1] = a, bb
+        x[pos + 2:pos + d] = t
+        pos += d
+    pos += K.get("f", 0) + K.get("z", 0)
+    ll = K.get("l", 0)
+    x[pos:pos + ll] = rng.uniform(0.1, 1.1, size=ll)
+    return x
+
+
+def random_qcp(m: int, n_soc: int, soc_dim: int, n_rsoc: int = 0, rsoc_dim: int = 4, n_free: int = 0, n_lin: int = 0,
+               nnz_per_col: int = 4, q_offdiag_per_col: int = 2, seed: int = 0, with_q: bool = True,
+               name: str | None = None) -> QCPProblem:
+    """cfg 3 family: SOCP/QCP with `n_soc` second-order cones (+ optional rotated cones, free and linear blocks),
+    random sparse A, Q = B'B-like sparse PSD (diagonal + symmetric off-diagonals, diagonally dominant).
+    Feasible by construction: x0 in int K, b = A x0; s0 in int K*, y0 random, c = A'y0 + s0 - Q x0."""
+    rng = np.random.default_rng(seed)
+    K = {}
+    if n_soc:
+        K["q"] = [soc_dim] * n_soc
+    if n_rsoc:
+        K["rq"] = [rsoc_dim] * n_rsoc
+    if n_free:
+        K["f"] = n_free
+    if n_lin:
+        K["l"] = n_lin
+    n = n_soc * soc_dim + n_rsoc * rsoc_dim + n_free + n_lin
+    k = min(nnz_per_col, m)
+    rows = rng.integers(0, m, size=(n, k))
+    cols = np.repeat(np.arange(n), k)
+    vals = rng.standard_normal(n * k)
+    r, c_, v = _patch_empty_rows(rows.reshape(-1).astype(np.int64), cols.astype(np.int64), vals, m, n, rng)
+    A = sp.coo_matrix((v, (r, c_)), shape=(m, n)).tocsc()
+    A.sum_duplicates()
+    A.sort_indices()
+    Q = None
+    if with_q:
+        qo = q_offdiag_per_col
+        ri = rng.integers(0, n, size=n * qo)
+        ci = np.repeat(np.arange(n), qo)
+        vv = 0.1 * rng.standard_normal(n * qo)
+        off = sp.coo_matrix((vv, (ri, ci)), shape=(n, n)).tocsr()
+        off = off + off.T
+        off.setdiag(0)
+        dom = np.asarray(abs(off).sum(axis=1)).ravel()
+        Q = (off + sp.diags(dom + rng.uniform(0.05, 1.0, size=n))).tocsc()
+        Q.sort_indices()
+    x0 = _cone_interior_point(K, n, rng)
+    pos_f = n_soc * soc_dim + n_rsoc * rsoc_dim
+    x0[pos_f:pos_f + n_free] = rng.standard_normal(n_free)
+    s0 = _cone_interior_point(K, n, rng)
+    s0[pos_f:pos_f + n_free] = 0.0   # dual of the free cone is {0}
+    y0 = rng.standard_normal(m)
+    b = A @ x0
+    c = A.T @ y0 + s0 - (Q @ x0 if Q is not None else 0.0)
+    return QCPProblem(m, n, A, Q, np.asarray(b), np.asarray(c), K, name or f"random_qcp_m{m}_n{n}")
+
+
+def cfg3(seed: int = 3, scale: float = 1.0) -> QCPProblem:
+    """BASELINE.json configs[2]: SOCP with 10k second-order cones of dimension 50 (n = 500k), nnz(A) = 10M
+    (20 per column), sparse PSD Q.  m = 100k."""
+    n_soc = max(2, int(round(10000 * scale)))
+    m = max(4, int(round(100000 * scale)))
+    return random_qcp(m, n_soc, 50, nnz_per_col=20, q_offdiag_per_col=2, seed=seed, with_q=True,
+                      name=f"cfg3_socp_scale{scale:g}")

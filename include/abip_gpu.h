@@ -259,6 +259,128 @@ int abipgpu_lp_spmv(abipgpu_lp *e, int trans, const abip_float *x, abip_float *y
 /* launch geometry and SpMV variant chosen from the row-length statistics */
 void abipgpu_lp_describe(const abipgpu_lp *e, char *buf, abip_int buflen);
 
+/* ------------------------------------------------------------------------------------------------
+ * (4) ABIP-QCP: min 1/2 x'Qx + c'x  s.t. Ax = b, x in K (SOC, rotated SOC, free, zero, orthant blocks in this
+ *     column order).  Entry and structs mirror src/abip-qcp/include/abip.h:67-165 and abip() (source/abip.c:1335);
+ *     abip_int of that build is `int` (make_abip_qcp.m does not define DLONG).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ABIP_QCP_MATRIX { /* include/amatrix.h:11-18 (CSC) */
+    double *x;
+    int *i;
+    int *p;
+    int m;
+    int n;
+} ABIPQcpMatrix;
+
+typedef struct ABIP_QCP_CONE { /* include/abip.h:67-76 */
+    int *q;
+    int qsize;
+    int *rq;
+    int rqsize;
+    int f;
+    int z;
+    int l;
+} ABIPQcpCone;
+
+typedef struct ABIP_QCP_SETTINGS { /* include/abip.h:91-131 (field order is the ABI) */
+    int normalize;
+    int scale_E;
+    int scale_bc;
+    double scale;
+    double rho_x;
+    double rho_y;
+    double rho_tau;
+    int max_ipm_iters;
+    int max_admm_iters;
+    double eps;
+    double eps_p;
+    double eps_d;
+    double eps_g;
+    double eps_inf;
+    double eps_unb;
+    double err_dif;
+    double alpha;
+    double cg_rate;
+    int use_indirect;
+    int inner_check_period;
+    int outer_check_period;
+    int verbose;
+    int linsys_solver; /* ignored: this engine always uses its m-space Schur PCG (see csrc/qcp_engine.cu) */
+    int prob_type;     /* must be 2 or 3 (general QCP) */
+    double time_limit; /* seconds */
+    double psi;
+    int origin_scaling;
+    int ruiz_scaling;
+    int pc_scaling;
+} ABIPQcpSettings;
+
+typedef struct ABIP_QCP_DATA { /* include/abip.h:79-89 */
+    int m;
+    int n;
+    ABIPQcpMatrix *A;
+    ABIPQcpMatrix *Q; /* symmetric, both triangles stored; may be NULL */
+    double *b;
+    double *c;
+    double lambda;
+    ABIPQcpSettings *stgs;
+} ABIPQcpData;
+
+typedef struct ABIP_QCP_INFO { /* include/abip.h:139-157 */
+    char status[32];
+    int status_val;
+    int ipm_iter;
+    int admm_iter;
+    double pobj;
+    double dobj;
+    double res_pri;
+    double res_dual;
+    double rel_gap;
+    double res_infeas;
+    double res_unbdd;
+    double setup_time;
+    double solve_time;
+    double avg_linsys_time;
+    double avg_cg_iters;
+} ABIPQcpInfo;
+
+void abip_qcp_gpu_set_default_settings(ABIPQcpData *d); /* source/util.c:203-255 */
+/* abip(d, sol, info, K), source/abip.c:1335-1371 */
+int abip_qcp_gpu(const ABIPQcpData *d, ABIPSolution *sol, ABIPQcpInfo *info, ABIPQcpCone *K);
+/* counters of the last abip_qcp_gpu call in this thread: ADMM-iteration launches, outer CG iterations, inner
+ * (H^-1) CG iterations, CUDA-event time inside the launches (ms) */
+void abip_qcp_gpu_last_counters(long *n_iter, long *n_cg, long *n_inner, double *kernel_ms);
+/* data scaling of the QCP (qcp_config.c:91-491) on host arrays, in place; D [m], E [n] are written */
+void abip_qcp_scale_data(ABIPQcpMatrix *A, ABIPQcpMatrix *Q, double *b, double *c, const ABIPQcpCone *K,
+                         const ABIPQcpSettings *stgs, double *D, double *E, double *sc_b, double *sc_c);
+
+/* device-resident QCP step functions */
+typedef struct ABIPGPU_QCP abipgpu_qcp;
+enum {
+    ABIPGPU_QSC_CG_ITS = 0, ABIPGPU_QSC_INNER_ITS = 1, ABIPGPU_QSC_TAU_T = 2, ABIPGPU_QSC_CG_RES = 3,
+    ABIPGPU_QSC_S_DIFF = 4, ABIPGPU_QSC_S_QU = 5, ABIPGPU_QSC_S_VO = 6, ABIPGPU_QSC_UMU = 7, ABIPGPU_QSC_YB = 8,
+    ABIPGPU_QSC_XC = 9, ABIPGPU_QSC_XQX = 10, ABIPGPU_QSC_AXD2 = 11, ABIPGPU_QSC_QXE2 = 12,
+    ABIPGPU_QSC_ATYS_E2 = 13, ABIPGPU_QSC_AXB_INF = 14, ABIPGPU_QSC_AXB_D_INF = 15, ABIPGPU_QSC_AX_D_INF = 16,
+    ABIPGPU_QSC_RESD_INF = 17, ABIPGPU_QSC_RESD_E_INF = 18, ABIPGPU_QSC_QX_E_INF = 19, ABIPGPU_QSC_TAU = 20,
+    ABIPGPU_QSC_VO_TAU = 21, ABIPGPU_QSC_A_COEF = 22,
+    ABIPGPU_QSC_COUNT = 32
+};
+/* A, Q, b, c, D, E: *scaled* data (CSC, int indices); builds CSR copies, preconditioners, the initial point
+ * (abip.c:912-992) and r = K^-1[-b; c], a = rho_tau + r'(rho o r) (pre_calculate, abip.c:886-910) */
+abipgpu_qcp *abipgpu_qcp_create(int m, int n, const int *Ap, const int *Ai, const double *Ax, const int *Qp,
+                                const int *Qi, const double *Qx, const double *b, const double *c, const double *D,
+                                const double *E, const int *q, int qsize, const int *rq, int rqsize, int f, int z,
+                                int l, double rho_x, double rho_y, double rho_tau, double alpha, double rtol,
+                                int device);
+void abipgpu_qcp_destroy(abipgpu_qcp *e);
+/* one inner iteration (abip.c:1130-1152): projection, barrier subproblem, dual update, conv-check/residual sums */
+int abipgpu_qcp_iter(abipgpu_qcp *e, long k, double mu, double beta, double *sc);
+/* vec (host, m+n) <- K^-1 vec with K = [rho_y I, A; -A', Q + rho_x I]; warm: y warm start (host, m) or NULL */
+int abipgpu_qcp_solve_vec(abipgpu_qcp *e, double *host_vec, const double *host_warm, double rtol, double *sc);
+int abipgpu_qcp_get_vec(abipgpu_qcp *e, int id, double *host, long len); /* 0 u, 1 v, 2 u_t, 3 r */
+int abipgpu_qcp_set_vec(abipgpu_qcp *e, int id, const double *host, long len);
+double abipgpu_qcp_a_coef(const abipgpu_qcp *e);
+void abipgpu_qcp_counters(const abipgpu_qcp *e, long *n_iter, long *n_cg, long *n_inner, double *kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

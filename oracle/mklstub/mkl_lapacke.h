@@ -1,0 +1,1 @@
+#include "mkl_types.h"

@@ -1,0 +1,139 @@
+"""GPU parity tests of the ABIP-QCP engine (through the C ABI) against the oracle (oracle/qcp_oracle.py, pinned to
+the compiled reference) and the golden outputs of the reference's direct (QDLDL) path.
+
+The reference's own pcg path for QCP is unreachable / non-convergent, so parity is defined against
+its direct path: same status, residuals <= eps, objective within 1e-6 relative, ADMM iterations within 5 %.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from abip_b200 import problems
+from abip_b200.qcp import QcpEngine, QSC, qcp_solve_raw, qcp_solve
+from abip_b200 import abip
+from oracle import qcp_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "qcp_golden.json")))
+
+CASES = {
+    "toy_qcp": lambda: problems.toy_qcp(),
+    "mixed_cones_q": lambda: problems.random_qcp(30, 6, 5, n_rsoc=3, rsoc_dim=4, n_free=4, n_lin=10, seed=1),
+    "socp_noq": lambda: problems.random_qcp(40, 10, 6, n_lin=20, seed=2, with_q=False),
+    "qp_lin_only": lambda: problems.random_qcp(50, 0, 0, n_lin=150, seed=3),
+    "soc_dim1_and_big": lambda: problems.random_qcp(20, 1, 60, n_lin=5, seed=4),
+    "rsoc_only": lambda: problems.random_qcp(25, 0, 0, n_rsoc=12, rsoc_dim=5, seed=6),
+    "cfg3_scale0.003": lambda: problems.cfg3(scale=0.003),
+    "cfg3_scale0.01": lambda: problems.cfg3(scale=0.01),
+}
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / (np.max(np.abs(b)) + 1e-300))
+
+
+def make_pair(p, **kw):
+    st = O.Settings(eps_p=1e-4, eps_d=1e-4, eps_g=1e-4, **kw)
+    w = O.Work(p.A, p.Q, p.b, p.c, p.K, st, "direct")
+    e = QcpEngine(w.A, w.Q, w.b, w.c, w.D, w.E, p.K, rho_x=st.rho_x, rho_y=st.rho_y, rho_tau=st.rho_tau,
+                  alpha=st.alpha, rtol=1e-10)
+    return w, e, st
+
+
+@pytest.mark.parametrize("name", ["toy_qcp", "mixed_cones_q", "socp_noq", "cfg3_scale0.003"])
+def test_linear_solve_and_precalc(name):
+    """K^-1 through the m-space Schur PCG vs the exact factorisation of the reference's KKT matrix
+    (qcp_config.c:699-748), incl. r = K^-1[-b; c] and a (abip.c:886-910)."""
+    p = CASES[name]()
+    w, e, st = make_pair(p)
+    assert rel(e.get("r"), w.r) < 1e-7
+    assert abs(e.a_coef() - w.a) < 1e-7 * abs(w.a)
+    rng = np.random.default_rng(0)
+    for warm in (None, rng.standard_normal(p.m)):
+        b = rng.standard_normal(p.m + p.n)
+        ref = b.copy()
+        w.solve_linsys(ref, None, 0)
+        got, sc = e.solve_vec(b, warm, rtol=1e-11)
+        assert rel(got, ref) < 1e-7, (name, rel(got, ref), sc[0])
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["toy_qcp", "mixed_cones_q", "socp_noq", "rsoc_only", "soc_dim1_and_big"])
+def test_iterations_stepwise(name):
+    """25 inner iterations at fixed (mu, beta): u, v, u_t, the inner convergence value and the residuals."""
+    p = CASES[name]()
+    w, e, st = make_pair(p)
+    w.mu, w.beta = 0.3, 1.0
+    r = O.Residuals()
+    for k in range(25):
+        O.projection(w, k)
+        O.solve_barrier_subproblem(w)
+        O.update_dual_vars(w)
+        sc = e.iter(k, w.mu, w.beta)
+        assert rel(e.get("ut"), w.u_t) < 1e-6, (k, "ut")
+        assert rel(e.get("u"), w.u) < 1e-6, (k, "u")
+        assert rel(e.get("v"), w.v) < 1e-6 * (1 + np.max(np.abs(w.u)) / (np.max(np.abs(w.v)) + 1e-300)), (k, "v")
+        err = O.inner_conv_check(w)
+        tau = sc[QSC["TAU"]]
+        qu_tau = -sc[QSC["UMU"]] / tau + sc[QSC["YB"]] - sc[QSC["XC"]]
+        vo_tau = sc[QSC["VO_TAU"]]
+        err_gpu = math.sqrt(sc[QSC["S_DIFF"]] + (qu_tau - vo_tau) ** 2) / (
+            1 + math.sqrt(sc[QSC["S_QU"]] + qu_tau ** 2) + math.sqrt(sc[QSC["S_VO"]] + vo_tau ** 2))
+        assert abs(err_gpu - err) < 1e-5 * err + 1e-10, (k, err_gpu, err)
+        O.calc_residuals(w, r, k + 1)
+        this_pr = sc[QSC["AXB_D_INF"]] / (w.sc_b + max(sc[QSC["AX_D_INF"]], w.sc_b * w.nm_inf_b))
+        this_dr = sc[QSC["RESD_E_INF"]] / (w.sc_c + max(w.sc_c * w.nm_inf_c, sc[QSC["QX_E_INF"]]))
+        assert abs(this_pr - r.res_pri) < 1e-5 * r.res_pri + 1e-12
+        assert abs(this_dr - r.res_dual) < 1e-5 * r.res_dual + 1e-12
+        e.set("u", w.u)
+        e.set("v", w.v)
+    e.close()
+
+
+def _in_cone(x, K, tol):
+    pos = 0
+    for d in K.get("q", []) or []:
+        if d:
+            assert x[pos] >= np.linalg.norm(x[pos + 1:pos + d]) - tol
+        pos += d
+    for d in K.get("rq", []) or []:
+        assert 2 * x[pos] * x[pos + 1] >= x[pos + 2:pos + d] @ x[pos + 2:pos + d] - tol and x[pos] >= -tol
+        pos += d
+    pos += (K.get("f", 0) or 0) + (K.get("z", 0) or 0)
+    ll = K.get("l", 0) or 0
+    assert (x[pos:pos + ll] >= -tol).all()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_full_solve_against_reference_golden(name):
+    g = GOLD[name]
+    p = CASES[name]()
+    x, y, s, info = qcp_solve_raw(p.A, p.Q, p.b, p.c, p.K, eps_p=1e-4, eps_d=1e-4, eps_g=1e-4, verbose=0)
+    assert info["status"] == g["status"]
+    assert abs(info["admm_iter"] - g["admm_iter"]) <= max(2, 0.05 * g["admm_iter"]), (info["admm_iter"], g["admm_iter"])
+    assert info["ipm_iter"] == g["ipm_iter"]
+    assert abs(info["pobj"] - g["pobj"]) <= 1e-6 * abs(g["pobj"]) + 1e-7
+    assert max(info["pres"], info["dres"], info["gap"]) < 1e-4
+    assert rel(x[:16], g["x_head"][:len(x[:16])]) < 1e-4
+    # size-independent properties of the returned point, recomputed from the ORIGINAL data
+    Qx = p.Q @ x if p.Q is not None else np.zeros(p.n)
+    assert np.max(np.abs(p.A @ x - p.b)) / (1 + max(np.max(np.abs(p.A @ x)), np.max(np.abs(p.b)))) < 2e-4
+    assert np.max(np.abs(Qx - p.A.T @ y + p.c - s)) / (1 + max(np.max(np.abs(Qx)), np.max(np.abs(p.c)))) < 2e-4
+    _in_cone(x, p.K, 1e-6 * (1 + np.max(np.abs(x))))
+    _in_cone(s, {k: v for k, v in p.K.items() if k != "f"} | {"z": p.K.get("f", 0)}, 1e-6 * (1 + np.max(np.abs(s))))
+
+
+def test_abip_entry_dispatches_to_qcp():
+    """abip(data, K, params) picks the QCP solver when K has non-LP cones (scripts/matlab/abip.m:22-28)."""
+    p = CASES["toy_qcp"]()
+    x, y, s, info = abip({"A": p.A, "Q": p.Q, "b": p.b, "c": p.c}, p.K, dict(tol=1e-4, verbose=0))
+    assert info["status"] == "Solved" and info["solver"] == "abip-qcp-b200"
+    assert abs(info["pobj"] - GOLD["toy_qcp"]["pobj"]) < 1e-6
+    # cone dimension mismatch is rejected like validate_cones (cones.c:37-45)
+    bad = dict(p.K)
+    bad["l"] = 5
+    x, y, s, info = qcp_solve(dict(A=p.A, Q=p.Q, b=p.b, c=p.c), bad, dict(verbose=0))
+    assert info["status_val"] == -4 and np.isnan(x).all()
