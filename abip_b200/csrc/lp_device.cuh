@@ -376,6 +376,105 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define PHASE_START(last) do { } while (0)
 #endif
 
+#define GRID_STRIDE(i, N) \
+    for (int i = blockIdx.x * kBlock + threadIdx.x, _gs = gridDim.x * kBlock; i < (N); i += _gs)
+
+// ---------------------------------------------------------------------------------------------------------
+// Multi-GPU: in-kernel collectives over NVLink peer memory (one process per GPU, buffers shared through CUDA IPC).
+// Partition: GPU g owns a block of COLUMNS of A, i.e. a row block of the stored CSR(A'); all
+// m-space vectors (y, PCG p/r/Gp, b, D, M) are replicated, n-space vectors (x, s, c, E) are sharded.  The only
+// vector exchange is the sum of the partial products A_g x_g (m doubles) -- validate() guarantees m <= n, so this
+// is always the smaller vector -- plus a few scalars per ADMM iteration; the PCG scalars need NO communication
+// because every GPU computes them redundantly on bit-identical replicated data.
+// Every rank sums the G contributions in rank order, so all ranks obtain bit-identical results and take the same
+// data-dependent branches.  Flags are sequence numbers: rank r publishes "my contribution #seq is complete" into
+// every peer's flag array; buffers are double-buffered by seq parity (a rank can be at most one collective ahead).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 8;
+constexpr int kCommScalars = 16;
+struct Comm {
+    int G, rank;
+    double* vec[kMaxRanks];               // per rank: [2][m_pad] partial m-vectors (IPC-mapped, own buffer included)
+    double* scal[kMaxRanks];              // per rank: [2][kCommScalars]
+    unsigned long long* flags[kMaxRanks]; // per rank: [kMaxRanks] "rank q has published collective #"
+    unsigned long long* seq;              // local: sequence counter persisted across launches
+    int* err;                             // local: sticky error (peer timeout)
+    long m_pad;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Device-side state of the communicator inside one kernel (registers).
+struct CommState {
+    unsigned long long seq;
+    bool failed;
+};
+
+// publish: local contributions for collective `seq` are complete (caller has executed a grid barrier after the
+// last write); wait until every rank has published.  Ends with all threads of the grid released.
+__device__ __forceinline__ void comm_exchange(const Comm& cm, CommState& st, cg::grid_group& grid) {
+    st.seq += 1;
+    if (blockIdx.x == 0 && threadIdx.x < cm.G) {
+        __threadfence_system();
+        st_release_sys(cm.flags[threadIdx.x] + cm.rank, st.seq);
+    }
+    if (threadIdx.x == 0 && !st.failed) {
+        const long long t0 = clock64();
+        for (int q = 0; q < cm.G; ++q) {
+            while (ld_acquire_sys(cm.flags[cm.rank] + q) < st.seq) {
+                if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died; fail instead of hanging the GPU
+                    *cm.err = 1;
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (*(volatile int*)cm.err) st.failed = true;
+}
+
+// out[i] = sum over ranks of their partial vectors (published in vec[q][parity]); every rank reads all G copies in
+// rank order (remote copies with L1-bypassing loads: peer lines may be stale in the local L1).
+template <class Fn>
+__device__ __forceinline__ void comm_sum_vec(const Comm& cm, CommState& st, cg::grid_group& grid, int m, Fn fn) {
+    grid.sync();  // local partials complete
+    comm_exchange(cm, st, grid);
+    const long off = (long)(st.seq & 1ull) * cm.m_pad;
+    GRID_STRIDE(i, m) {
+        double s = 0.0;
+        for (int q = 0; q < cm.G; ++q) s += __ldcv(cm.vec[q] + off + i);
+        fn(i, s);
+    }
+}
+__device__ __forceinline__ double* comm_vec_slot(const Comm& cm, const CommState& st) {
+    return cm.vec[cm.rank] + (long)((st.seq + 1) & 1ull) * cm.m_pad;  // buffer of the NEXT collective
+}
+
+// vals[k] (identical on every thread of this rank) -> sum over ranks, in rank order
+template <int K>
+__device__ __forceinline__ void comm_sum_scalars(const Comm& cm, CommState& st, cg::grid_group& grid, double (&vals)[K]) {
+    static_assert(K <= kCommScalars, "too many scalars");
+    double* mine = cm.scal[cm.rank] + ((st.seq + 1) & 1ull) * kCommScalars;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int k = 0; k < K; ++k) mine[k] = vals[k];
+    grid.sync();
+    comm_exchange(cm, st, grid);
+    const long off = (long)(st.seq & 1ull) * kCommScalars;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = 0.0;
+        for (int q = 0; q < cm.G; ++q) s += __ldcv(cm.scal[q] + off + k);
+        vals[k] = s;
+    }
+}
+
 // Constant problem data + PCG workspace (kernel parameter, passed by value).
 struct LpCtx {
     int m, n;
@@ -393,6 +492,7 @@ struct LpCtx {
     double* partials;
     double* sc;  // scalar block [ABIPGPU_SC_COUNT]
     double* phase_ns;  // [32] debug phase timing or nullptr
+    Comm comm;         // multi-GPU (comm.G == 1: unused)
 };
 
 struct SolveOut {
@@ -400,8 +500,6 @@ struct SolveOut {
     double tol, res;
 };
 
-#define GRID_STRIDE(i, N) \
-    for (int i = blockIdx.x * kBlock + threadIdx.x, _gs = gridDim.x * kBlock; i < (N); i += _gs)
 
 // ---------------------------------------------------------------------------------------------------------
 // solve_lin_sys on device (reference linsys/indirect.c:393-434 incl. pcg :321-391 and mat_vec :205-220).
@@ -410,9 +508,9 @@ struct SolveOut {
 //   grid.sync() and R.finish<1>() to obtain it.
 // Barriers per solve: 2 + 4 per CG iteration (+1 by the caller).
 // ---------------------------------------------------------------------------------------------------------
-template <bool EPI>
-__device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg::grid_group& grid, double* b,
-                                                  const double* s, long iter, SolveOut& out) {
+template <bool EPI, bool DIST>
+__device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg::grid_group& grid, CommState& cs,
+                                                  double* b, const double* s, long iter, SolveOut& out) {
     const int m = c.m;
     double* by = b;
     double* bx = b + m;
@@ -420,12 +518,23 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
     // S1: by += A bx, accumulating |by|^2 of the *incoming* by for the tolerance (indirect.c:406-409, trap 2);
     //     independent of that, tmp = A' s for the warm-start residual.
     double a1[1] = {0.0};
-    spmv_rows(c.A, bx, R.ws, &c.AT, [&](int row, double a) {
-        const double o = by[row];
-        a1[0] = fma(o, o, a1[0]);
-        by[row] = o + a;
-    });
-    if (s) spmv_rows(c.AT, s, R.ws, &c.A, [&](int row, double a) { c.tmp[row] = a; });
+    if constexpr (!DIST) {
+        spmv_rows(c.A, bx, R.ws, &c.AT, [&](int row, double a) {
+            const double o = by[row];
+            a1[0] = fma(o, o, a1[0]);
+            by[row] = o + a;
+        });
+        if (s) spmv_rows(c.AT, s, R.ws, &c.A, [&](int row, double a) { c.tmp[row] = a; });
+    } else {  // partial product of the local column block, summed over the GPUs
+        double* slot = comm_vec_slot(c.comm, cs);
+        spmv_rows(c.A, bx, R.ws, &c.AT, [&](int row, double a) { slot[row] = a; });
+        if (s) spmv_rows(c.AT, s, R.ws, &c.A, [&](int row, double a) { c.tmp[row] = a; });
+        comm_sum_vec(c.comm, cs, grid, m, [&](int i, double tot) {
+            const double o = by[i];
+            a1[0] = fma(o, o, a1[0]);
+            by[i] = o + tot;
+        });
+    }
     R.block_store<1>(a1);
     grid.sync();
     R.finish<1>(a1);
@@ -435,7 +544,7 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
     // S2: r = by - (rho s + A tmp), x = s (stored in by), z = M r, p = z   (indirect.c:343-365)
     double a2[2] = {0.0, 0.0};
     if (s) {
-        spmv_rows(c.A, c.tmp, R.ws, &c.AT, [&](int row, double a) {
+        auto warm_epi = [&](int row, double a) {
             const double si = s[row];
             const double ri = by[row] - fma(c.rho_y, si, a);
             const double zi = __ldg(c.M + row) * ri;
@@ -444,7 +553,14 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
             c.p[row] = zi;
             a2[0] = fma(ri, ri, a2[0]);
             a2[1] = fma(zi, ri, a2[1]);
-        });
+        };
+        if constexpr (!DIST) {
+            spmv_rows(c.A, c.tmp, R.ws, &c.AT, warm_epi);
+        } else {
+            double* slot = comm_vec_slot(c.comm, cs);
+            spmv_rows(c.A, c.tmp, R.ws, &c.AT, [&](int row, double a) { slot[row] = a; });
+            comm_sum_vec(c.comm, cs, grid, m, warm_epi);
+        }
     } else {
         GRID_STRIDE(i, m) {
             const double ri = by[i];
@@ -471,12 +587,19 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
             PHASE_MARK(c, tl, 4);
             // L2: Gp = A tmp + rho p ; p.Gp
             double d1[1] = {0.0};
-            spmv_rows(c.A, c.tmp, R.ws, &c.AT, [&](int row, double a) {
+            auto gp_epi = [&](int row, double a) {
                 const double pi = c.p[row];
                 const double gp = fma(c.rho_y, pi, a);
                 c.Gp[row] = gp;
                 d1[0] = fma(pi, gp, d1[0]);
-            });
+            };
+            if constexpr (!DIST) {
+                spmv_rows(c.A, c.tmp, R.ws, &c.AT, gp_epi);
+            } else {
+                double* slot = comm_vec_slot(c.comm, cs);
+                spmv_rows(c.A, c.tmp, R.ws, &c.AT, [&](int row, double a) { slot[row] = a; });
+                comm_sum_vec(c.comm, cs, grid, m, gp_epi);
+            }
             R.block_store<1>(d1);
             grid.sync();
             R.finish<1>(d1);
@@ -508,20 +631,41 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
         }
     }
     // S4: bx = -bx + A' by   (indirect.c:419-420)
-    double a3[1] = {0.0};
+    // (DIST: slot 0 = replicated y part, slot 1 = local x part, summed over the GPUs by the caller)
+    double a3[2] = {0.0, 0.0};
     spmv_rows(c.AT, by, R.ws, &c.A, [&](int row, double a) {
         const double nv = a - bx[row];
         bx[row] = nv;
-        if (EPI) a3[0] = fma(nv, __ldg(c.h + m + row), a3[0]);
+        if (EPI) a3[DIST ? 1 : 0] = fma(nv, __ldg(c.h + m + row), a3[DIST ? 1 : 0]);
     });
     if (EPI) {
         GRID_STRIDE(i, m) a3[0] = fma(by[i], __ldg(c.h + i), a3[0]);
-        R.block_store<1>(a3);
+        if constexpr (DIST) R.block_store<2>(a3);
+        else {
+            double a31[1] = {a3[0]};
+            R.block_store<1>(a31);
+        }
     }
     PHASE_MARK(c, tl, 8);
     out.its = its;
     out.tol = tol;
     out.res = rn;
+}
+
+// finishes the epilogue dot u_t[0:l-1].h started by dev_solve_lin_sys<EPI = true> (call after a grid barrier)
+template <bool DIST>
+__device__ __forceinline__ double dev_finish_epi_dot(const LpCtx& c, Reducer& R, cg::grid_group& grid, CommState& cs) {
+    if constexpr (!DIST) {
+        double hd[1];
+        R.finish<1>(hd);
+        return hd[0];
+    } else {
+        double hd[2];
+        R.finish<2>(hd);
+        double x[1] = {hd[1]};
+        comm_sum_scalars<1>(c.comm, cs, grid, x);
+        return hd[0] + x[0];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -530,12 +674,13 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
 // Optionally records u_prev = u on the (x,tau) tail (abip.c:2133; only the tail is ever read back).
 // Ends with a grid barrier.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dev_build_rhs(const LpCtx& c, Reducer& R, cg::grid_group& grid, const double* u,
-                                              const double* v, double* ut, double* u_prev_out) {
+template <bool DIST>
+__device__ __forceinline__ void dev_build_rhs(const LpCtx& c, Reducer& R, cg::grid_group& grid, CommState& cs,
+                                              const double* u, const double* v, double* ut, double* u_prev_out) {
     const int m = c.m, lm1 = c.m + c.n;
     spmv_prefetch(c.A, R.ws);  // the solve that follows starts with A; its first chunks stream in meanwhile
     const double tt = u[lm1] + v[lm1];
-    double a[1] = {0.0};
+    double a[2] = {0.0, 0.0};  // DIST: [replicated y part, local x part]
     GRID_STRIDE(i, lm1) {
         const double ui = u[i];
         double w = ui + v[i];
@@ -543,16 +688,29 @@ __device__ __forceinline__ void dev_build_rhs(const LpCtx& c, Reducer& R, cg::gr
         else if (u_prev_out) u_prev_out[i] = ui;
         w = fma(-tt, __ldg(c.h + i), w);
         ut[i] = w;
-        a[0] = fma(w, __ldg(c.g + i), a[0]);
+        const int slot = (DIST && i >= m) ? 1 : 0;
+        a[slot] = fma(w, __ldg(c.g + i), a[slot]);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         ut[lm1] = tt;
         if (u_prev_out) u_prev_out[lm1] = u[lm1];
     }
-    R.block_store<1>(a);
-    grid.sync();
-    R.finish<1>(a);
-    const double coef = -a[0] / (c.g_th + 1.0);
+    double dot;
+    if constexpr (!DIST) {
+        double a1[1] = {a[0]};
+        R.block_store<1>(a1);
+        grid.sync();
+        R.finish<1>(a1);
+        dot = a1[0];
+    } else {
+        R.block_store<2>(a);
+        grid.sync();
+        R.finish<2>(a);
+        double x[1] = {a[1]};
+        comm_sum_scalars<1>(c.comm, cs, grid, x);
+        dot = a[0] + x[0];
+    }
+    const double coef = -dot / (c.g_th + 1.0);
     GRID_STRIDE(i, lm1) {
         double w = fma(coef, __ldg(c.h + i), ut[i]);
         if (i >= m) w = -w;

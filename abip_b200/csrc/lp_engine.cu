@@ -24,15 +24,16 @@ struct IterArgs {
 
 // Q-norm / residual sums for one (u, v) pair: src/abip.c:1964-1992 (unweighted) and :385-456 (D/E weighted).
 // Writes 11 partial sums into reducer slots [slot0, slot0+11).
-__device__ __forceinline__ void dev_qnorm_sums(const LpCtx& c, Reducer& R, const double* u, const double* v,
-                                               int half, int slot0, bool more) {
+template <bool DIST>
+__device__ __forceinline__ void dev_qnorm_sums(const LpCtx& c, Reducer& R, cg::grid_group& grid, CommState& cs,
+                                               const double* u, const double* v, int half, int slot0, bool more) {
     const int m = c.m, n = c.n;
     const double tau = u[m + n];
     const double* y = u;
     const double* x = u + m;
     const double* s = v + m;
     double a[5] = {0, 0, 0, 0, 0};  // S_PR, W_AX, W_PR, BTY, UU_Y
-    spmv_rows(c.A, x, R.ws, &c.AT, [&](int row, double ax) {
+    auto a_epi = [&](int row, double ax) {
         const double bi = __ldg(c.b + row);
         const double pr = fma(-bi, tau, ax);
         double d2 = 1.0;
@@ -43,7 +44,14 @@ __device__ __forceinline__ void dev_qnorm_sums(const LpCtx& c, Reducer& R, const
         a[2] = fma(pr * pr, d2, a[2]);
         a[3] = fma(bi, yi, a[3]);
         a[4] = fma(yi, yi, a[4]);
-    });
+    };
+    if constexpr (!DIST) {
+        spmv_rows(c.A, x, R.ws, &c.AT, a_epi);
+    } else {
+        double* slot = comm_vec_slot(c.comm, cs);
+        spmv_rows(c.A, x, R.ws, &c.AT, [&](int row, double ax) { slot[row] = ax; });
+        comm_sum_vec(c.comm, cs, grid, m, a_epi);
+    }
     R.block_store<5>(a, slot0);
     double d[6] = {0, 0, 0, 0, 0, 0};  // S_DR, W_ATYS, W_DR, CTX, UU_X, VV
     spmv_rows(c.AT, y, R.ws, more ? &c.A : nullptr, [&](int row, double aty) {
@@ -75,20 +83,22 @@ __device__ __forceinline__ void write_qnorm_sc(double* sc, int base, const doubl
 }
 
 // One full inner ADMM iteration (src/abip.c:2133-2173).
+template <bool DIST>
 __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_admm_iter(LpCtx c, IterArgs a) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Reducer R = make_reducer(smem_raw, c.partials);
+    CommState cs{DIST ? *c.comm.seq : 0ull, false};
     const int m = c.m, lm1 = c.m + c.n, l = lm1 + 1;
 
     PHASE_START(tk);
-    dev_build_rhs(c, R, grid, a.u, a.v, a.ut, a.u_prev);
+    dev_build_rhs<DIST>(c, R, grid, cs, a.u, a.v, a.ut, a.u_prev);
     PHASE_MARK(c, tk, 0);
     SolveOut so;
-    dev_solve_lin_sys<true>(c, R, grid, a.ut, a.u, a.k, so);
+    dev_solve_lin_sys<true, DIST>(c, R, grid, cs, a.ut, a.u, a.k, so);
     grid.sync();
     double hd[1];
-    R.finish<1>(hd);
+    hd[0] = dev_finish_epi_dot<DIST>(c, R, grid, cs);
     PHASE_START(tk2);
     const double lam = a.mu / a.beta;
     const double al = c.alpha;
@@ -149,8 +159,8 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_admm_iter(Lp
 
     // iterate_Q_norm_resd sums (abip.c:1951-2051); every 10th inner iteration also on the running average
     const int has_avg = ((a.j + 1) % 10 == 0) ? 1 : 0;
-    dev_qnorm_sums(c, R, a.u, a.v, a.half_update, 0, has_avg != 0);
-    if (has_avg) dev_qnorm_sums(c, R, a.u_avgc, a.v_avgc, a.half_update, 11, false);
+    dev_qnorm_sums<DIST>(c, R, grid, cs, a.u, a.v, a.half_update, 0, has_avg != 0);
+    if (has_avg) dev_qnorm_sums<DIST>(c, R, grid, cs, a.u_avgc, a.v_avgc, a.half_update, 11, false);
     R.ws.drain();
     grid.sync();
     double t[22];
@@ -159,6 +169,16 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_admm_iter(Lp
         double t11[11];
         R.finish<11>(t11);
         for (int q = 0; q < 11; ++q) t[q] = t11[q];
+    }
+    if constexpr (DIST) {  // the six x-block sums (slots 5..10, 16..21) are local: sum them over the GPUs
+        double x[12];
+        for (int q = 0; q < 6; ++q) { x[q] = t[5 + q]; x[6 + q] = has_avg ? t[16 + q] : 0.0; }
+        comm_sum_scalars<12>(c.comm, cs, grid, x);
+        for (int q = 0; q < 6; ++q) { t[5 + q] = x[q]; if (has_avg) t[16 + q] = x[6 + q]; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            *c.comm.seq = cs.seq;
+            c.sc[ABIPGPU_SC_COMM_ERR] = cs.failed ? 1.0 : 0.0;
+        }
     }
     PHASE_MARK(c, tk2, 10);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -181,19 +201,20 @@ struct BBArgs {
 // One ADMM step as written inside update_adapt_params (src/adaptive.c:89-123 / :126-156): from (up, vp) produce
 // (ut, un, vn).  When `dots` is set, also reduces the 5 BB inner products of :158-178 where
 // (u_mid, v_mid, v_first) = (up, vp, v_prev of the round).
-__device__ __forceinline__ void dev_bb_half(const LpCtx& c, Reducer& R, cg::grid_group& grid, const double* up,
-                                            const double* vp, double* ut, double* un, double* vn, long k, double lam,
-                                            const double* v_first, bool dots, int& its) {
+template <bool DIST>
+__device__ __forceinline__ void dev_bb_half(const LpCtx& c, Reducer& R, cg::grid_group& grid, CommState& cs,
+                                            const double* up, const double* vp, double* ut, double* un, double* vn,
+                                            long k, double lam, const double* v_first, bool dots, int& its) {
     const int m = c.m, lm1 = c.m + c.n, l = lm1 + 1;
-    dev_build_rhs(c, R, grid, up, vp, ut, nullptr);
+    dev_build_rhs<DIST>(c, R, grid, cs, up, vp, ut, nullptr);
     SolveOut so;
-    dev_solve_lin_sys<true>(c, R, grid, ut, up, k, so);
+    dev_solve_lin_sys<true, DIST>(c, R, grid, cs, ut, up, k, so);
     its = so.its;
     grid.sync();
     double hd[1];
-    R.finish<1>(hd);
+    hd[0] = dev_finish_epi_dot<DIST>(c, R, grid, cs);
     const double al = c.alpha;
-    double d[5] = {0, 0, 0, 0, 0};  // utut, utv, uu, vv, uv
+    double d[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // utut, utv, uu, vv, uv (DIST: +5 = local x part)
     GRID_STRIDE(i, l) {
         double uti = ut[i];
         if (i == lm1) {  // only the owner of the tau entry reads/writes it (no cross-block hazard)
@@ -217,27 +238,45 @@ __device__ __forceinline__ void dev_bb_half(const LpCtx& c, Reducer& R, cg::grid
             const double dut = 2.0 * vpi + uo - upi - vo - v_first[i];
             const double du = upi - uo;
             const double dv = (uo - upi) * (al - 1.0) + vo - vpi;
-            d[0] = fma(dut, dut, d[0]);
-            d[1] = fma(dut, dv, d[1]);
-            d[2] = fma(du, du, d[2]);
-            d[3] = fma(dv, dv, d[3]);
-            d[4] = fma(du, dv, d[4]);
+            const int o = (DIST && i >= m && i != lm1) ? 5 : 0;  // y and tau entries are replicated
+            d[o + 0] = fma(dut, dut, d[o + 0]);
+            d[o + 1] = fma(dut, dv, d[o + 1]);
+            d[o + 2] = fma(du, du, d[o + 2]);
+            d[o + 3] = fma(dv, dv, d[o + 3]);
+            d[o + 4] = fma(du, dv, d[o + 4]);
         }
     }
-    if (dots) R.block_store<5>(d);
+    if (dots) {
+        if constexpr (DIST) R.block_store<10>(d);
+        else {
+            double d5[5] = {d[0], d[1], d[2], d[3], d[4]};
+            R.block_store<5>(d5);
+        }
+    }
     grid.sync();
     if (dots) {
-        R.finish<5>(d);
+        if constexpr (DIST) {
+            R.finish<10>(d);
+            double x[5] = {d[5], d[6], d[7], d[8], d[9]};
+            comm_sum_scalars<5>(c.comm, cs, grid, x);
+            for (int q = 0; q < 5; ++q) d[q] += x[q];
+        } else {
+            double d5[5];
+            R.finish<5>(d5);
+            for (int q = 0; q < 5; ++q) d[q] = d5[q];
+        }
         if (blockIdx.x == 0 && threadIdx.x == 0)
             for (int q = 0; q < 5; ++q) c.sc[ABIPGPU_SC_BB_UTUT + q] = d[q];
     }
 }
 
 // One lookback round of the Barzilai-Borwein search (src/adaptive.c:89-178).
+template <bool DIST>
 __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_bb_round(LpCtx c, BBArgs a) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Reducer R = make_reducer(smem_raw, c.partials);
+    CommState cs{DIST ? *c.comm.seq : 0ull, false};
     const int m = c.m, l = c.m + c.n + 1;
     const double lam = a.mu / a.beta_prev;
     if (a.carry) {  // state hand-over of the previous round (adaptive.c:230-247)
@@ -249,9 +288,13 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_bb_round(LpC
         grid.sync();
     }
     int its1, its2;
-    dev_bb_half(c, R, grid, a.u_prev, a.v_prev, a.ut, a.u, a.v, a.k, lam, nullptr, false, its1);
-    dev_bb_half(c, R, grid, a.u, a.v, a.ut_next, a.u_next, a.v_next, a.k, lam, a.v_prev, true, its2);
-    R.ws.drain();  // no bulk copy may be outstanding when the CTA exits
+    dev_bb_half<DIST>(c, R, grid, cs, a.u_prev, a.v_prev, a.ut, a.u, a.v, a.k, lam, nullptr, false, its1);
+    dev_bb_half<DIST>(c, R, grid, cs, a.u, a.v, a.ut_next, a.u_next, a.v_next, a.k, lam, a.v_prev, true, its2);
+    R.ws.drain();  // no asynchronous copy may be outstanding when the CTA exits
+    if (DIST && blockIdx.x == 0 && threadIdx.x == 0) {
+        *c.comm.seq = cs.seq;
+        c.sc[ABIPGPU_SC_COMM_ERR] = cs.failed ? 1.0 : 0.0;
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         c.sc[ABIPGPU_SC_CG_ITS] = (double)its1;
         c.sc[ABIPGPU_SC_CG_ITS2] = (double)its2;
@@ -259,28 +302,40 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_bb_round(LpC
 }
 
 // solve_lin_sys on a device vector; post_g: g_x *= -1 and g_th = h.g (src/abip.c:1922-1924)
+template <bool DIST>
 __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
     k_solve_vec(LpCtx c, double* b, const double* s, long iter, int post_g) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Reducer R = make_reducer(smem_raw, c.partials);
+    CommState cs{DIST ? *c.comm.seq : 0ull, false};
     SolveOut so;
     spmv_prefetch(c.A, R.ws);
-    dev_solve_lin_sys<false>(c, R, grid, b, s, iter, so);
+    dev_solve_lin_sys<false, DIST>(c, R, grid, cs, b, s, iter, so);
     R.ws.drain();
     if (post_g) {
         grid.sync();
         const int m = c.m, lm1 = c.m + c.n;
-        double a[1] = {0.0};
+        double a[2] = {0.0, 0.0};
         GRID_STRIDE(i, lm1) {
             double gi = b[i];
             if (i >= m) { gi = -gi; b[i] = gi; }
-            a[0] = fma(__ldg(c.h + i), gi, a[0]);
+            const int slot = (DIST && i >= m) ? 1 : 0;
+            a[slot] = fma(__ldg(c.h + i), gi, a[slot]);
         }
-        R.block_store<1>(a);
+        R.block_store<2>(a);
         grid.sync();
-        R.finish<1>(a);
-        if (blockIdx.x == 0 && threadIdx.x == 0) c.sc[ABIPGPU_SC_VEC_NORM2] = a[0];
+        R.finish<2>(a);
+        if constexpr (DIST) {
+            double x[1] = {a[1]};
+            comm_sum_scalars<1>(c.comm, cs, grid, x);
+            a[1] = x[0];
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) c.sc[ABIPGPU_SC_VEC_NORM2] = a[0] + a[1];
+    }
+    if (DIST && blockIdx.x == 0 && threadIdx.x == 0) {
+        *c.comm.seq = cs.seq;
+        c.sc[ABIPGPU_SC_COMM_ERR] = cs.failed ? 1.0 : 0.0;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         c.sc[ABIPGPU_SC_CG_ITS] = (double)so.its;
@@ -300,7 +355,7 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
 
 // min / sum of u_i v_i over the (x, tau) tail: update_barrier_dynamic, src/abip.c:957-960
 __global__ void __launch_bounds__(kBlock) k_mu_stats(const double* u, const double* v, int m, int l, double* partials,
-                                                     double* sc) {
+                                                     double* sc, Comm comm) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double s_sum[kWarps], s_min[kWarps];
     double sum = 0.0, mn = 1e10;
@@ -325,9 +380,35 @@ __global__ void __launch_bounds__(kBlock) k_mu_stats(const double* u, const doub
         partials[gridDim.x + blockIdx.x] = q;
     }
     grid.sync();
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        double s = 0.0, q = 1e10;
+    double s = 0.0, q = 1e10;
+    if (comm.G > 1 || (blockIdx.x == 0 && threadIdx.x == 0))
         for (int i = 0; i < (int)gridDim.x; ++i) { s += __ldcg(partials + i); q = fmin(q, __ldcg(partials + gridDim.x + i)); }
+    if (comm.G > 1) {
+        // the tau entry (index l-1) is replicated: take it out of the local sums, exchange, add it back once
+        const double xt = u[l - 1] * v[l - 1];
+        CommState cs{*comm.seq, false};
+        double* mine = comm.scal[comm.rank] + ((cs.seq + 1) & 1ull) * kCommScalars;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            // local min over the x shard only (recompute without tau is not possible from the partials: min is
+            // idempotent, so including tau on every rank is harmless); the sum must drop it
+            mine[0] = s - xt;
+            mine[1] = q;
+        }
+        grid.sync();
+        comm_exchange(comm, cs, grid);
+        const long off = (long)(cs.seq & 1ull) * kCommScalars;
+        s = xt;
+        q = 1e10;
+        for (int r = 0; r < comm.G; ++r) {
+            s += __ldcv(comm.scal[r] + off);
+            q = fmin(q, __ldcv(comm.scal[r] + off + 1));
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            *comm.seq = cs.seq;
+            sc[ABIPGPU_SC_COMM_ERR] = cs.failed ? 1.0 : 0.0;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         sc[ABIPGPU_SC_SUM_XS] = s;
         sc[ABIPGPU_SC_MIN_XS] = q;
     }
@@ -411,8 +492,14 @@ struct ABIPGPU_LP {
     ABIPSettings stgs;
     ABIPGpuStats stats;
     double B_A = 0, B_AT = 0;  // algorithmic bytes of one SpMV pass
-    char desc[512];
+    char desc[768];
     bool restart_synced = false;
+    // multi-GPU (column-block partition)
+    int dist_G = 1, dist_rank = 0;
+    long n_global = 0;
+    unsigned char* comm_buf = nullptr;      // [vec 2*m_pad doubles | scal 2*kCommScalars doubles | flags kMaxRanks u64 | seq | err]
+    size_t comm_bytes = 0;
+    void* peer_bufs[kMaxRanks] = {nullptr};
 };
 
 static int coop_grid(const void* kernel, int num_sms, size_t smem, int* out) {
@@ -441,6 +528,10 @@ static int read_sc(abipgpu_lp* e, abip_float* sc) {
     CK(cudaStreamSynchronize(e->stream));
     e->stats.d2h_bytes += sizeof(double) * ABIPGPU_SC_COUNT;
     if (sc) memcpy(sc, e->hsc, sizeof(double) * ABIPGPU_SC_COUNT);
+    if (e->dist_G > 1 && e->hsc[ABIPGPU_SC_COMM_ERR] != 0.0) {
+        fprintf(stderr, "[abip_gpu] rank %d: a peer GPU did not answer (multi-GPU collective timed out)\n", e->dist_rank);
+        return -1;
+    }
     return 0;
 }
 
@@ -509,11 +600,16 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     // persistent grid: a multiple of the SM count, common to all SpMV-bearing kernels
     {
         int g1, g2, g3, g4;
-        if (coop_grid((const void*)k_admm_iter, e->num_sms, kSmemBytes, &g1) ||
-            coop_grid((const void*)k_bb_round, e->num_sms, kSmemBytes, &g2) ||
-            coop_grid((const void*)k_solve_vec, e->num_sms, kSmemBytes, &g3) ||
+        int h1, h2, h3;
+        if (coop_grid((const void*)k_admm_iter<false>, e->num_sms, kSmemBytes, &g1) ||
+            coop_grid((const void*)k_bb_round<false>, e->num_sms, kSmemBytes, &g2) ||
+            coop_grid((const void*)k_solve_vec<false>, e->num_sms, kSmemBytes, &g3) ||
+            coop_grid((const void*)k_admm_iter<true>, e->num_sms, kSmemBytes, &h1) ||
+            coop_grid((const void*)k_bb_round<true>, e->num_sms, kSmemBytes, &h2) ||
+            coop_grid((const void*)k_solve_vec<true>, e->num_sms, kSmemBytes, &h3) ||
             coop_grid((const void*)k_mu_stats, e->num_sms, 0, &g4))
             return -1;
+        g1 = std::min(g1, h1); g2 = std::min(g2, h2); g3 = std::min(g3, h3);
         CK(cudaFuncSetAttribute((const void*)k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         e->grid = std::min(g1, std::min(g2, g3));
         e->grid_mu = g4;
@@ -586,6 +682,8 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     c.tmp = e->tmp;
     c.partials = e->partials;
     c.sc = e->dsc;
+    memset(&c.comm, 0, sizeof(c.comm));
+    c.comm.G = 1;
 #ifdef ABIP_PHASE_TIMING
     c.phase_ns = e->dphase;
 #else
@@ -641,6 +739,9 @@ void abipgpu_lp_destroy(abipgpu_lp* e) {
     cudaFree(e->A_ptr); cudaFree(e->A_idx); cudaFree(e->A_val);
     cudaFree(e->AT_ptr); cudaFree(e->AT_idx); cudaFree(e->AT_val);
     cudaFree(e->A_wc); cudaFree(e->AT_wc); cudaFree(e->A_chunk); cudaFree(e->AT_chunk);
+    for (int q = 0; q < kMaxRanks; ++q)
+        if (e->peer_bufs[q] && q != e->dist_rank) cudaIpcCloseMemHandle(e->peer_bufs[q]);
+    cudaFree(e->comm_buf);
     cudaFree(e->slab);
     if (e->hsc) cudaFreeHost(e->hsc);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -668,7 +769,7 @@ int abipgpu_lp_set_problem(abipgpu_lp* e, const abip_float* b, const abip_float*
     e->ctx.E = e->have_scaling ? e->dE : nullptr;
     k_build_h<<<(m + n + 255) / 256, 256, 0, e->stream>>>(e->db, e->dc, e->vec[ABIPGPU_VEC_H], e->vec[ABIPGPU_VEC_G], m, n);
     CK(cudaGetLastError());
-    if (launch_coop(e, (const void*)k_solve_vec, e->grid, kSmemBytes, e->ctx, e->vec[ABIPGPU_VEC_G], (const double*)nullptr,
+    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_solve_vec<true> : (const void*)k_solve_vec<false>, e->grid, kSmemBytes, e->ctx, e->vec[ABIPGPU_VEC_G], (const double*)nullptr,
                     (long)-1, 1))
         return -1;
     if (read_sc(e, nullptr)) return -1;
@@ -737,7 +838,7 @@ int abipgpu_lp_admm_iter(abipgpu_lp* e, abip_int j, abip_int k, abip_float mu, a
     // both give the same residue class, so the firing rule reduces to (j+1) % fre == 0
     if (a.restart_active && e->stgs.restart_fre > 0 && (j + 1) % e->stgs.restart_fre == 0) a.restart_fire = 1;
     CK(cudaEventRecord(e->ev0, e->stream));
-    if (launch_coop(e, (const void*)k_admm_iter, e->grid, kSmemBytes, e->ctx, a)) return -1;
+    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_admm_iter<true> : (const void*)k_admm_iter<false>, e->grid, kSmemBytes, e->ctx, a)) return -1;
     CK(cudaEventRecord(e->ev1, e->stream));
     if (read_sc(e, sc)) return -1;
     float ms = 0;
@@ -759,7 +860,7 @@ int abipgpu_lp_mu_stats(abipgpu_lp* e, int avg_criterion, abip_float* sc) {
     CK(cudaSetDevice(e->device));
     const double* u = e->vec[avg_criterion ? ABIPGPU_VEC_UAVGC : ABIPGPU_VEC_U];
     const double* v = e->vec[avg_criterion ? ABIPGPU_VEC_VAVGC : ABIPGPU_VEC_V];
-    if (launch_coop(e, (const void*)k_mu_stats, e->grid_mu, (size_t)0, u, v, e->m, e->l, e->partials, e->dsc)) return -1;
+    if (launch_coop(e, (const void*)k_mu_stats, e->grid_mu, (size_t)0, u, v, e->m, e->l, e->partials, e->dsc, e->ctx.comm)) return -1;
     return read_sc(e, sc);
 }
 
@@ -805,7 +906,7 @@ int abipgpu_lp_bb_round(abipgpu_lp* e, int carry, abip_int k, abip_float mu, abi
     a.mu = mu;
     a.beta_prev = beta_prev;
     CK(cudaEventRecord(e->ev0, e->stream));
-    if (launch_coop(e, (const void*)k_bb_round, e->grid, kSmemBytes, e->ctx, a)) return -1;
+    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_bb_round<true> : (const void*)k_bb_round<false>, e->grid, kSmemBytes, e->ctx, a)) return -1;
     CK(cudaEventRecord(e->ev1, e->stream));
     if (read_sc(e, sc)) return -1;
     float ms = 0;
@@ -824,7 +925,7 @@ int abipgpu_lp_solve_vec(abipgpu_lp* e, int rhs_id, int warm_id, abip_int iter, 
     CK(cudaSetDevice(e->device));
     if (rhs_id < 0 || rhs_id > 20 || warm_id > 20) return -1;
     const double* s = warm_id >= 0 ? e->vec[warm_id] : nullptr;
-    if (launch_coop(e, (const void*)k_solve_vec, e->grid, kSmemBytes, e->ctx, e->vec[rhs_id], s, (long)iter, 0)) return -1;
+    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_solve_vec<true> : (const void*)k_solve_vec<false>, e->grid, kSmemBytes, e->ctx, e->vec[rhs_id], s, (long)iter, 0)) return -1;
     if (read_sc(e, sc)) return -1;
     account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], s != nullptr);
     return 0;
@@ -881,7 +982,7 @@ int abipgpu_lp_solve_host(abipgpu_lp* e, double* b, const double* s, long iter, 
     const int mn = e->m + e->n;
     CK(cudaMemcpyAsync(e->xin, b, sizeof(double) * mn, cudaMemcpyHostToDevice, e->stream));
     if (s) CK(cudaMemcpyAsync(e->yout, s, sizeof(double) * e->m, cudaMemcpyHostToDevice, e->stream));
-    if (launch_coop(e, (const void*)k_solve_vec, e->grid, kSmemBytes, e->ctx, e->xin, (const double*)(s ? e->yout : nullptr),
+    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_solve_vec<true> : (const void*)k_solve_vec<false>, e->grid, kSmemBytes, e->ctx, e->xin, (const double*)(s ? e->yout : nullptr),
                     iter, 0))
         return -1;
     CK(cudaMemcpyAsync(b, e->xin, sizeof(double) * mn, cudaMemcpyDeviceToHost, e->stream));
@@ -892,6 +993,68 @@ int abipgpu_lp_solve_host(abipgpu_lp* e, double* b, const double* s, long iter, 
     if (cg_its) *cg_its = (int)e->hsc[ABIPGPU_SC_CG_ITS];
     return 0;
 }
+
+// ---- multi-GPU communicator set-up (CUDA IPC): each rank allocates one buffer, exports its handle, and maps the
+// buffers of all peers.  The exchange of the 64-byte handles is the caller's job (torch.distributed all_gather).
+static void comm_layout(long m, size_t* off_scal, size_t* off_flags, size_t* off_seq, size_t* off_err, size_t* total,
+                        long* m_pad) {
+    *m_pad = (m + 31) & ~31L;
+    *off_scal = sizeof(double) * 2 * (size_t)*m_pad;
+    *off_flags = *off_scal + sizeof(double) * 2 * kCommScalars;
+    *off_seq = *off_flags + sizeof(unsigned long long) * kMaxRanks;
+    *off_err = *off_seq + sizeof(unsigned long long);
+    *total = ((*off_err + sizeof(int) + 255) / 256) * 256;
+}
+
+extern "C" int abipgpu_lp_comm_export(abipgpu_lp* e, void* handle64) {
+    CK(cudaSetDevice(e->device));
+    size_t o1, o2, o3, o4, total;
+    long m_pad;
+    comm_layout(e->m, &o1, &o2, &o3, &o4, &total, &m_pad);
+    if (!e->comm_buf) {
+        CK(cudaMalloc((void**)&e->comm_buf, total));
+        CK(cudaMemset(e->comm_buf, 0, total));
+        e->comm_bytes = total;
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, e->comm_buf));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+extern "C" int abipgpu_lp_comm_connect(abipgpu_lp* e, int G, int rank, const void* handles /* G x 64 bytes */) {
+    CK(cudaSetDevice(e->device));
+    if (G < 1 || G > kMaxRanks || rank < 0 || rank >= G || !e->comm_buf) return -1;
+    size_t o1, o2, o3, o4, total;
+    long m_pad;
+    comm_layout(e->m, &o1, &o2, &o3, &o4, &total, &m_pad);
+    Comm& cm = e->ctx.comm;
+    cm.G = G;
+    cm.rank = rank;
+    cm.m_pad = m_pad;
+    for (int q = 0; q < G; ++q) {
+        void* base = nullptr;
+        if (q == rank) {
+            base = e->comm_buf;
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const unsigned char*)handles + 64 * q, 64);
+            CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        e->peer_bufs[q] = base;
+        cm.vec[q] = (double*)base;
+        cm.scal[q] = (double*)((unsigned char*)base + o1);
+        cm.flags[q] = (unsigned long long*)((unsigned char*)base + o2);
+    }
+    cm.seq = (unsigned long long*)(e->comm_buf + o3);
+    cm.err = (int*)(e->comm_buf + o4);
+    e->dist_G = G;
+    e->dist_rank = rank;
+    return 0;
+}
+
+extern "C" void abipgpu_lp_set_global_n(abipgpu_lp* e, long n_global) { e->n_global = n_global; }
 
 ABIPGpuStats* abipgpu_lp_stats(abipgpu_lp* e) { return &e->stats; }
 extern "C" int abipgpu_lp_phase_times(abipgpu_lp* e, double* out32, int reset) {  // debug builds (-DABIP_PHASE_TIMING)

@@ -12,3 +12,6 @@ ABIPGpuStats* abipgpu_lp_stats(abipgpu_lp* e);
 int abipgpu_lp_dims(const abipgpu_lp* e, int* m, int* n);
 int abipgpu_lp_sync(abipgpu_lp* e);
 int abipgpu_lp_solve_timer(abipgpu_lp* e, int stop);
+extern "C" int abipgpu_lp_comm_export(abipgpu_lp* e, void* handle64);
+extern "C" int abipgpu_lp_comm_connect(abipgpu_lp* e, int G, int rank, const void* handles);
+extern "C" void abipgpu_lp_set_global_n(abipgpu_lp* e, long n_global);

@@ -277,7 +277,9 @@ struct Resid {  // struct ABIP_RESIDUALS, include/abip.h:178-196
 };
 
 struct ABIP_GPU_WORK {  // device-resident replacement of struct ABIP_WORK (include/abip.h:126-176)
-    abip_int m = 0, n = 0;
+    abip_int m = 0, n = 0;    // global dimensions
+    abip_int c0 = 0, nl = 0;  // multi-GPU: this rank owns columns [c0, c0 + nl) (single GPU: all of them)
+    int dist_G = 1, dist_rank = 0;
     ABIPMatrix* A = nullptr;  // scaled private copy (COPYAMATRIX behaviour, abip.c:1799-1810)
     ABIPScaling scal{nullptr, nullptr, 0, 0};
     bool have_scal = false;
@@ -546,7 +548,7 @@ void print_summary(const ABIP_GPU_WORK* w, abip_int i, abip_int k, const Resid* 
 
 // get_solution + get_info (src/abip.c:1308-1414), un_normalize_sol (src/normalize.c:133-158)
 int get_solution(ABIP_GPU_WORK* w, ABIPSolution* sol, ABIPInfo* info, Resid* r, abip_int ipm_iter, abip_int admm_iter) {
-    const abip_int m = w->m, n = w->n, l = m + n + 1;
+    const abip_int m = w->m, n = w->n, nl = w->nl, l = m + nl + 1;  // l: length of this rank's (u, v)
     calc_residuals(w, r, ipm_iter, admm_iter);
     if (!sol->x) sol->x = (double*)malloc(sizeof(double) * n);
     if (!sol->y) sol->y = (double*)malloc(sizeof(double) * m);
@@ -557,8 +559,11 @@ int get_solution(ABIP_GPU_WORK* w, ABIPSolution* sol, ABIPInfo* info, Resid* r, 
         abipgpu_lp_get_vec(w->eng, avg ? ABIPGPU_VEC_VAVGC : ABIPGPU_VEC_V, vv.data(), l) != 0)
         return -1;
     std::copy(uu.begin(), uu.begin() + m, sol->y);
-    std::copy(uu.begin() + m, uu.begin() + m + n, sol->x);
-    std::copy(vv.begin() + m, vv.begin() + m + n, sol->s);
+    // multi-GPU: each rank returns its own column shard of x and s (zeros elsewhere; the caller sums the shards)
+    std::fill(sol->x, sol->x + n, 0.0);
+    std::fill(sol->s, sol->s + n, 0.0);
+    std::copy(uu.begin() + m, uu.begin() + m + nl, sol->x + w->c0);
+    std::copy(vv.begin() + m, vv.begin() + m + nl, sol->s + w->c0);
     enum { SOLVED, INDET, INFEAS, UNBDD } kind;
     const abip_int sv = info->status_val;
     if (sv == ABIP_UNFINISHED) {
@@ -646,7 +651,47 @@ void abip_gpu_set_default_settings(ABIPData* d) {  // src/util.c:288-329, mexfil
     s->max_time = 3600; s->pfeasopt = 0;
 }
 
-ABIPGpuWork* abip_gpu_init(const ABIPData* d, ABIPInfo* info) {  // ABIP(init) + init_work, abip.c:1739-1841, 2341-2389
+static ABIPGpuWork* gpu_init_impl(const ABIPData* d, ABIPInfo* info, int rank, int G);
+
+// contiguous column blocks balanced by nonzeros: rank r owns columns [c0, c0 + nl)
+void abip_gpu_column_partition(abip_int n, const abip_int* Ap, abip_int world, abip_int rank, abip_int* c0, abip_int* nl) {
+    const abip_int nnz = Ap[n];
+    auto cut = [&](abip_int r) {
+        if (r >= world) return n;
+        const double target = (double)nnz * (double)r / (double)world;
+        abip_int lo = 0, hi = n;
+        while (lo < hi) {
+            const abip_int mid = (lo + hi) / 2;
+            if ((double)Ap[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    *c0 = cut(rank);
+    *nl = cut(rank + 1) - *c0;
+}
+
+ABIPGpuWork* abip_gpu_init(const ABIPData* d, ABIPInfo* info) { return gpu_init_impl(d, info, 0, 1); }
+
+// Multi-GPU (one process per GPU): every rank passes the FULL problem; the equilibration is computed redundantly on
+// every rank (identical D, E), then rank r keeps a contiguous block of columns balanced by nonzeros.  The caller
+// must then exchange the IPC handles: abip_gpu_comm_export on every rank, all-gather, abip_gpu_comm_connect.
+ABIPGpuWork* abip_gpu_init_dist(const ABIPData* d, ABIPInfo* info, abip_int rank, abip_int world) {
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return nullptr;
+    return gpu_init_impl(d, info, (int)rank, (int)world);
+}
+
+abip_int abip_gpu_comm_export(ABIPGpuWork* w, void* handle64) { return abipgpu_lp_comm_export(w->eng, handle64); }
+
+abip_int abip_gpu_comm_connect(ABIPGpuWork* w, const void* handles) {
+    return abipgpu_lp_comm_connect(w->eng, w->dist_G, w->dist_rank, handles);
+}
+
+void abip_gpu_partition(const ABIPGpuWork* w, abip_int* c0, abip_int* nl) {
+    *c0 = w->c0;
+    *nl = w->nl;
+}
+
+static ABIPGpuWork* gpu_init_impl(const ABIPData* d, ABIPInfo* info, int rank, int G) {  // ABIP(init) + init_work, abip.c:1739-1841, 2341-2389
     if (!d || !info) {
         printf("ERROR: Missing ABIPData or ABIPInfo input\n");
         return nullptr;
@@ -686,11 +731,46 @@ ABIPGpuWork* abip_gpu_init(const ABIPData* d, ABIPInfo* info) {  // ABIP(init) +
         w->have_scal = true;
     }
     const char* dev = getenv("ABIP_GPU_DEVICE");
-    w->eng = abipgpu_lp_create(w->m, w->n, w->A->p, w->A->i, w->A->x, &w->stgs, dev ? atoi(dev) : 0);
+    w->dist_G = G;
+    w->dist_rank = rank;
+    w->c0 = 0;
+    w->nl = w->n;
+    if (G > 1) {  // contiguous column blocks balanced by nonzeros
+        if (w->stgs.half_update) {
+            printf("ERROR: half_update is not supported by the multi-GPU engine\n");
+            abip_gpu_finish(w);
+            return nullptr;
+        }
+        abip_gpu_column_partition(w->n, w->A->p, G, rank, &w->c0, &w->nl);
+        if (w->nl <= 0) {
+            printf("ERROR: empty column block on rank %d\n", rank);
+            abip_gpu_finish(w);
+            return nullptr;
+        }
+    }
+    {
+        const abip_int p0 = w->A->p[w->c0];
+        std::vector<abip_int> lp(w->nl + 1);
+        for (abip_int j = 0; j <= w->nl; ++j) lp[j] = w->A->p[w->c0 + j] - p0;
+        w->eng = abipgpu_lp_create(w->m, w->nl, lp.data(), w->A->i + p0, w->A->x + p0, &w->stgs, dev ? atoi(dev) : 0);
+    }
     if (!w->eng) {
         printf("ERROR: init_lin_sys_work failure\n");
         abip_gpu_finish(w);
         return nullptr;
+    }
+    abipgpu_lp_set_global_n(w->eng, w->n);
+    if (G > 1) {
+        // the Jacobi preconditioner M = 1/diag(AA') (indirect.c:36-79) involves ALL columns: replace the engine's
+        // local one by the global diagonal so that the replicated PCG is identical on every rank
+        std::vector<double> M(w->m, 0.0);
+        const abip_int nnz = w->A->p[w->n];
+        for (abip_int k = 0; k < nnz; ++k) M[w->A->i[k]] += w->A->x[k] * w->A->x[k];
+        for (abip_int i = 0; i < w->m; ++i) M[i] = 1.0 / M[i];
+        if (abipgpu_lp_set_vec(w->eng, ABIPGPU_VEC_M, M.data(), w->m) != 0) {
+            abip_gpu_finish(w);
+            return nullptr;
+        }
     }
     if (d->stgs->verbose) {
         char buf[512];
@@ -749,8 +829,8 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
         printf("WARN: warm_start behaves as in the reference build: iterates restart from sqrt(mu/beta)\n");
     }
     if (abipgpu_lp_cold_start(w->eng, w->mu, w->beta) != 0 ||
-        abipgpu_lp_set_problem(w->eng, w->b.data(), w->c.data(), s.normalize ? w->scal.D : nullptr,
-                               s.normalize ? w->scal.E : nullptr) != 0)
+        abipgpu_lp_set_problem(w->eng, w->b.data(), w->c.data() + w->c0, s.normalize ? w->scal.D : nullptr,
+                               s.normalize ? w->scal.E + w->c0 : nullptr) != 0)
         return failure(m, n, sol, info, ABIP_FAILED, "error in update_work", "Failure");
 
     if (s.verbose) print_header_line(w);

@@ -1,0 +1,109 @@
+"""Multi-GPU ABIP-LP: one process per GPU (torchrun), torch.distributed for the plumbing (exchange of the CUDA-IPC
+handles, assembly of the solution shards); the data path runs inside the persistent kernels over NVLink peer memory
+(csrc/lp_device.cuh: comm_sum_vec / comm_sum_scalars) -- no NCCL call inside the solve.
+
+Partition: rank r owns a contiguous block of COLUMNS of A balanced by nonzeros, i.e. a row block of the stored
+CSR(A'); m-space vectors are replicated, n-space vectors sharded."""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+from . import _capi
+from .api import CscHolder, _lp_settings, _fp
+
+
+def column_partition(n: int, Ap: np.ndarray, world: int, rank: int):
+    """[c0, c0 + nl) owned by `rank` (same rule as the C side: abip_gpu_column_partition)."""
+    L = _capi.lib()
+    Ap = np.ascontiguousarray(Ap, dtype=np.int64)
+    c0, nl = C.c_long(), C.c_long()
+    L.abip_gpu_column_partition(int(n), Ap.ctypes.data_as(C.POINTER(C.c_long)), int(world), int(rank), C.byref(c0),
+                                C.byref(nl))
+    return int(c0.value), int(nl.value)
+
+
+def exchange_handles(handle: bytes, group=None) -> bytes:
+    """all-gather of the 64-byte IPC handles, rank order (works with gloo on CPU tensors and nccl on CUDA tensors)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    return b"".join(bytes(t.cpu().tolist()) for t in out)
+
+
+def assemble_shards(local: np.ndarray, group=None) -> np.ndarray:
+    """sum of the zero-padded shards = full vector, on every rank"""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+class LpSolverDist:
+    """Collective counterpart of LpSolver: every rank constructs it with the FULL problem and calls solve()."""
+
+    def __init__(self, A, params: dict | None = None, group=None, **raw_settings):
+        import torch.distributed as dist
+        self.L = _capi.lib()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.p, self.st = _lp_settings(params, **raw_settings)
+        self.H = CscHolder(A)
+        self.info = _capi.ABIPInfo()
+        self._b = np.zeros(self.H.m)
+        self._c = np.zeros(self.H.n)
+        self.d = _capi.ABIPData(self.H.m, self.H.n, C.pointer(self.H.c), _fp(self._b), _fp(self._c),
+                                float(self.H.nnz) / (float(self.H.m) * float(self.H.n)), C.pointer(self.st))
+        self.w = self.L.abip_gpu_init_dist(C.byref(self.d), C.byref(self.info), self.rank, self.world)
+        if not self.w:
+            raise RuntimeError("abip_gpu_init_dist failed")
+        buf = (C.c_ubyte * 64)()
+        if self.L.abip_gpu_comm_export(self.w, C.cast(buf, C.c_void_p)) != 0:
+            raise RuntimeError("abip_gpu_comm_export failed")
+        allh = exchange_handles(bytes(buf), group)
+        hb = (C.c_ubyte * len(allh)).from_buffer_copy(allh)
+        if self.L.abip_gpu_comm_connect(self.w, C.cast(hb, C.c_void_p)) != 0:
+            raise RuntimeError("abip_gpu_comm_connect failed")
+        dist.barrier(group)  # every rank has mapped every buffer before the first kernel spins on a flag
+        self.setup_time_ms = self.info.setup_time
+        self._libc = C.CDLL(None)
+        self._libc.free.argtypes = [C.c_void_p]
+
+    def solve(self, b, c):
+        self._b[:] = b
+        self._c[:] = c
+        sol = _capi.ABIPSolution()
+        info = _capi.ABIPInfo()
+        self.L.abip_gpu_solve(self.w, C.byref(self.d), C.byref(sol), C.byref(info))
+        stats = _capi.ABIPGpuStats()
+        self.L.abip_gpu_get_stats(self.w, C.byref(stats))
+        out = {}
+        for name, ln in (("x", self.H.n), ("y", self.H.m), ("s", self.H.n)):
+            ptr = getattr(sol, name)
+            out[name] = np.ctypeslib.as_array(ptr, shape=(ln,)).copy() if ptr else np.full(ln, np.nan)
+            if ptr:
+                self._libc.free(C.cast(ptr, C.c_void_p))
+        x = assemble_shards(out["x"], self.group)
+        s = assemble_shards(out["s"], self.group)
+        res = dict(status=info.status.decode(), status_val=int(info.status_val), ipm_iter=int(info.ipm_iter),
+                   admm_iter=int(info.admm_iter), pres=info.res_pri, dres=info.res_dual, gap=info.rel_gap,
+                   pobj=info.pobj, dobj=info.dobj, solve_time_ms=info.solve_time,
+                   stats={f: getattr(stats, f) for f, _ in stats._fields_})
+        return x, out["y"], s, res
+
+    def close(self):
+        if self.w:
+            self.L.abip_gpu_finish(self.w)
+            self.w = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

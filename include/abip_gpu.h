@@ -170,6 +170,17 @@ abip_int abip_gpu_solve(ABIPGpuWork *w, const ABIPData *d, ABIPSolution *sol, AB
 void abip_gpu_finish(ABIPGpuWork *w);
 abip_int abip_gpu_main(const ABIPData *d, ABIPSolution *sol, ABIPInfo *info);
 
+/* Multi-GPU, one process per GPU (new; the reference is single-process).  Every rank passes the FULL problem to
+ * abip_gpu_init_dist; rank r keeps a block of columns of A (a row block of the stored A').  The ranks then exchange
+ * the 64-byte CUDA-IPC handles (abip_gpu_comm_export -> all-gather -> abip_gpu_comm_connect) and call abip_gpu_solve
+ * collectively; sol->y is complete on every rank, sol->x / sol->s hold this rank's shard [c0, c0+nl) and zeros
+ * elsewhere (sum over ranks = full vectors). */
+ABIPGpuWork *abip_gpu_init_dist(const ABIPData *d, ABIPInfo *info, abip_int rank, abip_int world);
+abip_int abip_gpu_comm_export(ABIPGpuWork *w, void *handle64);
+abip_int abip_gpu_comm_connect(ABIPGpuWork *w, const void *handles /* world x 64 bytes, rank order */);
+void abip_gpu_partition(const ABIPGpuWork *w, abip_int *c0, abip_int *nl);
+void abip_gpu_column_partition(abip_int n, const abip_int *Ap, abip_int world, abip_int rank, abip_int *c0, abip_int *nl);
+
 /* counters of the last abip_gpu_solve on this work (for roofline accounting) */
 typedef struct ABIP_GPU_STATS {
     abip_int n_admm_launch;   /* ADMM-iteration kernel launches */
@@ -223,6 +234,7 @@ enum {
     /* mu statistics: abip.c:957-960 */
     ABIPGPU_SC_MIN_XS = 48, ABIPGPU_SC_SUM_XS = 49,
     ABIPGPU_SC_VEC_NORM2 = 50,
+    ABIPGPU_SC_COMM_ERR = 63, /* multi-GPU: a peer did not answer within the spin limit */
     ABIPGPU_SC_COUNT = 64
 };
 
