@@ -3,7 +3,7 @@
 Product layout: csrc/ (hand-written sm_100a CUDA kernels + the C ABI of include/abip_gpu.h) and the
 host-side mirror of the reference's `abip(data, K, params)` entry (api.py).  No CPU fallback.
 """
-from .api import abip, lp_solve, get_params, LinSysPlugin, LpEngine, LpSolver  # noqa: F401
+from .api import abip, lp_solve, lp_solve_batch, get_params, LinSysPlugin, LpEngine, LpSolver  # noqa: F401
 from . import problems  # noqa: F401
 
-__all__ = ["abip", "lp_solve", "get_params", "LinSysPlugin", "LpEngine", "LpSolver", "problems"]
+__all__ = ["abip", "lp_solve", "get_params", "LinSysPlugin", "LpEngine", "LpSolver", "lp_solve_batch", "problems"]

@@ -176,6 +176,50 @@ class LpSolver:
             pass
 
 
+def lp_solve_batch(problems, params: dict | None = None, concurrency: int = 16, ctas_per_problem: int = 8,
+                   **raw_settings):
+    """Batch of independent LPs on the current GPU (abip_gpu_batch_main).  problems: iterable of objects with
+    csc()/m/n/b/c (abip_b200.problems.LPProblem) or (A, b, c) tuples.  Returns a list of (x, y, s, info)."""
+    L = _capi.lib()
+    p, st0 = _lp_settings(params, **raw_settings)
+    keep, datas = [], []
+    for pr in problems:
+        A, b, c = (pr.csc(), pr.b, pr.c) if hasattr(pr, "csc") else pr
+        H = CscHolder(A)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        st = _capi.ABIPSettings.from_buffer_copy(st0)
+        d = _capi.ABIPData(H.m, H.n, C.pointer(H.c), _fp(b), _fp(c), float(H.nnz) / (float(H.m) * float(H.n)),
+                           C.pointer(st))
+        keep.append((H, b, c, st))
+        datas.append(d)
+    n = len(datas)
+    ptrs = (C.POINTER(_capi.ABIPData) * n)(*[C.pointer(d) for d in datas])
+    sols = (_capi.ABIPSolution * n)()
+    infos = (_capi.ABIPInfo * n)()
+    t0 = time.perf_counter()
+    nfail = L.abip_gpu_batch_main(ptrs, sols, infos, n, int(concurrency), int(ctas_per_problem))
+    wall = time.perf_counter() - t0
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    out = []
+    for i in range(n):
+        H = keep[i][0]
+        vec = {}
+        for name, ln in (("x", H.n), ("y", H.m), ("s", H.n)):
+            ptr = getattr(sols[i], name)
+            vec[name] = np.ctypeslib.as_array(ptr, shape=(ln,)).copy() if ptr else np.full(ln, np.nan)
+            if ptr:
+                libc.free(C.cast(ptr, C.c_void_p))
+        inf = infos[i]
+        out.append((vec["x"], vec["y"], vec["s"],
+                    dict(status=inf.status.decode(), status_val=int(inf.status_val), ipm_iter=int(inf.ipm_iter),
+                         admm_iter=int(inf.admm_iter), pres=inf.res_pri, dres=inf.res_dual, gap=inf.rel_gap,
+                         pobj=inf.pobj, dobj=inf.dobj, solve_time_ms=inf.solve_time, batch_wall_s=wall,
+                         batch_failed=int(nfail))))
+    return out
+
+
 def abip(data: dict, K: dict, params: dict | None = None):
     """[x, y, s, info] = abip(data, K, params) -- scripts/matlab/abip.m:1-30.
 

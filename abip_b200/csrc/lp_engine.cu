@@ -545,6 +545,9 @@ static int upload(T** dst, const std::vector<T>& src, abipgpu_lp* e) {
     return 0;
 }
 
+static thread_local int t_grid_request = 0;  // CTAs per engine (batch mode); 0 = whole device
+extern "C" void abipgpu_lp_request_grid(int ctas) { t_grid_request = ctas; }
+
 static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap, const abip_int* Ai,
                        const abip_float* Ax, const ABIPSettings* stgs, int device) {
     const long nnz = Ap[n];
@@ -613,6 +616,10 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         CK(cudaFuncSetAttribute((const void*)k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         e->grid = std::min(g1, std::min(g2, g3));
         e->grid_mu = g4;
+        if (t_grid_request > 0) {  // batch mode: several small engines share the device
+            e->grid = std::min(e->grid, t_grid_request);
+            e->grid_mu = std::min(e->grid_mu, t_grid_request);
+        }
     }
     const int W = e->grid * kWarps;
     SpmvPlan planA, planAT;

@@ -15,3 +15,4 @@ int abipgpu_lp_solve_timer(abipgpu_lp* e, int stop);
 extern "C" int abipgpu_lp_comm_export(abipgpu_lp* e, void* handle64);
 extern "C" int abipgpu_lp_comm_connect(abipgpu_lp* e, int G, int rank, const void* handles);
 extern "C" void abipgpu_lp_set_global_n(abipgpu_lp* e, long n_global);
+extern "C" void abipgpu_lp_request_grid(int ctas);

@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -952,5 +954,31 @@ abip_int abip_gpu_main(const ABIPData* d, ABIPSolution* sol, ABIPInfo* info) {  
 }
 
 void abip_gpu_get_stats(const ABIPGpuWork* w, ABIPGpuStats* out) { *out = w->last_stats; }
+
+// Batch of independent LPs on ONE GPU (BASELINE.json configs[4]; the reference equivalent is a loop of ABIP(main)
+// calls, one process per core).  `concurrency` host threads pull problems from a shared counter; every problem gets
+// its own engine with a persistent grid of `ctas_per_problem` CTAs on its own stream, so several cooperative kernels
+// share the 148 SMs (concurrency * ctas_per_problem <= SM count keeps all of them co-resident).
+abip_int abip_gpu_batch_main(const ABIPData* const* problems, ABIPSolution* sols, ABIPInfo* infos, abip_int count,
+                             abip_int concurrency, abip_int ctas_per_problem) {
+    if (!problems || !sols || !infos || count <= 0) return -1;
+    if (concurrency < 1) concurrency = 1;
+    std::atomic<long> next{0};
+    std::atomic<long> failed{0};
+    auto worker = [&]() {
+        abipgpu_lp_request_grid((int)ctas_per_problem);
+        for (;;) {
+            const long i = next.fetch_add(1);
+            if (i >= count) break;
+            const abip_int st = abip_gpu_main(problems[i], &sols[i], &infos[i]);
+            if (st == ABIP_FAILED) failed.fetch_add(1);
+        }
+        abipgpu_lp_request_grid(0);
+    };
+    std::vector<std::thread> pool;
+    for (abip_int t = 0; t < concurrency; ++t) pool.emplace_back(worker);
+    for (auto& th : pool) th.join();
+    return (abip_int)failed.load();
+}
 
 }  // extern "C"

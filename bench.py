@@ -48,6 +48,24 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """DRAM bytes of one k_admm_iter launch from the committed ncu --set full capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r01_k_admm_iter_ncu.txt")
+    if not os.path.exists(path):
+        return None
+    rd = wr = None
+    for ln in open(path):
+        if ln.startswith("dram__bytes_read.sum"):
+            v = float(ln.split("=")[1]); rd = v * (1e9 if "Gbyte" in ln else 1e6)
+        if ln.startswith("dram__bytes_write.sum"):
+            v = float(ln.split("=")[1]); wr = v * (1e9 if "Gbyte" in ln else 1e6)
+    if rd is None or wr is None:
+        return None
+    return {"dram_bytes_per_launch": rd + wr,
+            "note": "ncu --set full capture of one k_admm_iter launch with 28 CG iterations (5.17 GB algorithmic), "
+                    "profiles/r01_k_admm_iter_ncu.txt"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -232,6 +250,31 @@ def run_ours(args):
         d2h = inf2["stats"]["d2h_bytes"]
     barrier()
 
+    # N > 1: the same workload as ONE instance sharded over the GPUs (column blocks of A, in-kernel NVLink
+    # peer-memory all-reduce; abip_b200/dist.py) -- strong scaling, reported beside the weak-scaling value
+    sharded = None
+    if world > 1:
+        from abip_b200.dist import LpSolverDist
+        from abip_b200 import problems as _pb
+        p0 = _pb.cfg2(seed=2, scale=args.scale)
+        ds = LpSolverDist(p0.csc(), params)
+        ds.solve(p0.b, p0.c)  # warm-up
+        barrier()
+        sh_ms, sh_its = 0.0, 0
+        for _ in range(args.steps):
+            xs, ys, ss, si = ds.solve(p0.b, p0.c)
+            sh_ms += si["stats"]["solve_event_ms"]
+            sh_its += si["admm_iter"]
+        barrier()
+        ds.close()
+        tsh = torch.tensor([sh_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tsh, op=dist.ReduceOp.MAX)
+        sharded = {"workload": "cfg2 as ONE instance, column blocks of A over %d GPUs" % world,
+                   "value": sh_its / (tsh[0].item() / 1e3), "unit": "iter/s", "scaling": "strong",
+                   "time_to_1e-4_s": tsh[0].item() / args.steps / 1e3, "status": si["status"],
+                   "admm_iter_per_solve": sh_its / args.steps,
+                   "collective": "in-kernel peer-memory sum of the m-vector A_g x_g + scalar blocks (no NCCL in the solve)"}
+
     # max over ranks of the device-timed region; whole-job iterations
     t = torch.tensor([event_ms, float(its), e2e_s, float(e2e_its)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -275,6 +318,12 @@ def run_ours(args):
             "counters": {"cg_iters": int(agg["n_cg_iters"]), "solves": int(agg["n_solves"]),
                          "spmv_A": int(agg["n_spmv_A"]), "spmv_AT": int(agg["n_spmv_AT"])},
         }
+        if sharded is not None:
+            line["sharded_single_instance"] = sharded
+        tr = ncu_traffic()
+        if tr is not None:
+            line["roofline"]["traffic"] = tr["dram_bytes_per_launch"]
+            line["roofline"]["traffic_note"] = tr["note"]
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, p)
         print(json.dumps(line))

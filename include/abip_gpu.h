@@ -181,6 +181,12 @@ abip_int abip_gpu_comm_connect(ABIPGpuWork *w, const void *handles /* world x 64
 void abip_gpu_partition(const ABIPGpuWork *w, abip_int *c0, abip_int *nl);
 void abip_gpu_column_partition(abip_int n, const abip_int *Ap, abip_int world, abip_int rank, abip_int *c0, abip_int *nl);
 
+/* Batch of independent LPs on one GPU (configs[4]): `concurrency` host threads, each problem on its own stream with a
+ * persistent grid of `ctas_per_problem` CTAs.  Returns the number of failed problems (< 0: bad arguments).
+ * The reference equivalent is a loop of ABIP(main) calls (one process per core). */
+abip_int abip_gpu_batch_main(const ABIPData *const *problems, ABIPSolution *sols, ABIPInfo *infos, abip_int count,
+                             abip_int concurrency, abip_int ctas_per_problem);
+
 /* counters of the last abip_gpu_solve on this work (for roofline accounting) */
 typedef struct ABIP_GPU_STATS {
     abip_int n_admm_launch;   /* ADMM-iteration kernel launches */

@@ -12,7 +12,7 @@ dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 case = sys.argv[1] if len(sys.argv) > 1 else 'small'
 p = {'small': lambda: problems.random_lp(200, 700, 4, seed=3), 'mcf': lambda: problems.mcf_lp(4, 40, 200, 6, 300, seed=6),
      'cfg1': problems.cfg1, 'cfg2s': lambda: problems.cfg2(scale=0.05), 'cfg2': problems.cfg2,
-     'cfg4s': lambda: problems.cfg4(scale=0.1), 'cfg4': problems.cfg4}[case]()
+     'cfg4s': lambda: problems.cfg4(scale=float(os.environ.get('CFG4_SCALE', '0.25'))), 'cfg4': problems.cfg4}[case]()
 print('rank', rank, 'init...', flush=True)
 sol = LpSolverDist(p.csc(), dict(tol=1e-4, verbose=int(os.environ.get('VERB', 0))))
 print('rank', rank, 'connected', flush=True)
