@@ -395,6 +395,7 @@ constexpr int kCommScalars = 16;
 struct Comm {
     int G, rank;
     double* vec[kMaxRanks];               // per rank: [2][m_pad] partial m-vectors (IPC-mapped, own buffer included)
+    double* red[kMaxRanks];               // per rank: [m_pad] reduced slice (two-step all-reduce, G > 2)
     double* scal[kMaxRanks];              // per rank: [2][kCommScalars]
     unsigned long long* flags[kMaxRanks]; // per rank: [kMaxRanks] "rank q has published collective #"
     unsigned long long* seq;              // local: sequence counter persisted across launches
@@ -440,17 +441,52 @@ __device__ __forceinline__ void comm_exchange(const Comm& cm, CommState& st, cg:
     if (*(volatile int*)cm.err) st.failed = true;
 }
 
-// out[i] = sum over ranks of their partial vectors (published in vec[q][parity]); every rank reads all G copies in
-// rank order (remote copies with L1-bypassing loads: peer lines may be stale in the local L1).
+// out[i] = sum over ranks of their partial vectors (published in vec[q][parity]), applied through fn(i, sum).
+//   G <= 2: every rank reads all copies in rank order (one exchange, (G-1) m doubles over NVLink);
+//   G  > 2: reduce-scatter + all-gather (two exchanges, 2 (G-1)/G m doubles): rank r sums its slice of the rows
+//           from all peers into its `red` buffer, then every rank collects the G reduced slices.
+// Remote copies are read with L1-bypassing loads (peer lines may be stale in the local L1).  Either way each
+// element is the same rank-ordered sum on every rank.
 template <class Fn>
 __device__ __forceinline__ void comm_sum_vec(const Comm& cm, CommState& st, cg::grid_group& grid, int m, Fn fn) {
     grid.sync();  // local partials complete
     comm_exchange(cm, st, grid);
     const long off = (long)(st.seq & 1ull) * cm.m_pad;
-    GRID_STRIDE(i, m) {
-        double s = 0.0;
-        for (int q = 0; q < cm.G; ++q) s += __ldcv(cm.vec[q] + off + i);
-        fn(i, s);
+    if (cm.G <= 2) {
+        GRID_STRIDE(i, m) {
+            double s = 0.0;
+            for (int q = 0; q < cm.G; ++q) s += __ldcv(cm.vec[q] + off + i);
+            fn(i, s);
+        }
+    } else {
+        const int sl = (m + cm.G - 1) / cm.G;
+        const int lo = cm.rank * sl, cnt = max(0, min(m, lo + sl) - lo);
+        double* mine = cm.red[cm.rank];
+        GRID_STRIDE(t, cnt) {
+            const int i = lo + t;
+            double s = 0.0;
+            for (int q = 0; q < cm.G; ++q) s += __ldcv(cm.vec[q] + off + i);
+            mine[i] = s;
+        }
+        // (red is single-buffered: it is written only after the exchange above, i.e. after every rank has finished
+        //  all reads of the previous collective)
+        grid.sync();
+        comm_exchange(cm, st, grid);
+        // collect the reduced slices: 4 independent peer loads in flight per thread (peer latency ~ 2-3 us)
+        const int gs = gridDim.x * kBlock;
+        for (int i0 = blockIdx.x * kBlock + threadIdx.x; i0 < m; i0 += 4 * gs) {
+            double v4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * gs;
+                v4[u] = i < m ? __ldcv(cm.red[i / sl] + i) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * gs;
+                if (i < m) fn(i, v4[u]);
+            }
+        }
     }
 }
 __device__ __forceinline__ double* comm_vec_slot(const Comm& cm, const CommState& st) {

@@ -1006,7 +1006,7 @@ int abipgpu_lp_solve_host(abipgpu_lp* e, double* b, const double* s, long iter, 
 static void comm_layout(long m, size_t* off_scal, size_t* off_flags, size_t* off_seq, size_t* off_err, size_t* total,
                         long* m_pad) {
     *m_pad = (m + 31) & ~31L;
-    *off_scal = sizeof(double) * 2 * (size_t)*m_pad;
+    *off_scal = sizeof(double) * 3 * (size_t)*m_pad;  // [2][m_pad] partials + [m_pad] reduced slice
     *off_flags = *off_scal + sizeof(double) * 2 * kCommScalars;
     *off_seq = *off_flags + sizeof(unsigned long long) * kMaxRanks;
     *off_err = *off_seq + sizeof(unsigned long long);
@@ -1051,6 +1051,7 @@ extern "C" int abipgpu_lp_comm_connect(abipgpu_lp* e, int G, int rank, const voi
         }
         e->peer_bufs[q] = base;
         cm.vec[q] = (double*)base;
+        cm.red[q] = (double*)base + 2 * m_pad;
         cm.scal[q] = (double*)((unsigned char*)base + o1);
         cm.flags[q] = (unsigned long long*)((unsigned char*)base + o2);
     }
