@@ -70,7 +70,7 @@ DECLARED_SYMBOLS = [
     "abip_normalize_A", "abip_un_normalize_A", "abip_free_A_matrix", "abip_copy_A_matrix",
     "abip_gpu_set_default_settings", "abip_gpu_init", "abip_gpu_solve", "abip_gpu_finish", "abip_gpu_main",
     "abip_gpu_get_stats", "abip_gpu_init_dist", "abip_gpu_comm_export", "abip_gpu_comm_connect", "abip_gpu_partition", "abip_gpu_column_partition", "abip_gpu_batch_main",
-    "abipgpu_lp_create", "abipgpu_lp_destroy", "abipgpu_lp_set_problem", "abipgpu_lp_cold_start",
+    "abipgpu_lp_create", "abipgpu_lp_create_scaling", "abipgpu_lp_destroy", "abipgpu_lp_set_problem", "abipgpu_lp_cold_start",
     "abipgpu_lp_outer_prologue", "abipgpu_lp_admm_iter", "abipgpu_lp_mu_stats", "abipgpu_lp_reinit",
     "abipgpu_lp_clamp_v", "abipgpu_lp_bb_begin", "abipgpu_lp_bb_round", "abipgpu_lp_solve_vec", "abipgpu_lp_get_vec",
     "abipgpu_lp_set_vec", "abipgpu_lp_g_th", "abipgpu_lp_spmv", "abipgpu_lp_describe",
@@ -122,6 +122,7 @@ def lib():
         "abip_gpu_column_partition": (None, [c_int, ip, c_int, c_int, P(c_int), P(c_int)]),
         "abip_gpu_batch_main": (c_int, [P(P(ABIPData)), P(ABIPSolution), P(ABIPInfo), c_int, c_int, c_int]),
         "abipgpu_lp_create": (vp, [c_int, c_int, ip, ip, fp, P(ABIPSettings), C.c_int]),
+        "abipgpu_lp_create_scaling": (vp, [c_int, c_int, ip, ip, fp, P(ABIPSettings), C.c_int, fp, fp, fp, fp]),
         "abipgpu_lp_destroy": (None, [vp]),
         "abipgpu_lp_set_problem": (C.c_int, [vp, fp, fp, fp, fp]),
         "abipgpu_lp_cold_start": (C.c_int, [vp, c_float, c_float]),

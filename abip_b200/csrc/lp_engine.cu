@@ -460,6 +460,109 @@ __global__ void k_precond(Csr A, double* M) {
     M[row] = 1.0 / s;
 }
 
+
+// =========================================================================================================
+// Equilibration of A on the device (reference linsys/common.c:150-565).  Works on the CSC
+// values (= CSR(A') values); CSR(A) values are gathered afterwards through the transposition permutation.  Sums run
+// sequentially in the reference's order with separate multiply and add (no FMA contraction), so D, E and the scaled
+// matrix are bit-identical to the host implementation abip_normalize_A.
+// kind: 0 pc (sqrt of 1-norm), 1 origin (2-norm), 2 ruiz (sqrt of inf-norm), 3 qp (sqrt(min nonzero * max))
+// =========================================================================================================
+__device__ __forceinline__ double clamp_scale(double v, double lo, double hi) { return v < lo ? 1.0 : (v > hi ? hi : v); }
+
+__global__ void k_eq_cols(int kind, const int* cptr, double* val, int n, double* E_acc, double lo, double hi) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int c1 = cptr[j], c2 = cptr[j + 1];
+    double acc = 0.0;
+    for (int k = c1; k < c2; ++k) {
+        const double a = fabs(val[k]);
+        if (kind == 0) acc = __dadd_rn(acc, a);
+        else if (kind == 1) acc = __dadd_rn(acc, __dmul_rn(a, a));
+        else acc = fmax(acc, a);
+    }
+    double e;
+    if (kind == 3) {
+        double mn = acc;
+        for (int k = c1; k < c2; ++k) {
+            const double a = fabs(val[k]);
+            if (a <= mn && a > 0) mn = a;
+        }
+        e = __dmul_rn(sqrt(mn), sqrt(acc));
+    } else {
+        e = sqrt(acc);
+    }
+    e = clamp_scale(e, lo, hi);
+    const double inv = 1.0 / e;
+    for (int k = c1; k < c2; ++k) val[k] = __dmul_rn(val[k], inv);
+    E_acc[j] = __dmul_rn(E_acc[j], e);
+}
+
+// row statistic in CSR order (ascending column = the reference's accumulation order), one thread per row
+__global__ void k_eq_rows(int kind, const int* rptr, const int* perm, const double* val, int m, double* Dt, double* D_acc,
+                          double lo, double hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int r1 = rptr[i], r2 = rptr[i + 1];
+    double d = 0.0;
+    for (int q = r1; q < r2; ++q) {
+        const double a = fabs(val[perm[q]]);
+        if (kind == 0) d = __dadd_rn(d, a);
+        else if (kind == 1) d = __dadd_rn(d, __dmul_rn(a, a));
+        else if (a >= d) d = a;
+    }
+    double v;
+    if (kind == 3) {
+        double mn = d;
+        for (int q = r1; q < r2; ++q) {
+            const double a = fabs(val[perm[q]]);
+            if (a <= mn && a > 0) mn = a;
+        }
+        v = sqrt(__dmul_rn(d, mn));
+    } else {
+        v = sqrt(d);
+    }
+    v = clamp_scale(v, lo, hi);
+    Dt[i] = v;
+    D_acc[i] = __dmul_rn(D_acc[i], v);
+}
+
+__global__ void k_eq_apply_rows(const int* ridx, double* val, long nnz, const double* Dt) {
+    const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nnz) val[k] = val[k] / Dt[ridx[k]];
+}
+
+__global__ void k_fill(double* a, long n, double v) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+__global__ void k_scale_all(double* a, long n, double f) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = __dmul_rn(a[i], f);
+}
+
+// per-row / per-column 2-norms of the scaled matrix divided by the count (common.c:535-557); summed on the host
+__global__ void k_eq_row_norms(const int* rptr, const int* perm, const double* val, int m, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    double s = 0.0;
+    for (int q = rptr[i]; q < rptr[i + 1]; ++q) { const double a = val[perm[q]]; s = __dadd_rn(s, __dmul_rn(a, a)); }
+    out[i] = sqrt(s) / m;
+}
+__global__ void k_eq_col_norms(const int* cptr, const double* val, int n, double* out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = 0.0;
+    for (int k = cptr[j]; k < cptr[j + 1]; ++k) s = __dadd_rn(s, __dmul_rn(val[k], val[k]));
+    out[j] = sqrt(s) / n;
+}
+
+__global__ void k_gather_perm(const double* src, const int* perm, double* dst, long nnz) {
+    const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nnz) dst[q] = src[perm[q]];
+}
+
 // =========================================================================================================
 // Host side of the engine
 // =========================================================================================================
@@ -548,8 +651,12 @@ static int upload(T** dst, const std::vector<T>& src, abipgpu_lp* e) {
 static thread_local int t_grid_request = 0;  // CTAs per engine (batch mode); 0 = whole device
 extern "C" void abipgpu_lp_request_grid(int ctas) { t_grid_request = ctas; }
 
+struct ScaleOut {  // host outputs of the device-side equilibration
+    double *D, *E, *mean_row, *mean_col;
+};
+
 static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap, const abip_int* Ai,
-                       const abip_float* Ax, const ABIPSettings* stgs, int device) {
+                       const abip_float* Ax, const ABIPSettings* stgs, int device, const ScaleOut* scale_out = nullptr) {
     const long nnz = Ap[n];
     if (m <= 0 || n <= 0 || nnz <= 0 || nnz >= 2147483647L || (long)m + n + 1 >= 2147483647L) {
         fprintf(stderr, "[abip_gpu] unsupported size m=%ld n=%ld nnz=%ld (int32 device indices)\n", (long)m,
@@ -578,8 +685,9 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     CK(cudaEventCreate(&e->ev_solve1));
 
     // CSR(A') is the caller's CSC; CSR(A) by counting sort (the reference's transpose(), indirect.c:81-139)
-    std::vector<int> at_ptr(n + 1), at_idx(nnz), a_ptr(m + 1, 0), a_idx(nnz);
-    std::vector<double> a_val(nnz);
+    std::vector<int> at_ptr(n + 1), at_idx(nnz), a_ptr(m + 1, 0), a_idx(nnz), perm;
+    std::vector<double> a_val(scale_out ? 0 : nnz);
+    if (scale_out) perm.resize(nnz);
     for (long j = 0; j <= n; ++j) at_ptr[j] = (int)Ap[j];
     for (long k = 0; k < nnz; ++k) {
         if (Ai[k] < 0 || Ai[k] >= m) {
@@ -596,7 +704,8 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
             for (long k = Ap[j]; k < Ap[j + 1]; ++k) {
                 const int q = fill[Ai[k]]++;
                 a_idx[q] = (int)j;
-                a_val[q] = Ax[k];
+                if (scale_out) perm[q] = (int)k;
+                else a_val[q] = Ax[k];
             }
     }
     std::vector<double> at_val(Ax, Ax + nnz);
@@ -626,7 +735,11 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     build_spmv_plan(a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA);
     build_spmv_plan(at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT);
 
-    if (upload(&e->A_ptr, a_ptr, e) || upload(&e->A_idx, a_idx, e) || upload(&e->A_val, a_val, e) ||
+    if (scale_out) a_val.assign(1, 0.0);  // placeholder; the values are gathered on the device below
+    if (upload(&e->A_ptr, a_ptr, e) || upload(&e->A_idx, a_idx, e) ||
+        (scale_out ? (cudaMalloc((void**)&e->A_val, (nnz + 8) * sizeof(double)) != cudaSuccess ||
+                      cudaMemsetAsync(e->A_val, 0, (nnz + 8) * sizeof(double), e->stream) != cudaSuccess)
+                   : upload(&e->A_val, a_val, e)) ||
         upload(&e->AT_ptr, at_ptr, e) || upload(&e->AT_idx, at_idx, e) || upload(&e->AT_val, at_val, e) ||
         upload(&e->A_wc, planA.warp_chunk, e) || upload(&e->AT_wc, planAT.warp_chunk, e) ||
         upload(&e->A_chunk, planA.chunk, e) || upload(&e->AT_chunk, planAT.chunk, e))
@@ -697,6 +810,51 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     c.phase_ns = nullptr;
 #endif
 
+    if (scale_out) {
+        int* d_perm = nullptr;
+        if (upload(&d_perm, perm, e)) return -1;
+        const double min_row = 1e-3 * sqrt((double)n), max_row = 1e3 * sqrt((double)n);
+        const double min_col = 1e-3 * sqrt((double)m), max_col = 1e3 * sqrt((double)m);
+        double* Dt = e->p;  // scratch [m]
+        const unsigned gm = (unsigned)((m + 255) / 256), gn = (unsigned)((n + 255) / 256), gz = (unsigned)((nnz + 255) / 256);
+        k_fill<<<gm, 256, 0, e->stream>>>(e->dD, m, 1.0);
+        k_fill<<<gn, 256, 0, e->stream>>>(e->dE, n, 1.0);
+        auto sweep = [&](int kind) {
+            k_eq_cols<<<gn, 256, 0, e->stream>>>(kind, e->AT_ptr, e->AT_val, (int)n, e->dE, min_col, max_col);
+            k_eq_rows<<<gm, 256, 0, e->stream>>>(kind, e->A_ptr, d_perm, e->AT_val, (int)m, Dt, e->dD, min_row, max_row);
+            k_eq_apply_rows<<<gz, 256, 0, e->stream>>>(e->AT_idx, e->AT_val, nnz, Dt);
+        };
+        if (stgs->pc_ruiz_rescale) sweep(0);
+        if (stgs->origin_rescale) sweep(1);
+        if (stgs->pc_ruiz_rescale)
+            for (abip_int it = 0; it < stgs->ruiz_iter; ++it) sweep(2);
+        if (stgs->qp_rescale) sweep(3);
+        // mean row / column norms (summed on the host in index order, like common.c:541-557)
+        double* rn = e->vec[ABIPGPU_VEC_UT];  // scratch [l] >= max(m, n)
+        std::vector<double> hn(std::max(m, n));
+        k_eq_row_norms<<<gm, 256, 0, e->stream>>>(e->A_ptr, d_perm, e->AT_val, (int)m, rn);
+        CK(cudaMemcpyAsync(hn.data(), rn, sizeof(double) * m, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        double mr = 0.0;
+        for (abip_int i = 0; i < m; ++i) mr += hn[i];
+        k_eq_col_norms<<<gn, 256, 0, e->stream>>>(e->AT_ptr, e->AT_val, (int)n, rn);
+        CK(cudaMemcpyAsync(hn.data(), rn, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        double mc = 0.0;
+        for (abip_int j = 0; j < n; ++j) mc += hn[j];
+        *scale_out->mean_row = mr;
+        *scale_out->mean_col = mc;
+        if (stgs->scale != 1) k_scale_all<<<gz, 256, 0, e->stream>>>(e->AT_val, nnz, stgs->scale);
+        k_gather_perm<<<gz, 256, 0, e->stream>>>(e->AT_val, d_perm, e->A_val, nnz);
+        CK(cudaMemsetAsync(rn, 0, sizeof(double) * e->l, e->stream));
+        CK(cudaMemsetAsync(Dt, 0, sizeof(double) * m, e->stream));
+        CK(cudaMemcpyAsync(scale_out->D, e->dD, sizeof(double) * m, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(scale_out->E, e->dE, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e->stream));
+        cudaFree(d_perm);
+        e->stats.d2h_bytes += 8.0 * 2 * (m + n);
+    }
     k_precond<<<(unsigned)((m + 255) / 256), 256, 0, e->stream>>>(c.A, e->dM);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
@@ -733,6 +891,21 @@ abipgpu_lp* abipgpu_lp_create(abip_int m, abip_int n, const abip_int* Ap, const 
     if (!Ap || !Ai || !Ax || !stgs) return nullptr;
     abipgpu_lp* e = new abipgpu_lp();
     if (create_impl(e, m, n, Ap, Ai, Ax, stgs, device) != 0) {
+        abipgpu_lp_destroy(e);
+        return nullptr;
+    }
+    return e;
+}
+
+// same as abipgpu_lp_create but A is UNSCALED: the equilibration (common.c:150-565) runs on the device; D [m], E [n] and
+// the two mean norms are returned to the host (needed for normalize_b_c and un_normalize_sol)
+abipgpu_lp* abipgpu_lp_create_scaling(abip_int m, abip_int n, const abip_int* Ap, const abip_int* Ai, const abip_float* Ax,
+                                      const ABIPSettings* stgs, int device, abip_float* D, abip_float* E,
+                                      abip_float* mean_norm_row_A, abip_float* mean_norm_col_A) {
+    if (!Ap || !Ai || !Ax || !stgs || !D || !E) return nullptr;
+    abipgpu_lp* e = new abipgpu_lp();
+    ScaleOut so{D, E, mean_norm_row_A, mean_norm_col_A};
+    if (create_impl(e, m, n, Ap, Ai, Ax, stgs, device, &so) != 0) {
         abipgpu_lp_destroy(e);
         return nullptr;
     }

@@ -723,6 +723,39 @@ static ABIPGpuWork* gpu_init_impl(const ABIPData* d, ABIPInfo* info, int rank, i
                d->stgs->rho_y);
         printf("Variables n = %i, constraints m = %i\n", (int)d->n, (int)d->m);
     }
+    const char* dev = getenv("ABIP_GPU_DEVICE");
+    w->dist_G = G;
+    w->dist_rank = rank;
+    w->c0 = 0;
+    w->nl = w->n;
+    const bool host_scaling = G > 1 || getenv("ABIP_GPU_HOST_SCALING") != nullptr;
+    if (!host_scaling) {
+        // single GPU: the caller's matrix goes to the device as it is and is equilibrated there (bit-identical to
+        // abip_normalize_A); the host keeps only D and E
+        if (w->stgs.normalize) {
+            w->scal.D = (double*)malloc(sizeof(double) * w->m);
+            w->scal.E = (double*)malloc(sizeof(double) * w->n);
+            w->have_scal = true;
+            w->eng = abipgpu_lp_create_scaling(w->m, w->n, d->A->p, d->A->i, d->A->x, &w->stgs, dev ? atoi(dev) : 0,
+                                               w->scal.D, w->scal.E, &w->scal.mean_norm_row_A, &w->scal.mean_norm_col_A);
+        } else {
+            w->eng = abipgpu_lp_create(w->m, w->n, d->A->p, d->A->i, d->A->x, &w->stgs, dev ? atoi(dev) : 0);
+        }
+        if (!w->eng) {
+            printf("ERROR: init_lin_sys_work failure\n");
+            abip_gpu_finish(w);
+            return nullptr;
+        }
+        abipgpu_lp_set_global_n(w->eng, w->n);
+        if (d->stgs->verbose) {
+            char buf[768];
+            abipgpu_lp_describe(w->eng, buf, sizeof(buf));
+            printf("Engine: %s\n", buf);
+        }
+        info->setup_time = now_ms() - t0;
+        if (d->stgs->verbose) printf("Setup time: %1.2es\n", info->setup_time / 1e3);
+        return w;
+    }
     if (!abip_copy_A_matrix(&w->A, d->A)) {
         printf("ERROR: copy A matrix failed\n");
         delete w;
@@ -732,11 +765,6 @@ static ABIPGpuWork* gpu_init_impl(const ABIPData* d, ABIPInfo* info, int rank, i
         abip_normalize_A(w->A, &w->stgs, &w->scal);
         w->have_scal = true;
     }
-    const char* dev = getenv("ABIP_GPU_DEVICE");
-    w->dist_G = G;
-    w->dist_rank = rank;
-    w->c0 = 0;
-    w->nl = w->n;
     if (G > 1) {  // contiguous column blocks balanced by nonzeros
         if (w->stgs.half_update) {
             printf("ERROR: half_update is not supported by the multi-GPU engine\n");
@@ -775,7 +803,7 @@ static ABIPGpuWork* gpu_init_impl(const ABIPData* d, ABIPInfo* info, int rank, i
         }
     }
     if (d->stgs->verbose) {
-        char buf[512];
+        char buf[768];
         abipgpu_lp_describe(w->eng, buf, sizeof(buf));
         printf("Engine: %s\n", buf);
     }

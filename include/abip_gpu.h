@@ -247,6 +247,11 @@ enum {
 /* A: *scaled* CSC (host).  Builds CSR(A), CSR(A'), preconditioner; allocates all work vectors. */
 abipgpu_lp *abipgpu_lp_create(abip_int m, abip_int n, const abip_int *Ap, const abip_int *Ai,
                               const abip_float *Ax, const ABIPSettings *stgs, int device);
+/* same, but A is UNSCALED: the equilibration of common.c:150-565 runs on the device (bit-identical to
+ * abip_normalize_A); D [m], E [n] and the mean row / column norms are returned for normalize_b_c / un_normalize_sol */
+abipgpu_lp *abipgpu_lp_create_scaling(abip_int m, abip_int n, const abip_int *Ap, const abip_int *Ai,
+                                      const abip_float *Ax, const ABIPSettings *stgs, int device, abip_float *D,
+                                      abip_float *E, abip_float *mean_norm_row_A, abip_float *mean_norm_col_A);
 void abipgpu_lp_destroy(abipgpu_lp *e);
 /* uploads scaled b, c (and D, E, may be NULL when normalize = 0); forms h = [-b; c], solves g = K^-1 h with
  * the iter = -1 tolerance, flips g_x, computes g_th (abip.c:1915-1924).  Returns < 0 on failure. */

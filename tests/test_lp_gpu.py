@@ -300,3 +300,38 @@ def test_settings_variants_against_reference_golden(name):
     assert abs(info["pobj"] - g["pobj"]) <= 1e-6 * abs(g["pobj"]) + 2 * eps * eps
     assert max(info["pres"], info["dres"], info["gap"]) < eps
     _check_solution(p, x, y, s, info, eps)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(origin_rescale=1), dict(qp_rescale=1, pc_ruiz_rescale=0), dict(scale=2.0)])
+def test_device_equilibration_is_bit_identical_to_host(kw):
+    """abipgpu_lp_create_scaling (device-side common.c:150-565) against abip_normalize_A (host C++) and the oracle."""
+    import ctypes as C
+    from abip_b200 import _capi, api
+    L = _capi.lib()
+    p = problems.mcf_lp(4, 40, 200, 6, 300, seed=6)
+    st = _capi.default_settings(verbose=0, **kw)
+    H = api.CscHolder((p.m, p.n, p.Ap.copy(), p.Ai.copy(), p.Ax.copy()))
+    sc = _capi.ABIPScaling()
+    L.abip_normalize_A(C.byref(H.c), C.byref(st), C.byref(sc))      # host reference (scales H in place)
+    Dh = np.ctypeslib.as_array(sc.D, shape=(p.m,)).copy()
+    Eh = np.ctypeslib.as_array(sc.E, shape=(p.n,)).copy()
+    Hu = api.CscHolder((p.m, p.n, p.Ap.copy(), p.Ai.copy(), p.Ax.copy()))
+    D, E = np.zeros(p.m), np.zeros(p.n)
+    mr, mc = C.c_double(), C.c_double()
+    e = L.abipgpu_lp_create_scaling(p.m, p.n, api._ip(Hu.Ap), api._ip(Hu.Ai), api._fp(Hu.Ax), C.byref(st), 0,
+                                    api._fp(D), api._fp(E), C.byref(mr), C.byref(mc))
+    assert e
+    assert np.array_equal(D, Dh) and np.array_equal(E, Eh)
+    assert mr.value == sc.mean_norm_row_A and mc.value == sc.mean_norm_col_A
+    # the scaled matrix on the device: A' y through the engine == scaled host matrix times y
+    import scipy.sparse as sp
+    As = sp.csc_matrix((H.Ax, H.Ai, H.Ap), shape=(p.m, p.n))
+    y = np.random.default_rng(0).standard_normal(p.m)
+    out = np.zeros(p.n)
+    assert L.abipgpu_lp_spmv(e, 1, api._fp(y), api._fp(out)) == 0
+    assert rel(out, As.T @ y) < 1e-13
+    x = np.random.default_rng(1).standard_normal(p.n)
+    out2 = np.zeros(p.m)
+    assert L.abipgpu_lp_spmv(e, 0, api._fp(x), api._fp(out2)) == 0
+    assert rel(out2, As @ x) < 1e-13
+    L.abipgpu_lp_destroy(e)
