@@ -15,16 +15,17 @@
 
 namespace cg = cooperative_groups;
 
-// Geometry chosen by measurement on B200 at cfg2 (profiles/r01_spmv_variants.md): one 1024-thread CTA per SM,
-// 256-nonzero chunks, single-stage cp.async ring (deeper rings cost L1 capacity, which the gathers need more).
+// Geometry chosen by measurement on B200 at cfg2 (profiles/r01_spmv_variants.md): two 512-thread CTAs per SM (32
+// warps per SM either way; the CTA-level barriers of the reductions are cheaper), 252-nonzero chunks in fixed
+// 256-element windows, one TMA-fed buffer per warp.
 #ifndef ABIP_BLOCK
-#define ABIP_BLOCK 1024
+#define ABIP_BLOCK 512
 #endif
 #ifndef ABIP_MIN_BLOCKS_PER_SM
-#define ABIP_MIN_BLOCKS_PER_SM 1
+#define ABIP_MIN_BLOCKS_PER_SM 2
 #endif
-#ifndef ABIP_STAGES
-#define ABIP_STAGES 1
+#ifndef ABIP_PAGE_CACHE
+#define ABIP_PAGE_CACHE 0  // shared-memory page cache of the gathered vector (see kPageLog2); measured: no gain yet
 #endif
 constexpr int kBlock = ABIP_BLOCK;
 constexpr int kWarps = kBlock / 32;
@@ -41,6 +42,13 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+// zero-filling variants for the page-cache loads (src_bytes = 0 => the destination is filled with zeros)
+__device__ __forceinline__ void cp_async16_zfill(unsigned dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8_zfill(unsigned dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -54,73 +62,146 @@ __device__ __forceinline__ void cp_async_wait() {
 //     #rows = 0 marks "row continues", #rows = -1 its last piece.
 // The device arrays are padded by 8 elements so that 16-byte aligned copy windows may over-read.
 #ifndef ABIP_CHUNK
-#define ABIP_CHUNK 256
+#define ABIP_CHUNK 252
+#endif
+#ifndef ABIP_CHUNK_ROWS
+#define ABIP_CHUNK_ROWS 64
 #endif
 constexpr int kChunk = ABIP_CHUNK;
-constexpr int kStages = ABIP_STAGES;
+constexpr int kChunkRows = ABIP_CHUNK_ROWS;  // rows per chunk (bounds the row-pointer window)
+
+// Page cache of the gathered vector.  The gathers x[col] are bound by the L1 wavefront rate
+// (one 128-byte line per cycle at best, ~25 distinct lines per warp request on cfg2), not by HBM.  The plan
+// therefore picks, per CTA and per matrix, the 256-byte pages of x that the CTA's rows reference most often; the
+// CTA copies them into shared memory at the start of the phase (coalesced) and the column indices of its slice of
+// the matrix are re-encoded: bit 31 set => offset into the shared-memory copy, otherwise a global column index.
+constexpr int kPageLog2 = 5;                 // 32 doubles = 256 bytes per page
+constexpr int kPageDoubles = 1 << kPageLog2;
+constexpr unsigned kPcFlag = 0x80000000u;
+
 struct Csr {
     const int* ptr;         // [nrows+1 (+8)]
-    const int* idx;         // [nnz (+8)] column indices
+    const int* idx;         // [nnz (+8)] column indices (page-cache encoded when cta_npages != nullptr)
     const double* val;      // [nnz (+8)]
     int nrows;
     const int* warp_chunk;  // [W+1] chunk range of each warp of the persistent grid
     const int4* chunk;      // [nchunks] {row0, nnz0, nrows | 0 | -1, nnz}
     int lanes_log2;         // lanes per row in the shared-memory row reduction (1 => reference summation order)
+    int ncols;              // length of the gathered vector (page loads are clipped to it)
+    int pc_stride;          // page-list stride per CTA
+    const int* cta_npages;  // [G] cached pages of each CTA, nullptr => no page cache
+    const int* cta_pages;   // [G * pc_stride] page ids (ascending)
+    // rows longer than kChunk ("long rows", nullptr when there are none): cut into pieces, each a chunk of its own
+    const int* cta_long;     // [G+1] range of long_rows owned by each CTA
+    const int4* long_rows;   // {row, first piece slot, #pieces, 0}
+    double* long_part;       // [#pieces] piece sums (scratch)
+    int plan_slot;           // 1 + slot of the per-warp plan cache in shared memory (0: not cached)
 };
 
-// Per-warp staging ring in shared memory.  Stage layout (bytes): [val window][idx window][row-ptr window].
-constexpr int kValWin = (kChunk + 2) * 8;                 // 16-byte aligned window may start 1 element early
-constexpr int kIdxWin = ((kChunk + 6 + 3) / 4) * 16;      // up to 3 elements early, rounded to 16 bytes
-constexpr int kPtrWin = ((kChunk + 1 + 6 + 3) / 4) * 16;  // kChunk + 1 row pointers
-constexpr int kStageBytes = ((kValWin + kIdxWin + kPtrWin + 127) / 128) * 128;
-constexpr int kWarpSmemBytes = kStages * kStageBytes;
-struct WarpSmem {
-    unsigned char* base;  // generic pointer to this warp's slice
-    unsigned base_s;      // same, shared-space address
-    int head;             // stage of the oldest chunk in flight
-    int inflight;         // chunks (= cp.async groups) in flight, <= kStages
-    const int4* cur;      // matrix (identified by its chunk array) whose chunks are in flight
-    int next_c;           // next chunk of `cur` to issue
+// Per-warp staging buffer in shared memory: [val window | idx window | row-ptr window].  The value and index windows
+// are FIXED-size (kWin elements) and start at the nonzero index (s & ~3) of the chunk, so one chunk (<= kChunk =
+// kWin - 4 nonzeros) always fits, every copy is a compile-time number of 16-byte cp.async operations, and the inner
+// loops use 128-bit shared-memory loads without bounds checks.  Elements of the window outside the chunk belong to
+// neighbouring rows (or to the zero padding behind the arrays): their products are computed and never summed.
+constexpr int kWin = 256;
+static_assert(kChunk + 3 <= kWin && kWin % 128 == 0, "one chunk = one window");
+constexpr int kPad = kWin + 8;                                // padding elements behind every matrix array
+constexpr int kValWin = kWin * 8;
+constexpr int kIdxWin = kWin * 4;
+constexpr int kPtrUnits = (kChunkRows + 1 + 3 + 3) / 4;       // 16-byte units: kChunkRows + 1 pointers, <= 3 early
+static_assert(kPtrUnits <= 32, "row-pointer window is copied by one instruction");
+constexpr int kPtrWin = kPtrUnits * 16;
+constexpr int kStageBytes = kValWin + kIdxWin + kPtrWin;
+constexpr int kWarpSmemBytes = kStageBytes;
+// mbarrier / TMA bulk-copy primitives (the chunk windows are contiguous, 16-byte aligned ranges of the matrix arrays:
+// three cp.async.bulk per chunk instead of seven 16-byte cp.async per lane -- the LDGSTS path cost 25 % of all L1
+// wavefronts of the kernel, the bulk copies bypass the LSU pipe entirely; SASS: UBLKCP)
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-    // all lanes: 16-byte cp.async copies of the chunk's three windows into stage (head + inflight) % kStages
-    __device__ __forceinline__ void issue(const Csr& A, int c) {
-        const int lane = threadIdx.x & 31;
-        const int stage = (head + inflight) % kStages;
-        const int4 d = __ldg(A.chunk + c);
-        const int s = d.y, n = d.w, row0 = d.x;
-        const int nr = d.z > 0 ? d.z : 0;
-        const unsigned st_s = base_s + stage * kStageBytes;
-        const int sv = s & ~1, nv = (((s + n + 1) & ~1) - sv) >> 1;            // 16-byte units of values
-        const int si = s & ~3, ni = (((s + n + 3) & ~3) - si) >> 2;            // ... of column indices
-        const int sr = row0 & ~3, np = nr > 0 ? ((((row0 + nr + 4) & ~3) - sr) >> 2) : 0;  // ... of row pointers
-        for (int i = lane; i < nv; i += 32) cp_async16(st_s + 16 * i, A.val + sv + 2 * i);
-        for (int i = lane; i < ni; i += 32) cp_async16(st_s + kValWin + 16 * i, A.idx + si + 4 * i);
-        for (int i = lane; i < np; i += 32) cp_async16(st_s + kValWin + kIdxWin + 16 * i, A.ptr + sr + 4 * i);
-        cp_async_commit();
-        ++inflight;
+struct WarpSmem {
+    unsigned char* base;  // generic pointer to this warp's buffer
+    unsigned base_s;      // same, shared-space address
+    unsigned bar_s;       // this warp's mbarrier (shared-space address)
+    unsigned parity;      // phase parity of the next wait
+    const int4* cur;      // matrix (identified by its chunk array) of the chunk in flight, nullptr: nothing in flight
+    int cur_c;            // its chunk index
+    double* pc;           // the CTA's page cache (shared by all its warps), generic pointer
+    int* plan;            // per-warp plan cache: kPlanSlots x {first descriptor (int4), c0, c1, valid, -}
+
+    // this warp's chunk range [c0, c1) of A and the descriptor of its first chunk.  The three dependent global loads
+    // cost ~2 us at the start of every phase; the two matrices of the CG loop are cached in shared memory instead.
+    __device__ __forceinline__ void get_plan(const Csr& A, int& c0, int& c1, int4& d0) {
+        const int gwarp = blockIdx.x * kWarps + (threadIdx.x >> 5);
+        int* e = plan + 8 * (A.plan_slot - 1);
+        if (A.plan_slot > 0) {
+            const int4 r = *reinterpret_cast<const int4*>(e + 4);
+            if (r.z == 1) {
+                c0 = r.x;
+                c1 = r.y;
+                d0 = *reinterpret_cast<const int4*>(e);
+                return;
+            }
+        }
+        c0 = __ldg(A.warp_chunk + gwarp);
+        c1 = __ldg(A.warp_chunk + gwarp + 1);
+        d0 = make_int4(0, 0, 0, 0);
+        if (c0 < c1) d0 = __ldg(A.chunk + c0);
+        if (A.plan_slot > 0) {
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) {
+                *reinterpret_cast<int4*>(e) = d0;
+                *reinterpret_cast<int4*>(e + 4) = make_int4(c0, c1, 1, 0);
+            }
+            __syncwarp();
+        }
     }
-    // wait until the oldest group has landed (groups complete in order) and make it visible to the whole warp
-    __device__ __forceinline__ void wait_head() {
-        if (inflight <= 1) cp_async_wait<0>();
-        else if (inflight == 2) cp_async_wait<1>();
-        else if (inflight == 3) cp_async_wait<2>();
-        else cp_async_wait<3>();
+
+    // start the asynchronous copy of chunk c (descriptor d) of A into the buffer.  All lanes call it: the buffer was
+    // last touched through the generic proxy (LDS/STS of every lane), the bulk copy writes through the async proxy.
+    __device__ __forceinline__ void issue(const Csr& A, int c, const int4& d) {
+        fence_proxy_async();
         __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+            const int si = d.y & ~3, sr = d.x & ~3;
+            const bool rows = d.z > 0;
+            mbar_expect_tx(bar_s, kValWin + kIdxWin + (rows ? kPtrWin : 0));
+            bulk_g2s(base_s, A.val + si, kValWin, bar_s);
+            bulk_g2s(base_s + kValWin, A.idx + si, kIdxWin, bar_s);
+            if (rows) bulk_g2s(base_s + kValWin + kIdxWin, A.ptr + sr, kPtrWin, bar_s);
+        }
+        cur = A.chunk;
+        cur_c = c;
     }
-    __device__ __forceinline__ void release_head() {
-        __syncwarp();  // every lane is done reading the stage before it is overwritten
-        head = (head + 1) % kStages;
-        --inflight;
+    __device__ __forceinline__ void wait() {
+        mbar_wait(bar_s, parity);
+        parity ^= 1u;
     }
     __device__ __forceinline__ void drain() {
-        cp_async_wait<0>();
-        __syncwarp();
-        head = 0;
-        inflight = 0;
+        if (cur) wait();
         cur = nullptr;
     }
 };
-static_assert(kStages >= 1 && kStages <= 4, "cp.async ring depth");
 
 // Deterministic grid-wide reduction helper (see file header).  partials is double-buffered so that a fast
 // block starting reduction t+1 can never overwrite values a slow block is still reading for reduction t.
@@ -215,126 +296,235 @@ struct Reducer {
 // barrier's fence).  Replaces _accum_by_Atrans (reference linsys/common.c:598-639) for both A and A'.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void spmv_prefetch(const Csr& A, WarpSmem& ws) {
-    const int gwarp = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    const int c0 = __ldg(A.warp_chunk + gwarp), c1 = __ldg(A.warp_chunk + gwarp + 1);
-    if (ws.cur == A.chunk) return;
+    int c0, c1;
+    int4 d0;
+    ws.get_plan(A, c0, c1, d0);
+    if (ws.cur == A.chunk && ws.cur_c == c0) return;
     ws.drain();
-    ws.cur = A.chunk;
-    ws.next_c = c0;
-    while (ws.inflight < kStages && ws.next_c < c1) ws.issue(A, ws.next_c++);
+    if (c0 < c1) ws.issue(A, c0, d0);
+}
+
+// Copies the CTA's cached pages of x into shared memory (all threads of the CTA; contains __syncthreads()).
+// Thread t copies 16-byte unit (t & 15) of pages (t >> 4) + 64 j: the page ids are fetched first (independent loads,
+// one L2 round trip), then all copies are issued asynchronously (second round trip) -- a dependent id -> copy chain
+// per page was measured at 13 us per phase.
+constexpr int kPcMaxPages = 512;
+__device__ __forceinline__ void spmv_load_pages(const Csr& A, const double* x, WarpSmem& ws) {
+    constexpr int J = kPcMaxPages * (kPageDoubles / 2) / kBlock;  // units per thread
+    constexpr int PJ = kBlock / (kPageDoubles / 2);               // pages per round
+    const int np = __ldg(A.cta_npages + blockIdx.x);
+    const int* pg = A.cta_pages + (size_t)blockIdx.x * A.pc_stride;
+    const int p0 = threadIdx.x / (kPageDoubles / 2), u = threadIdx.x % (kPageDoubles / 2);
+    int id[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) id[j] = (p0 + PJ * j < np) ? __ldg(pg + p0 + PJ * j) : -1;
+    __syncthreads();  // every warp of the CTA is done with the previous phase's pages
+    const unsigned pc_s = smem_u32(ws.pc);
+    const bool al16 = (reinterpret_cast<unsigned long long>(x) & 15ull) == 0;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        if (id[j] >= 0) {
+            const int col = (id[j] << kPageLog2) + 2 * u;
+            const unsigned dst = pc_s + 8u * (((p0 + PJ * j) << kPageLog2) + 2 * u);
+            if (al16) {
+                const int nb = min(max(A.ncols - col, 0), 2) * 8;
+                cp_async16_zfill(dst, x + (nb ? col : 0), nb);
+            } else {
+                cp_async8_zfill(dst, x + (col < A.ncols ? col : 0), col < A.ncols ? 8 : 0);
+                cp_async8_zfill(dst + 8, x + (col + 1 < A.ncols ? col + 1 : 0), col + 1 < A.ncols ? 8 : 0);
+            }
+        }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+}
+
+#ifdef ABIP_PHASE_TIMING
+// debug: SM-clock cycles per warp spent in the sections of the chunk loop, summed over all warps and calls
+// [0] wait for the chunk  [1] gather + multiply  [2] row sums + epilogue  [3] issue of the next chunk  [4] chunks
+__device__ unsigned long long g_spmv_prof[16];  // [0..7] matrices with 1 lane/row (A'), [8..15] others (A)
+#define SPROF_DECL unsigned long long _p0 = clock64(), _pa[4] = {0, 0, 0, 0}, _pn = 0
+#define SPROF(i) do { const unsigned long long _t = clock64(); _pa[i] += _t - _p0; _p0 = _t; } while (0)
+#define SPROF_RESET() _p0 = clock64()
+#define SPROF_FLUSH()                                                                \
+    do {                                                                             \
+        if ((threadIdx.x & 31) == 0) {                                               \
+            const int _b = A.lanes_log2 ? 8 : 0;                                     \
+            for (int _i = 0; _i < 4; ++_i) atomicAdd(&g_spmv_prof[_b + _i], _pa[_i]); \
+            atomicAdd(&g_spmv_prof[_b + 4], _pn);                                    \
+        }                                                                            \
+    } while (0)
+#else
+#define SPROF_DECL do { } while (0)
+#define SPROF(i) do { } while (0)
+#define SPROF_RESET() do { } while (0)
+#define SPROF_FLUSH() do { } while (0)
+#endif
+
+// gather of one element of x: page-cache hit (bit 31 of the encoded index) => shared memory, else global memory.
+// One generic load serves both address spaces, so the warp does not diverge.
+__device__ __forceinline__ double gather_x(const double* x, const double* pc, int ci) {
+#if ABIP_PAGE_CACHE
+    const double* p = ci < 0 ? pc + (ci & 0x7fffffff) : x + ci;
+    return *p;
+#else
+    return x[ci];
+#endif
 }
 
 template <class RowFn>
 __device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, WarpSmem& ws, const Csr* next, RowFn fn) {
-    constexpr int U = kChunk / 32;
+#if ABIP_PAGE_CACHE
+    if (A.cta_npages) spmv_load_pages(A, x, ws);
+#endif
+    const double* pc = ws.pc;
     const int lane = threadIdx.x & 31;
-    const int gwarp = blockIdx.x * kWarps + (threadIdx.x >> 5);
     const int lg = A.lanes_log2;
     const int L = 1 << lg;
     const int sl = lane & (L - 1);
     const int sub = lane >> lg;
     const int rpw = 32 >> lg;
-    const int c0 = __ldg(A.warp_chunk + gwarp), c1 = __ldg(A.warp_chunk + gwarp + 1);
-    int nx_c = 0, nx_c1 = 0;
-    if (next) {
-        nx_c = __ldg(next->warp_chunk + gwarp);
-        nx_c1 = __ldg(next->warp_chunk + gwarp + 1);
-    }
-    if (ws.cur != A.chunk) {  // nothing useful in flight
+    int c0, c1, nx_c = 0, nx_c1 = 0;
+    int4 d, dnx = make_int4(0, 0, 0, 0);  // dnx: first chunk of this warp in the next phase's matrix
+    ws.get_plan(A, c0, c1, d);
+    if (next) ws.get_plan(*next, nx_c, nx_c1, dnx);
+    if (c0 < c1 && !(ws.cur == A.chunk && ws.cur_c == c0)) {  // nothing useful in flight
         ws.drain();
-        ws.cur = A.chunk;
-        ws.next_c = c0;
+        ws.issue(A, c0, d);
     }
-    double acc_long = 0.0;
+    unsigned char* st = ws.base;
+    double* vw = reinterpret_cast<double*>(st);
+    const int* iw = reinterpret_cast<const int*>(st + kValWin);
+    SPROF_DECL;
     for (int c = c0; c < c1; ++c) {
-        // keep the ring full: first our own chunks, then the first chunks of the next phase's matrix
-        while (ws.inflight < kStages) {
-            if (ws.next_c < c1) ws.issue(A, ws.next_c++);
-            else if (next && nx_c < nx_c1) ws.issue(*next, nx_c++);
-            else break;
-        }
-        ws.wait_head();
-        unsigned char* st = ws.base + ws.head * kStageBytes;
-        const int4 d = __ldg(A.chunk + c);  // loaded by issue() a moment ago: L1 hit
+        int4 dn = dnx;  // descriptor of the chunk to stream in next (loaded now, used after this chunk)
+        if (c + 1 < c1) dn = __ldg(A.chunk + c + 1);
+        SPROF_RESET();
+        ws.wait();
+        SPROF(0);
         const int row0 = d.x, s = d.y, nr = d.z, n = d.w;
-        double* vs = reinterpret_cast<double*>(st) + (s & 1);
-        const int* is = reinterpret_cast<const int*>(st + kValWin) + (s & 3);
-        if (nr <= 0) {  // piece of a long row
+        const int off = s & 3;
+        // 1. gather x for the whole window (8 independent loads per lane), multiply
+        double xv[2][4];
+        int4 ci[2];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int k = lane + 32 * u;
-                if (k < n) acc_long = fma(vs[k], x[is[k]], acc_long);
-            }
-            if (nr < 0) {
+        for (int u = 0; u < 2; ++u) ci[u] = reinterpret_cast<const int4*>(iw)[lane + 32 * u];
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) acc_long += __shfl_xor_sync(0xffffffffu, acc_long, off);
-                if (lane == 0) fn(row0, acc_long);
-                acc_long = 0.0;
-            }
-            ws.release_head();
-            continue;
+        for (int u = 0; u < 2; ++u) {
+            xv[u][0] = gather_x(x, pc, ci[u].x);
+            xv[u][1] = gather_x(x, pc, ci[u].y);
+            xv[u][2] = gather_x(x, pc, ci[u].z);
+            xv[u][3] = gather_x(x, pc, ci[u].w);
         }
-        // 1. gather x (U independent loads per lane) and multiply in place
-        double xv[U];
+        if (nr <= 0) {  // piece of a long row: elements [off, off + n) of the window; slot -nr - 1 of the scratch
+            double acc = 0.0;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int k = lane + 32 * u;
-            xv[u] = (k < n) ? x[is[k]] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int k = lane + 32 * u;
-            if (k < n) vs[k] *= xv[u];
-        }
-        __syncwarp();
-        // 2. row sums out of shared memory, L lanes per row; each sum is parked in the row's first product slot
-        const int* rp = reinterpret_cast<const int*>(st + kValWin + kIdxWin) + (row0 & 3);
-        if (L == 1) {
-            for (int rr = lane; rr < nr; rr += 32) {
-                const int a = rp[rr] - s, b = rp[rr + 1] - s;
-                double acc = 0.0;
-                for (int k = a; k < b; ++k) acc += vs[k];
-                fn(row0 + rr, acc);
+            for (int u = 0; u < 2; ++u) {
+                const int q = lane + 32 * u;
+                const double2 v01 = reinterpret_cast<const double2*>(vw)[2 * q];
+                const double2 v23 = reinterpret_cast<const double2*>(vw)[2 * q + 1];
+                const int k = 4 * q - off;
+                if ((unsigned)k < (unsigned)n) acc = fma(v01.x, xv[u][0], acc);
+                if ((unsigned)(k + 1) < (unsigned)n) acc = fma(v01.y, xv[u][1], acc);
+                if ((unsigned)(k + 2) < (unsigned)n) acc = fma(v23.x, xv[u][2], acc);
+                if ((unsigned)(k + 3) < (unsigned)n) acc = fma(v23.y, xv[u][3], acc);
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) A.long_part[-nr - 1] = acc;
         } else {
-            for (int base = 0; base < nr; base += rpw) {
-                const int rr = base + sub;
-                const bool ok = rr < nr;
-                double acc = 0.0;
-                int a = 0, b = 0;
-                if (ok) {
-                    a = rp[rr] - s;
-                    b = rp[rr + 1] - s;
-                    for (int k = a + sl; k < b; k += L) acc += vs[k];
-                }
-                for (int off = L >> 1; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off, L);
-                __syncwarp();  // every lane of the group has read its products before slot a is overwritten
-                if (ok && sl == 0 && a < b) vs[a] = acc;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int q = lane + 32 * u;
+                double2 v01 = reinterpret_cast<const double2*>(vw)[2 * q];
+                double2 v23 = reinterpret_cast<const double2*>(vw)[2 * q + 1];
+                v01.x *= xv[u][0];
+                v01.y *= xv[u][1];
+                v23.x *= xv[u][2];
+                v23.y *= xv[u][3];
+                reinterpret_cast<double2*>(vw)[2 * q] = v01;
+                reinterpret_cast<double2*>(vw)[2 * q + 1] = v23;
             }
             __syncwarp();
-            // 3. epilogue for all rows of the chunk at once (one lane per row: the epilogue's own global loads
-            //    overlap instead of serialising per pass)
-            for (int rr = lane; rr < nr; rr += 32) {
-                const int a = rp[rr] - s, b = rp[rr + 1] - s;
-                fn(row0 + rr, a < b ? vs[a] : 0.0);
+            SPROF(1);
+            // 2. row sums out of shared memory, L lanes per row; each sum is parked in the row's first product slot
+            double* vs = vw + off - s;  // vs[k]: product of nonzero k (global nonzero index)
+            const int* rp = reinterpret_cast<const int*>(st + kValWin + kIdxWin) + (row0 & 3);
+            if (L == 1) {
+                for (int rr = lane; rr < nr; rr += 32) {
+                    const int a = rp[rr], b = rp[rr + 1];
+                    double acc = 0.0;
+                    for (int k = a; k < b; ++k) acc += vs[k];
+                    fn(row0 + rr, acc);
+                }
+            } else {
+                for (int base = 0; base < nr; base += rpw) {
+                    const int rr = base + sub;
+                    const bool ok = rr < nr;
+                    double acc = 0.0;
+                    int a = 0, b = 0;
+                    if (ok) {
+                        a = rp[rr];
+                        b = rp[rr + 1];
+                        for (int k = a + sl; k < b; k += L) acc += vs[k];
+                    }
+                    for (int o = L >> 1; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, L);
+                    __syncwarp();  // every lane of the group has read its products before slot a is overwritten
+                    if (ok && sl == 0 && a < b) vs[a] = acc;
+                }
+                __syncwarp();
+                // 3. epilogue for all rows of the chunk at once (one lane per row: the epilogue's own global loads
+                //    overlap instead of serialising per pass)
+                for (int rr = lane; rr < nr; rr += 32) {
+                    const int a = rp[rr], b = rp[rr + 1];
+                    fn(row0 + rr, a < b ? vs[a] : 0.0);
+                }
             }
         }
-        ws.release_head();
+        __syncwarp();  // every lane is done reading the buffer before it is overwritten
+        SPROF(2);
+        // stream in the next chunk: our own, or (across the grid barrier) the first one of the next phase's matrix
+        if (c + 1 < c1) ws.issue(A, c + 1, dn);
+        else if (next && nx_c < nx_c1) ws.issue(*next, nx_c, dn);
+        else ws.cur = nullptr;
+        d = dn;
+        SPROF(3);
+#ifdef ABIP_PHASE_TIMING
+        ++_pn;
+#endif
     }
-    if (next) {  // whatever is in flight now belongs to `next`
-        if (ws.inflight == 0 && nx_c < nx_c1) {
-            while (ws.inflight < kStages && nx_c < nx_c1) ws.issue(*next, nx_c++);
+    SPROF_FLUSH();
+    if (c0 >= c1 && next && nx_c < nx_c1 && !(ws.cur == next->chunk && ws.cur_c == nx_c)) {
+        ws.drain();
+        ws.issue(*next, nx_c, dnx);
+    }
+    // long rows of this CTA: add the piece sums in piece order (pieces were computed by different warps of the CTA)
+    if (A.long_rows) {
+        const int j0 = __ldg(A.cta_long + blockIdx.x), j1 = __ldg(A.cta_long + blockIdx.x + 1);
+        if (j0 < j1) {  // uniform per CTA
+            __syncthreads();
+            for (int j = j0 + (int)threadIdx.x; j < j1; j += kBlock) {
+                const int4 lr = __ldg(A.long_rows + j);
+                double acc = 0.0;
+                for (int i = 0; i < lr.z; ++i) acc += A.long_part[lr.y + i];
+                fn(lr.x, acc);
+            }
+            __syncthreads();  // the scratch may be rewritten by the next pass over this matrix
         }
-        ws.cur = next->chunk;
-        ws.next_c = nx_c;
-    } else {
-        ws.cur = nullptr;
     }
 }
 
 // Dynamic shared memory of every persistent kernel: [reducer scratch][per-warp staging rings]
 constexpr size_t kRedBytes = sizeof(double) * kMaxRed * kWarps;
-constexpr size_t kSmemBytes = ((kRedBytes + 127) / 128) * 128 + (size_t)kWarps * kWarpSmemBytes;
+constexpr size_t kBarOff = kRedBytes;                                            // one mbarrier per warp
+constexpr int kPlanSlots = 2;
+constexpr size_t kPlanOff = ((kBarOff + 8 * kWarps + 15) / 16) * 16;             // per-warp plan cache
+constexpr size_t kStageOff = ((kPlanOff + 32 * kPlanSlots * kWarps + 127) / 128) * 128;
+constexpr size_t kSmemBytes = kStageOff + (size_t)kWarps * kWarpSmemBytes;
+// ... followed by the optional page cache [slots * 256 B] (LP engine; launch with kSmemBytes + slots * 256)
+constexpr int kSmemMaxOptin = 232448;  // 227 KB per CTA on sm_100
+constexpr int kPcSlotsMax = (kSmemMaxOptin - (int)kSmemBytes) / (kPageDoubles * 8) < 512 ? (kSmemMaxOptin - (int)kSmemBytes) / (kPageDoubles * 8) : 512;
 __device__ __forceinline__ Reducer make_reducer(unsigned char* smem_raw, double* partials) {
     const int w = threadIdx.x >> 5;
     Reducer R;
@@ -342,13 +532,23 @@ __device__ __forceinline__ Reducer make_reducer(unsigned char* smem_raw, double*
     R.sm = reinterpret_cast<double*>(smem_raw);
     R.G = (int)gridDim.x;
     R.parity = 0;
-    unsigned char* wbase = smem_raw + ((kRedBytes + 127) / 128) * 128 + (size_t)w * kWarpSmemBytes;
+    unsigned char* wbase = smem_raw + kStageOff + (size_t)w * kWarpSmemBytes;
+    R.ws.bar_s = smem_u32(smem_raw + kBarOff + 8 * w);
+    R.ws.parity = 0;
+    R.ws.plan = reinterpret_cast<int*>(smem_raw + kPlanOff) + 8 * kPlanSlots * w;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < kPlanSlots; ++i) R.ws.plan[8 * i + 6] = 0;
+        mbar_init(R.ws.bar_s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();
+    __syncwarp();
     R.ws.base = wbase;
     R.ws.base_s = smem_u32(wbase);
-    R.ws.head = 0;
-    R.ws.inflight = 0;
     R.ws.cur = nullptr;
-    R.ws.next_c = 0;
+    R.ws.cur_c = 0;
+    R.ws.pc = reinterpret_cast<double*>(smem_raw + kSmemBytes);  // present only when the launch asked for it
     return R;
 }
 
@@ -371,7 +571,17 @@ __device__ __forceinline__ unsigned long long gtimer() {
         }                                                          \
     } while (0)
 #define PHASE_START(last) unsigned long long last = gtimer()
+// per-warp busy time of one SpMV phase: phase_ns[32 + which * W + global warp] (which: 0 = A', 1 = A)
+#define WARP_T0(t) unsigned long long t = gtimer()
+#define WARP_T1(c, t, which)                                                                              \
+    do {                                                                                                  \
+        if ((threadIdx.x & 31) == 0 && (c).phase_ns)                                                      \
+            (c).phase_ns[32 + (which) * gridDim.x * kWarps + blockIdx.x * kWarps + (threadIdx.x >> 5)] += \
+                (double)(gtimer() - (t));                                                                 \
+    } while (0)
 #else
+#define WARP_T0(t) do { } while (0)
+#define WARP_T1(c, t, which) do { } while (0)
 #define PHASE_MARK(c, last, id) do { } while (0)
 #define PHASE_START(last) do { } while (0)
 #endif
@@ -618,7 +828,9 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
     if (!(rn < fmin(tol, 1e-18))) {
         for (int it = 0; it < m; ++it) {
             // L1: tmp = A' p
+            WARP_T0(tw1);
             spmv_rows(c.AT, c.p, R.ws, &c.A, [&](int row, double a) { c.tmp[row] = a; });
+            WARP_T1(c, tw1, 0);
             grid.sync();
             PHASE_MARK(c, tl, 4);
             // L2: Gp = A tmp + rho p ; p.Gp
@@ -630,7 +842,9 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
                 d1[0] = fma(pi, gp, d1[0]);
             };
             if constexpr (!DIST) {
+                WARP_T0(tw2);
                 spmv_rows(c.A, c.tmp, R.ws, &c.AT, gp_epi);
+                WARP_T1(c, tw2, 1);
             } else {
                 double* slot = comm_vec_slot(c.comm, cs);
                 spmv_rows(c.A, c.tmp, R.ws, &c.AT, [&](int row, double a) { slot[row] = a; });

@@ -578,6 +578,12 @@ struct ABIPGPU_LP {
     int grid = 0, grid_mu = 0;  // every SpMV-bearing kernel uses the same persistent grid (the plan is per warp)
     // matrix
     int *A_ptr = nullptr, *A_idx = nullptr, *AT_ptr = nullptr, *AT_idx = nullptr, *A_wc = nullptr, *AT_wc = nullptr;
+    int *A_pcn = nullptr, *A_pcp = nullptr, *AT_pcn = nullptr, *AT_pcp = nullptr;  // page-cache plan (per CTA)
+    int *A_cl = nullptr, *AT_cl = nullptr;       // long-row tables (spmv_host.h: upload_long_rows)
+    int4 *A_lr = nullptr, *AT_lr = nullptr;
+    double *A_lp = nullptr, *AT_lp = nullptr;
+    size_t smem = kSmemBytes;  // dynamic shared memory of the persistent kernels (+ page cache)
+    int pc_slots = 0;
     int4 *A_chunk = nullptr, *AT_chunk = nullptr;
     double *A_val = nullptr, *AT_val = nullptr;
     // everything else lives in one slab
@@ -640,7 +646,7 @@ static int read_sc(abipgpu_lp* e, abip_float* sc) {
 
 template <class T>
 static int upload(T** dst, const std::vector<T>& src, abipgpu_lp* e) {
-    const size_t bytes = (src.size() + 8) * sizeof(T);  // +8: 16-byte aligned TMA windows may over-read
+    const size_t bytes = (src.size() + kPad) * sizeof(T);  // fixed-size staging windows over-read behind the arrays
     CK(cudaMalloc((void**)dst, bytes));
     CK(cudaMemsetAsync(*dst, 0, bytes, e->stream));
     if (!src.empty()) CK(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, e->stream));
@@ -713,16 +719,22 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     {
         int g1, g2, g3, g4;
         int h1, h2, h3;
-        if (coop_grid((const void*)k_admm_iter<false>, e->num_sms, kSmemBytes, &g1) ||
-            coop_grid((const void*)k_bb_round<false>, e->num_sms, kSmemBytes, &g2) ||
-            coop_grid((const void*)k_solve_vec<false>, e->num_sms, kSmemBytes, &g3) ||
-            coop_grid((const void*)k_admm_iter<true>, e->num_sms, kSmemBytes, &h1) ||
-            coop_grid((const void*)k_bb_round<true>, e->num_sms, kSmemBytes, &h2) ||
-            coop_grid((const void*)k_solve_vec<true>, e->num_sms, kSmemBytes, &h3) ||
+        // page cache of the gathered vectors: whole-device engines only (batch engines share the SMs)
+        e->pc_slots = t_grid_request > 0 ? 0 : std::max(0, std::min(env_int("ABIP_GPU_PC_SLOTS", kPcSlotsMax), kPcSlotsMax));
+#if !ABIP_PAGE_CACHE
+        e->pc_slots = 0;
+#endif
+        e->smem = kSmemBytes + (size_t)e->pc_slots * kPageDoubles * sizeof(double);
+        if (coop_grid((const void*)k_admm_iter<false>, e->num_sms, e->smem, &g1) ||
+            coop_grid((const void*)k_bb_round<false>, e->num_sms, e->smem, &g2) ||
+            coop_grid((const void*)k_solve_vec<false>, e->num_sms, e->smem, &g3) ||
+            coop_grid((const void*)k_admm_iter<true>, e->num_sms, e->smem, &h1) ||
+            coop_grid((const void*)k_bb_round<true>, e->num_sms, e->smem, &h2) ||
+            coop_grid((const void*)k_solve_vec<true>, e->num_sms, e->smem, &h3) ||
             coop_grid((const void*)k_mu_stats, e->num_sms, 0, &g4))
             return -1;
         g1 = std::min(g1, h1); g2 = std::min(g2, h2); g3 = std::min(g3, h3);
-        CK(cudaFuncSetAttribute((const void*)k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        CK(cudaFuncSetAttribute((const void*)k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMaxOptin));
         e->grid = std::min(g1, std::min(g2, g3));
         e->grid_mu = g4;
         if (t_grid_request > 0) {  // batch mode: several small engines share the device
@@ -734,15 +746,28 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     SpmvPlan planA, planAT;
     build_spmv_plan(a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA);
     build_spmv_plan(at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT);
+    // page-cache plan; the device-side equilibration needs the raw row indices of the CSC once more
+    PageCache pcA, pcAT;
+    std::vector<int> at_idx_raw;
+    if (scale_out && e->pc_slots > 0) at_idx_raw = at_idx;
+    {
+        const int min_refs = std::max(1, env_int("ABIP_GPU_PC_MINREFS", 4));
+        build_page_cache(planA, a_idx, n, e->grid, e->pc_slots, min_refs, &pcA);
+        build_page_cache(planAT, at_idx, m, e->grid, e->pc_slots, min_refs, &pcAT);
+    }
 
     if (scale_out) a_val.assign(1, 0.0);  // placeholder; the values are gathered on the device below
     if (upload(&e->A_ptr, a_ptr, e) || upload(&e->A_idx, a_idx, e) ||
-        (scale_out ? (cudaMalloc((void**)&e->A_val, (nnz + 8) * sizeof(double)) != cudaSuccess ||
-                      cudaMemsetAsync(e->A_val, 0, (nnz + 8) * sizeof(double), e->stream) != cudaSuccess)
+        (scale_out ? (cudaMalloc((void**)&e->A_val, (nnz + kPad) * sizeof(double)) != cudaSuccess ||
+                      cudaMemsetAsync(e->A_val, 0, (nnz + kPad) * sizeof(double), e->stream) != cudaSuccess)
                    : upload(&e->A_val, a_val, e)) ||
         upload(&e->AT_ptr, at_ptr, e) || upload(&e->AT_idx, at_idx, e) || upload(&e->AT_val, at_val, e) ||
         upload(&e->A_wc, planA.warp_chunk, e) || upload(&e->AT_wc, planAT.warp_chunk, e) ||
-        upload(&e->A_chunk, planA.chunk, e) || upload(&e->AT_chunk, planAT.chunk, e))
+        upload(&e->A_chunk, planA.chunk, e) || upload(&e->AT_chunk, planAT.chunk, e) ||
+        upload(&e->A_pcn, pcA.npages, e) || upload(&e->A_pcp, pcA.pages, e) ||
+        upload(&e->AT_pcn, pcAT.npages, e) || upload(&e->AT_pcp, pcAT.pages, e) ||
+        upload_long_rows(planA, &e->A_cl, &e->A_lr, &e->A_lp, e->stream) ||
+        upload_long_rows(planAT, &e->AT_cl, &e->AT_lr, &e->AT_lp, e->stream))
         return -1;
     const int gmax = std::max(e->grid, e->grid_mu);
 
@@ -750,7 +775,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     const size_t L = ((size_t)e->l + 31) & ~(size_t)31;
     const size_t Mm = ((size_t)m + 31) & ~(size_t)31, Nn = ((size_t)n + 31) & ~(size_t)31;
     const size_t n_l_vecs = 21 + 2;  // ids 0..20 + xin + yout
-    const size_t total = n_l_vecs * L + 7 * Mm + 3 * Nn + (size_t)2 * kMaxRed * gmax + 64 + ABIPGPU_SC_COUNT + 32;
+    const size_t total = n_l_vecs * L + 7 * Mm + 3 * Nn + (size_t)2 * kMaxRed * gmax + 64 + ABIPGPU_SC_COUNT + 32 + 2 * (size_t)gmax * kWarps;
     CK(cudaMalloc((void**)&e->slab, total * sizeof(double)));
     CK(cudaMemsetAsync(e->slab, 0, total * sizeof(double), e->stream));
     e->slab_doubles = total;
@@ -777,14 +802,16 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     e->tmp = take(Nn);
     e->partials = take((size_t)2 * kMaxRed * gmax + 64);
     e->dsc = take(ABIPGPU_SC_COUNT);
-    e->dphase = take(32);
+    e->dphase = take(32 + 2 * (size_t)gmax * kWarps);
     CK(cudaMallocHost((void**)&e->hsc, sizeof(double) * ABIPGPU_SC_COUNT));
 
     LpCtx& c = e->ctx;
     c.m = (int)m;
     c.n = (int)n;
-    c.A = Csr{e->A_ptr, e->A_idx, e->A_val, (int)m, e->A_wc, e->A_chunk, planA.lanes_log2};
-    c.AT = Csr{e->AT_ptr, e->AT_idx, e->AT_val, (int)n, e->AT_wc, e->AT_chunk, planAT.lanes_log2};
+    c.A = Csr{e->A_ptr, e->A_idx, e->A_val, (int)m, e->A_wc, e->A_chunk, planA.lanes_log2,
+              (int)n, pcA.stride, e->pc_slots > 0 ? e->A_pcn : nullptr, e->A_pcp, e->A_cl, e->A_lr, e->A_lp, 1};
+    c.AT = Csr{e->AT_ptr, e->AT_idx, e->AT_val, (int)n, e->AT_wc, e->AT_chunk, planAT.lanes_log2,
+               (int)m, pcAT.stride, e->pc_slots > 0 ? e->AT_pcn : nullptr, e->AT_pcp, e->AT_cl, e->AT_lr, e->AT_lp, 2};
     c.M = e->dM;
     c.D = nullptr;
     c.E = nullptr;
@@ -811,8 +838,10 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
 #endif
 
     if (scale_out) {
-        int* d_perm = nullptr;
+        int *d_perm = nullptr, *d_raw = nullptr;
         if (upload(&d_perm, perm, e)) return -1;
+        if (!at_idx_raw.empty() && upload(&d_raw, at_idx_raw, e)) return -1;
+        const int* at_rows = d_raw ? d_raw : e->AT_idx;
         const double min_row = 1e-3 * sqrt((double)n), max_row = 1e3 * sqrt((double)n);
         const double min_col = 1e-3 * sqrt((double)m), max_col = 1e3 * sqrt((double)m);
         double* Dt = e->p;  // scratch [m]
@@ -822,7 +851,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         auto sweep = [&](int kind) {
             k_eq_cols<<<gn, 256, 0, e->stream>>>(kind, e->AT_ptr, e->AT_val, (int)n, e->dE, min_col, max_col);
             k_eq_rows<<<gm, 256, 0, e->stream>>>(kind, e->A_ptr, d_perm, e->AT_val, (int)m, Dt, e->dD, min_row, max_row);
-            k_eq_apply_rows<<<gz, 256, 0, e->stream>>>(e->AT_idx, e->AT_val, nnz, Dt);
+            k_eq_apply_rows<<<gz, 256, 0, e->stream>>>(at_rows, e->AT_val, nnz, Dt);
         };
         if (stgs->pc_ruiz_rescale) sweep(0);
         if (stgs->origin_rescale) sweep(1);
@@ -853,6 +882,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(e->stream));
         cudaFree(d_perm);
+        cudaFree(d_raw);
         e->stats.d2h_bytes += 8.0 * 2 * (m + n);
     }
     k_precond<<<(unsigned)((m + 255) / 256), 256, 0, e->stream>>>(c.A, e->dM);
@@ -865,10 +895,11 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     snprintf(e->desc, sizeof(e->desc),
              "device %d (%s, %d SMs) persistent grid %d x %d threads, %zu B smem/block | CSR(A): %d rows, mean %.1f max %d "
              "nnz/row, %zu chunks (%d long rows), %d lane(s)/row | CSR(A'): %d rows, mean %.1f max %d, %zu chunks (%d long), "
-             "%d lane(s)/row | nnz=%ld",
-             device, prop.name, e->num_sms, e->grid, kBlock, (size_t)kSmemBytes, (int)m, planA.mean, planA.max_len,
+             "%d lane(s)/row | nnz=%ld | page cache %d x 256 B per CTA: %.1f%% of the gathers of A, %.1f%% of A' from shared memory",
+             device, prop.name, e->num_sms, e->grid, kBlock, (size_t)e->smem, (int)m, planA.mean, planA.max_len,
              planA.chunk.size(), planA.n_long, 1 << planA.lanes_log2, (int)n, planAT.mean, planAT.max_len,
-             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz);
+             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, e->pc_slots, 100.0 * pcA.hits / nnz,
+             100.0 * pcAT.hits / nnz);
     return 0;
 }
 
@@ -918,6 +949,8 @@ void abipgpu_lp_destroy(abipgpu_lp* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->A_ptr); cudaFree(e->A_idx); cudaFree(e->A_val);
     cudaFree(e->AT_ptr); cudaFree(e->AT_idx); cudaFree(e->AT_val);
+    cudaFree(e->A_pcn); cudaFree(e->A_pcp); cudaFree(e->AT_pcn); cudaFree(e->AT_pcp);
+    cudaFree(e->A_cl); cudaFree(e->AT_cl); cudaFree(e->A_lr); cudaFree(e->AT_lr); cudaFree(e->A_lp); cudaFree(e->AT_lp);
     cudaFree(e->A_wc); cudaFree(e->AT_wc); cudaFree(e->A_chunk); cudaFree(e->AT_chunk);
     for (int q = 0; q < kMaxRanks; ++q)
         if (e->peer_bufs[q] && q != e->dist_rank) cudaIpcCloseMemHandle(e->peer_bufs[q]);
@@ -949,7 +982,7 @@ int abipgpu_lp_set_problem(abipgpu_lp* e, const abip_float* b, const abip_float*
     e->ctx.E = e->have_scaling ? e->dE : nullptr;
     k_build_h<<<(m + n + 255) / 256, 256, 0, e->stream>>>(e->db, e->dc, e->vec[ABIPGPU_VEC_H], e->vec[ABIPGPU_VEC_G], m, n);
     CK(cudaGetLastError());
-    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_solve_vec<true> : (const void*)k_solve_vec<false>, e->grid, kSmemBytes, e->ctx, e->vec[ABIPGPU_VEC_G], (const double*)nullptr,
+    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_solve_vec<true> : (const void*)k_solve_vec<false>, e->grid, e->smem, e->ctx, e->vec[ABIPGPU_VEC_G], (const double*)nullptr,
                     (long)-1, 1))
         return -1;
     if (read_sc(e, nullptr)) return -1;
@@ -1018,7 +1051,7 @@ int abipgpu_lp_admm_iter(abipgpu_lp* e, abip_int j, abip_int k, abip_float mu, a
     // both give the same residue class, so the firing rule reduces to (j+1) % fre == 0
     if (a.restart_active && e->stgs.restart_fre > 0 && (j + 1) % e->stgs.restart_fre == 0) a.restart_fire = 1;
     CK(cudaEventRecord(e->ev0, e->stream));
-    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_admm_iter<true> : (const void*)k_admm_iter<false>, e->grid, kSmemBytes, e->ctx, a)) return -1;
+    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_admm_iter<true> : (const void*)k_admm_iter<false>, e->grid, e->smem, e->ctx, a)) return -1;
     CK(cudaEventRecord(e->ev1, e->stream));
     if (read_sc(e, sc)) return -1;
     float ms = 0;
@@ -1086,7 +1119,7 @@ int abipgpu_lp_bb_round(abipgpu_lp* e, int carry, abip_int k, abip_float mu, abi
     a.mu = mu;
     a.beta_prev = beta_prev;
     CK(cudaEventRecord(e->ev0, e->stream));
-    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_bb_round<true> : (const void*)k_bb_round<false>, e->grid, kSmemBytes, e->ctx, a)) return -1;
+    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_bb_round<true> : (const void*)k_bb_round<false>, e->grid, e->smem, e->ctx, a)) return -1;
     CK(cudaEventRecord(e->ev1, e->stream));
     if (read_sc(e, sc)) return -1;
     float ms = 0;
@@ -1105,7 +1138,7 @@ int abipgpu_lp_solve_vec(abipgpu_lp* e, int rhs_id, int warm_id, abip_int iter, 
     CK(cudaSetDevice(e->device));
     if (rhs_id < 0 || rhs_id > 20 || warm_id > 20) return -1;
     const double* s = warm_id >= 0 ? e->vec[warm_id] : nullptr;
-    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_solve_vec<true> : (const void*)k_solve_vec<false>, e->grid, kSmemBytes, e->ctx, e->vec[rhs_id], s, (long)iter, 0)) return -1;
+    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_solve_vec<true> : (const void*)k_solve_vec<false>, e->grid, e->smem, e->ctx, e->vec[rhs_id], s, (long)iter, 0)) return -1;
     if (read_sc(e, sc)) return -1;
     account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], s != nullptr);
     return 0;
@@ -1145,7 +1178,7 @@ int abipgpu_lp_spmv_host(abipgpu_lp* e, int trans, const double* x, double* y, i
     const int nin = trans ? e->m : e->n, nout = trans ? e->n : e->m;
     CK(cudaMemcpyAsync(e->xin, x, sizeof(double) * nin, cudaMemcpyHostToDevice, e->stream));
     if (accumulate) CK(cudaMemcpyAsync(e->yout, y, sizeof(double) * nout, cudaMemcpyHostToDevice, e->stream));
-    k_spmv<<<e->grid, kBlock, kSmemBytes, e->stream>>>(trans ? e->ctx.AT : e->ctx.A, e->xin, e->yout, accumulate);
+    k_spmv<<<e->grid, kBlock, e->smem, e->stream>>>(trans ? e->ctx.AT : e->ctx.A, e->xin, e->yout, accumulate);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(y, e->yout, sizeof(double) * nout, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -1162,7 +1195,7 @@ int abipgpu_lp_solve_host(abipgpu_lp* e, double* b, const double* s, long iter, 
     const int mn = e->m + e->n;
     CK(cudaMemcpyAsync(e->xin, b, sizeof(double) * mn, cudaMemcpyHostToDevice, e->stream));
     if (s) CK(cudaMemcpyAsync(e->yout, s, sizeof(double) * e->m, cudaMemcpyHostToDevice, e->stream));
-    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_solve_vec<true> : (const void*)k_solve_vec<false>, e->grid, kSmemBytes, e->ctx, e->xin, (const double*)(s ? e->yout : nullptr),
+    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_solve_vec<true> : (const void*)k_solve_vec<false>, e->grid, e->smem, e->ctx, e->xin, (const double*)(s ? e->yout : nullptr),
                     iter, 0))
         return -1;
     CK(cudaMemcpyAsync(b, e->xin, sizeof(double) * mn, cudaMemcpyDeviceToHost, e->stream));
@@ -1245,6 +1278,25 @@ extern "C" int abipgpu_lp_phase_times(abipgpu_lp* e, double* out32, int reset) {
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
+extern "C" int abipgpu_lp_warp_times(abipgpu_lp* e, double* out, int* W) {  // [2][W] per-warp SpMV busy ns (debug builds)
+    CK(cudaSetDevice(e->device));
+    *W = e->grid * kWarps;
+    CK(cudaMemcpyAsync(out, e->dphase + 32, sizeof(double) * 2 * (*W), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+#ifdef ABIP_PHASE_TIMING
+extern "C" int abipgpu_lp_spmv_prof(abipgpu_lp* e, unsigned long long* out16, int reset) {
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpyFromSymbol(out16, g_spmv_prof, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        CK(cudaMemcpyToSymbol(g_spmv_prof, z, sizeof(z)));
+    }
+    return 0;
+}
+#endif
 int abipgpu_lp_solve_timer(abipgpu_lp* e, int stop) {  // CUDA events on the engine stream around a whole solve
     CK(cudaSetDevice(e->device));
     if (!stop) {

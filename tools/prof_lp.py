@@ -36,3 +36,26 @@ if hasattr(L, 'abipgpu_lp_phase_times'):
         for i, nm in enumerate(names):
             if out[16 + i] > 0:
                 print('phase %-9s count %6d  avg %8.2f us  total %8.2f ms' % (nm, out[16 + i], out[i] / out[16 + i] / 1e3, out[i] / 1e6))
+if hasattr(L, 'abipgpu_lp_warp_times') and out[16:].sum() > 0:
+    W = C.c_int(0)
+    buf = np.zeros(2 * 148 * 32 * 4)
+    L.abipgpu_lp_warp_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.abipgpu_lp_warp_times(e.e, buf.ctypes.data_as(C.POINTER(C.c_double)), C.byref(W))
+    W = W.value
+    calls = out[16 + 4]
+    for which, nm in ((0, "A' pass"), (1, 'A pass')):
+        t = buf[which * W:(which + 1) * W] / max(calls, 1) / 1e3   # us per call per warp
+        cta = t.reshape(-1, 32)
+        print('%s per-warp busy us: min %.1f p10 %.1f mean %.1f p90 %.1f max %.1f | per-CTA max: min %.1f mean %.1f max %.1f | per-CTA mean: min %.1f max %.1f'
+              % (nm, t.min(), np.percentile(t, 10), t.mean(), np.percentile(t, 90), t.max(), cta.max(1).min(), cta.max(1).mean(),
+                 cta.max(1).max(), cta.mean(1).min(), cta.mean(1).max()))
+        srt = np.argsort(cta.max(1))
+        print('   slowest CTAs', srt[-6:], cta.max(1)[srt[-6:]].round(1), 'fastest', srt[:4], cta.max(1)[srt[:4]].round(1))
+if hasattr(L, 'abipgpu_lp_spmv_prof'):
+    pr = (C.c_ulonglong * 16)()
+    L.abipgpu_lp_spmv_prof.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]
+    L.abipgpu_lp_spmv_prof(e.e, pr, 0)
+    for b, nm in ((0, "A'"), (8, 'A ')):
+        nch = max(pr[b + 4], 1)
+        print('%s chunk loop, cycles per chunk per warp: wait %.0f  gather+mul %.0f  rowsum+epi %.0f  issue %.0f  (chunks %d)'
+              % (nm, pr[b] / nch, pr[b + 1] / nch, pr[b + 2] / nch, pr[b + 3] / nch, pr[b + 4]))
