@@ -405,6 +405,34 @@ __device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, WarpSme
         SPROF(0);
         const int row0 = d.x, s = d.y, nr = d.z, n = d.w;
         const int off = s & 3;
+        if (nr > 0 && L == 1) {
+            // short rows (mean <= 16 nonzeros): one lane per row straight out of the staged windows -- index, value,
+            // gather, multiply, add in the row's own order (the reference's summation order, no FMA contraction so the
+            // result does not depend on the path).  No product round trip through shared memory: per 32 nonzeros ~19
+            // L1 data-pipe wavefronts instead of ~27, and neighbouring rows gather neighbouring columns together.
+            const double* vs = vw + off - s;
+            const int* is = iw + off - s;
+            const int* rp = reinterpret_cast<const int*>(st + kValWin + kIdxWin) + (row0 & 3);
+            for (int rr = lane; rr < nr; rr += 32) {
+                const int a = rp[rr], b = rp[rr + 1];
+                double acc = 0.0;
+#pragma unroll 4
+                for (int k = a; k < b; ++k) acc = __dadd_rn(acc, __dmul_rn(vs[k], gather_x(x, pc, is[k])));
+                fn(row0 + rr, acc);
+            }
+            SPROF(1);
+            __syncwarp();
+            SPROF(2);
+            if (c + 1 < c1) ws.issue(A, c + 1, dn);
+            else if (next && nx_c < nx_c1) ws.issue(*next, nx_c, dn);
+            else ws.cur = nullptr;
+            d = dn;
+            SPROF(3);
+#ifdef ABIP_PHASE_TIMING
+            ++_pn;
+#endif
+            continue;
+        }
         // 1. gather x for the whole window (8 independent loads per lane), multiply
         double xv[2][4];
         int4 ci[2];

@@ -45,7 +45,9 @@ if hasattr(L, 'abipgpu_lp_warp_times') and out[16:].sum() > 0:
     calls = out[16 + 4]
     for which, nm in ((0, "A' pass"), (1, 'A pass')):
         t = buf[which * W:(which + 1) * W] / max(calls, 1) / 1e3   # us per call per warp
-        cta = t.reshape(-1, 32)
+        import re
+        wpc = int(re.search(r'x (\d+) threads', e.describe()).group(1)) // 32
+        cta = t.reshape(-1, wpc)
         print('%s per-warp busy us: min %.1f p10 %.1f mean %.1f p90 %.1f max %.1f | per-CTA max: min %.1f mean %.1f max %.1f | per-CTA mean: min %.1f max %.1f'
               % (nm, t.min(), np.percentile(t, 10), t.mean(), np.percentile(t, 90), t.max(), cta.max(1).min(), cta.max(1).mean(),
                  cta.max(1).max(), cta.mean(1).min(), cta.mean(1).max()))
