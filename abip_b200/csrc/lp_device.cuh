@@ -31,6 +31,17 @@ constexpr int kBlock = ABIP_BLOCK;
 constexpr int kWarps = kBlock / 32;
 constexpr int kMaxRed = 24;  // max scalars reduced between two grid barriers
 
+// Virtual grid: the persistent device code never reads blockIdx / gridDim directly.  An ordinary launch maps them
+// 1:1; the batched launch (k_batch, lp_engine.cu: one CTA = one independent small LP) presents every CTA as block 0 of a
+// one-block grid, so the same phases run unchanged and the grid barrier degenerates to a CTA barrier.
+__shared__ int2 s_vgrid;  // {block id, number of blocks}
+__device__ __forceinline__ int VB() { return s_vgrid.x; }
+__device__ __forceinline__ int VG() { return s_vgrid.y; }
+__device__ __forceinline__ void vgrid_init(bool batched) {
+    if (threadIdx.x == 0) s_vgrid = batched ? make_int2(0, 1) : make_int2((int)blockIdx.x, (int)gridDim.x);
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Asynchronous global -> shared staging of the matrix arrays (cp.async 16 B per lane, SASS LDGSTS, L2-only
 // caching so the stream does not evict the gathered vector from L1).  No registers are tied up by the loads in
@@ -152,7 +163,7 @@ struct WarpSmem {
     // this warp's chunk range [c0, c1) of A and the descriptor of its first chunk.  The three dependent global loads
     // cost ~2 us at the start of every phase; the two matrices of the CG loop are cached in shared memory instead.
     __device__ __forceinline__ void get_plan(const Csr& A, int& c0, int& c1, int4& d0) {
-        const int gwarp = blockIdx.x * kWarps + (threadIdx.x >> 5);
+        const int gwarp = VB() * kWarps + (threadIdx.x >> 5);
         int* e = plan + 8 * (A.plan_slot - 1);
         if (A.plan_slot > 0) {
             const int4 r = *reinterpret_cast<const int4*>(e + 4);
@@ -229,7 +240,7 @@ struct Reducer {
             double s = 0.0;
 #pragma unroll
             for (int i = 0; i < kWarps; ++i) s += sm[threadIdx.x * kWarps + i];
-            partials[(parity * kMaxRed + slot0 + threadIdx.x) * G + blockIdx.x] = s;
+            partials[(parity * kMaxRed + slot0 + threadIdx.x) * G + VB()] = s;
         }
         __syncthreads();
         // the grid barrier that follows orders these writes before finish()
@@ -251,7 +262,7 @@ struct Reducer {
             double s = 0.0;
 #pragma unroll
             for (int i = 0; i < kWarps; ++i) s = fmax(s, sm[threadIdx.x * kWarps + i]);
-            partials[(parity * kMaxRed + slot0 + threadIdx.x) * G + blockIdx.x] = s;
+            partials[(parity * kMaxRed + slot0 + threadIdx.x) * G + VB()] = s;
         }
         __syncthreads();
     }
@@ -312,8 +323,8 @@ constexpr int kPcMaxPages = 512;
 __device__ __forceinline__ void spmv_load_pages(const Csr& A, const double* x, WarpSmem& ws) {
     constexpr int J = kPcMaxPages * (kPageDoubles / 2) / kBlock;  // units per thread
     constexpr int PJ = kBlock / (kPageDoubles / 2);               // pages per round
-    const int np = __ldg(A.cta_npages + blockIdx.x);
-    const int* pg = A.cta_pages + (size_t)blockIdx.x * A.pc_stride;
+    const int np = __ldg(A.cta_npages + VB());
+    const int* pg = A.cta_pages + (size_t)VB() * A.pc_stride;
     const int p0 = threadIdx.x / (kPageDoubles / 2), u = threadIdx.x % (kPageDoubles / 2);
     int id[J];
 #pragma unroll
@@ -529,7 +540,7 @@ __device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, WarpSme
     }
     // long rows of this CTA: add the piece sums in piece order (pieces were computed by different warps of the CTA)
     if (A.long_rows) {
-        const int j0 = __ldg(A.cta_long + blockIdx.x), j1 = __ldg(A.cta_long + blockIdx.x + 1);
+        const int j0 = __ldg(A.cta_long + VB()), j1 = __ldg(A.cta_long + VB() + 1);
         if (j0 < j1) {  // uniform per CTA
             __syncthreads();
             for (int j = j0 + (int)threadIdx.x; j < j1; j += kBlock) {
@@ -551,14 +562,15 @@ constexpr size_t kPlanOff = ((kBarOff + 8 * kWarps + 15) / 16) * 16;            
 constexpr size_t kStageOff = ((kPlanOff + 32 * kPlanSlots * kWarps + 127) / 128) * 128;
 constexpr size_t kSmemBytes = kStageOff + (size_t)kWarps * kWarpSmemBytes;
 // ... followed by the optional page cache [slots * 256 B] (LP engine; launch with kSmemBytes + slots * 256)
-constexpr int kSmemMaxOptin = 232448;  // 227 KB per CTA on sm_100
+constexpr int kSmemMaxOptin = 232448 - 1024;  // 227 KB per CTA on sm_100, minus the static shared memory of the kernels
 constexpr int kPcSlotsMax = (kSmemMaxOptin - (int)kSmemBytes) / (kPageDoubles * 8) < 512 ? (kSmemMaxOptin - (int)kSmemBytes) / (kPageDoubles * 8) : 512;
-__device__ __forceinline__ Reducer make_reducer(unsigned char* smem_raw, double* partials) {
+__device__ __forceinline__ Reducer make_reducer(unsigned char* smem_raw, double* partials, bool batched = false) {
+    vgrid_init(batched);
     const int w = threadIdx.x >> 5;
     Reducer R;
     R.partials = partials;
     R.sm = reinterpret_cast<double*>(smem_raw);
-    R.G = (int)gridDim.x;
+    R.G = VG();
     R.parity = 0;
     unsigned char* wbase = smem_raw + kStageOff + (size_t)w * kWarpSmemBytes;
     R.ws.bar_s = smem_u32(smem_raw + kBarOff + 8 * w);
@@ -591,7 +603,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 #define PHASE_MARK(c, last, id)                                    \
     do {                                                           \
-        if (blockIdx.x == 0 && threadIdx.x == 0 && (c).phase_ns) { \
+        if (VB() == 0 && threadIdx.x == 0 && (c).phase_ns) { \
             const unsigned long long _t = gtimer();                \
             (c).phase_ns[(id)] += (double)(_t - (last));           \
             (c).phase_ns[16 + (id)] += 1.0;                        \
@@ -604,7 +616,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define WARP_T1(c, t, which)                                                                              \
     do {                                                                                                  \
         if ((threadIdx.x & 31) == 0 && (c).phase_ns)                                                      \
-            (c).phase_ns[32 + (which) * gridDim.x * kWarps + blockIdx.x * kWarps + (threadIdx.x >> 5)] += \
+            (c).phase_ns[32 + (which) * VG() * kWarps + VB() * kWarps + (threadIdx.x >> 5)] += \
                 (double)(gtimer() - (t));                                                                 \
     } while (0)
 #else
@@ -614,8 +626,18 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define PHASE_START(last) do { } while (0)
 #endif
 
+// grid barrier; an engine confined to one CTA (batches of small LPs, one CTA per problem) only needs a CTA barrier
+__device__ __forceinline__ void grid_sync(cg::grid_group& grid) {
+    if (VG() == 1) {
+        __threadfence_block();
+        __syncthreads();
+    } else {
+        grid.sync();
+    }
+}
+
 #define GRID_STRIDE(i, N) \
-    for (int i = blockIdx.x * kBlock + threadIdx.x, _gs = gridDim.x * kBlock; i < (N); i += _gs)
+    for (int i = VB() * kBlock + threadIdx.x, _gs = VG() * kBlock; i < (N); i += _gs)
 
 // ---------------------------------------------------------------------------------------------------------
 // Multi-GPU: in-kernel collectives over NVLink peer memory (one process per GPU, buffers shared through CUDA IPC).
@@ -660,7 +682,7 @@ struct CommState {
 // last write); wait until every rank has published.  Ends with all threads of the grid released.
 __device__ __forceinline__ void comm_exchange(const Comm& cm, CommState& st, cg::grid_group& grid) {
     st.seq += 1;
-    if (blockIdx.x == 0 && threadIdx.x < cm.G) {
+    if (VB() == 0 && threadIdx.x < cm.G) {
         __threadfence_system();
         st_release_sys(cm.flags[threadIdx.x] + cm.rank, st.seq);
     }
@@ -687,7 +709,7 @@ __device__ __forceinline__ void comm_exchange(const Comm& cm, CommState& st, cg:
 // element is the same rank-ordered sum on every rank.
 template <class Fn>
 __device__ __forceinline__ void comm_sum_vec(const Comm& cm, CommState& st, cg::grid_group& grid, int m, Fn fn) {
-    grid.sync();  // local partials complete
+    grid_sync(grid);  // local partials complete
     comm_exchange(cm, st, grid);
     const long off = (long)(st.seq & 1ull) * cm.m_pad;
     if (cm.G <= 2) {
@@ -708,11 +730,11 @@ __device__ __forceinline__ void comm_sum_vec(const Comm& cm, CommState& st, cg::
         }
         // (red is single-buffered: it is written only after the exchange above, i.e. after every rank has finished
         //  all reads of the previous collective)
-        grid.sync();
+        grid_sync(grid);
         comm_exchange(cm, st, grid);
         // collect the reduced slices: 4 independent peer loads in flight per thread (peer latency ~ 2-3 us)
-        const int gs = gridDim.x * kBlock;
-        for (int i0 = blockIdx.x * kBlock + threadIdx.x; i0 < m; i0 += 4 * gs) {
+        const int gs = VG() * kBlock;
+        for (int i0 = VB() * kBlock + threadIdx.x; i0 < m; i0 += 4 * gs) {
             double v4[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -736,9 +758,9 @@ template <int K>
 __device__ __forceinline__ void comm_sum_scalars(const Comm& cm, CommState& st, cg::grid_group& grid, double (&vals)[K]) {
     static_assert(K <= kCommScalars, "too many scalars");
     double* mine = cm.scal[cm.rank] + ((st.seq + 1) & 1ull) * kCommScalars;
-    if (blockIdx.x == 0 && threadIdx.x == 0)
+    if (VB() == 0 && threadIdx.x == 0)
         for (int k = 0; k < K; ++k) mine[k] = vals[k];
-    grid.sync();
+    grid_sync(grid);
     comm_exchange(cm, st, grid);
     const long off = (long)(st.seq & 1ull) * kCommScalars;
 #pragma unroll
@@ -810,7 +832,7 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
         });
     }
     R.block_store<1>(a1);
-    grid.sync();
+    grid_sync(grid);
     R.finish<1>(a1);
     PHASE_MARK(c, tl, 2);
     double tol = sqrt(a1[0]) * (iter < 0 ? 1e-9 : 0.1 / pow((double)iter + 1.0, c.cg_rate));
@@ -847,7 +869,7 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
         }
     }
     R.block_store<2>(a2);
-    grid.sync();
+    grid_sync(grid);
     R.finish<2>(a2);
     PHASE_MARK(c, tl, 3);
     double rn = sqrt(a2[0]);
@@ -859,7 +881,7 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
             WARP_T0(tw1);
             spmv_rows(c.AT, c.p, R.ws, &c.A, [&](int row, double a) { c.tmp[row] = a; });
             WARP_T1(c, tw1, 0);
-            grid.sync();
+            grid_sync(grid);
             PHASE_MARK(c, tl, 4);
             // L2: Gp = A tmp + rho p ; p.Gp
             double d1[1] = {0.0};
@@ -879,7 +901,7 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
                 comm_sum_vec(c.comm, cs, grid, m, gp_epi);
             }
             R.block_store<1>(d1);
-            grid.sync();
+            grid_sync(grid);
             R.finish<1>(d1);
             PHASE_MARK(c, tl, 5);
             const double alpha = ipzr / d1[0];
@@ -894,7 +916,7 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
                 d2[1] = fma(zi, ri, d2[1]);
             }
             R.block_store<2>(d2);
-            grid.sync();
+            grid_sync(grid);
             R.finish<2>(d2);
             PHASE_MARK(c, tl, 6);
             its = it + 1;
@@ -904,7 +926,7 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
             ipzr = d2[1];
             // L4: p = beta p + M r
             GRID_STRIDE(i, m) c.p[i] = fma(beta, c.p[i], __ldg(c.M + i) * c.r[i]);
-            grid.sync();
+            grid_sync(grid);
             PHASE_MARK(c, tl, 7);
         }
     }
@@ -969,7 +991,7 @@ __device__ __forceinline__ void dev_build_rhs(const LpCtx& c, Reducer& R, cg::gr
         const int slot = (DIST && i >= m) ? 1 : 0;
         a[slot] = fma(w, __ldg(c.g + i), a[slot]);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (VB() == 0 && threadIdx.x == 0) {
         ut[lm1] = tt;
         if (u_prev_out) u_prev_out[lm1] = u[lm1];
     }
@@ -977,12 +999,12 @@ __device__ __forceinline__ void dev_build_rhs(const LpCtx& c, Reducer& R, cg::gr
     if constexpr (!DIST) {
         double a1[1] = {a[0]};
         R.block_store<1>(a1);
-        grid.sync();
+        grid_sync(grid);
         R.finish<1>(a1);
         dot = a1[0];
     } else {
         R.block_store<2>(a);
-        grid.sync();
+        grid_sync(grid);
         R.finish<2>(a);
         double x[1] = {a[1]};
         comm_sum_scalars<1>(c.comm, cs, grid, x);
@@ -994,7 +1016,7 @@ __device__ __forceinline__ void dev_build_rhs(const LpCtx& c, Reducer& R, cg::gr
         if (i >= m) w = -w;
         ut[i] = w;
     }
-    grid.sync();
+    grid_sync(grid);
 }
 
 // barrier proximal step on one coordinate (src/abip.c:742-746)

@@ -84,10 +84,9 @@ __device__ __forceinline__ void write_qnorm_sc(double* sc, int base, const doubl
 
 // One full inner ADMM iteration (src/abip.c:2133-2173).
 template <bool DIST>
-__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_admm_iter(LpCtx c, IterArgs a) {
+__device__ __forceinline__ void body_admm_iter(const LpCtx& c, const IterArgs& a, unsigned char* smem_raw, bool batched) {
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Reducer R = make_reducer(smem_raw, c.partials);
+    Reducer R = make_reducer(smem_raw, c.partials, batched);
     CommState cs{DIST ? *c.comm.seq : 0ull, false};
     const int m = c.m, lm1 = c.m + c.n, l = lm1 + 1;
 
@@ -96,7 +95,7 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_admm_iter(Lp
     PHASE_MARK(c, tk, 0);
     SolveOut so;
     dev_solve_lin_sys<true, DIST>(c, R, grid, cs, a.ut, a.u, a.k, so);
-    grid.sync();
+    grid_sync(grid);
     double hd[1];
     hd[0] = dev_finish_epi_dot<DIST>(c, R, grid, cs);
     PHASE_START(tk2);
@@ -154,7 +153,7 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_admm_iter(Lp
             a.v_avgc[i] = vs / dom;
         }
     }
-    grid.sync();
+    grid_sync(grid);
     PHASE_MARK(c, tk2, 9);
 
     // iterate_Q_norm_resd sums (abip.c:1951-2051); every 10th inner iteration also on the running average
@@ -162,7 +161,7 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_admm_iter(Lp
     dev_qnorm_sums<DIST>(c, R, grid, cs, a.u, a.v, a.half_update, 0, has_avg != 0);
     if (has_avg) dev_qnorm_sums<DIST>(c, R, grid, cs, a.u_avgc, a.v_avgc, a.half_update, 11, false);
     R.ws.drain();
-    grid.sync();
+    grid_sync(grid);
     double t[22];
     if (has_avg) R.finish<22>(t);
     else {
@@ -175,13 +174,13 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_admm_iter(Lp
         for (int q = 0; q < 6; ++q) { x[q] = t[5 + q]; x[6 + q] = has_avg ? t[16 + q] : 0.0; }
         comm_sum_scalars<12>(c.comm, cs, grid, x);
         for (int q = 0; q < 6; ++q) { t[5 + q] = x[q]; if (has_avg) t[16 + q] = x[6 + q]; }
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (VB() == 0 && threadIdx.x == 0) {
             *c.comm.seq = cs.seq;
             c.sc[ABIPGPU_SC_COMM_ERR] = cs.failed ? 1.0 : 0.0;
         }
     }
     PHASE_MARK(c, tk2, 10);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (VB() == 0 && threadIdx.x == 0) {
         c.sc[ABIPGPU_SC_CG_ITS] = (double)so.its;
         c.sc[ABIPGPU_SC_CG_TOL] = so.tol;
         c.sc[ABIPGPU_SC_CG_RES] = so.res;
@@ -210,7 +209,7 @@ __device__ __forceinline__ void dev_bb_half(const LpCtx& c, Reducer& R, cg::grid
     SolveOut so;
     dev_solve_lin_sys<true, DIST>(c, R, grid, cs, ut, up, k, so);
     its = so.its;
-    grid.sync();
+    grid_sync(grid);
     double hd[1];
     hd[0] = dev_finish_epi_dot<DIST>(c, R, grid, cs);
     const double al = c.alpha;
@@ -253,7 +252,7 @@ __device__ __forceinline__ void dev_bb_half(const LpCtx& c, Reducer& R, cg::grid
             R.block_store<5>(d5);
         }
     }
-    grid.sync();
+    grid_sync(grid);
     if (dots) {
         if constexpr (DIST) {
             R.finish<10>(d);
@@ -265,17 +264,16 @@ __device__ __forceinline__ void dev_bb_half(const LpCtx& c, Reducer& R, cg::grid
             R.finish<5>(d5);
             for (int q = 0; q < 5; ++q) d[q] = d5[q];
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0)
+        if (VB() == 0 && threadIdx.x == 0)
             for (int q = 0; q < 5; ++q) c.sc[ABIPGPU_SC_BB_UTUT + q] = d[q];
     }
 }
 
 // One lookback round of the Barzilai-Borwein search (src/adaptive.c:89-178).
 template <bool DIST>
-__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_bb_round(LpCtx c, BBArgs a) {
+__device__ __forceinline__ void body_bb_round(const LpCtx& c, const BBArgs& a, unsigned char* smem_raw, bool batched) {
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Reducer R = make_reducer(smem_raw, c.partials);
+    Reducer R = make_reducer(smem_raw, c.partials, batched);
     CommState cs{DIST ? *c.comm.seq : 0ull, false};
     const int m = c.m, l = c.m + c.n + 1;
     const double lam = a.mu / a.beta_prev;
@@ -285,17 +283,17 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_bb_round(LpC
             a.u_prev[i] = ui;
             a.v_prev[i] = (a.carry == 1 && i >= m) ? lam / ui : a.v[i];
         }
-        grid.sync();
+        grid_sync(grid);
     }
     int its1, its2;
     dev_bb_half<DIST>(c, R, grid, cs, a.u_prev, a.v_prev, a.ut, a.u, a.v, a.k, lam, nullptr, false, its1);
     dev_bb_half<DIST>(c, R, grid, cs, a.u, a.v, a.ut_next, a.u_next, a.v_next, a.k, lam, a.v_prev, true, its2);
     R.ws.drain();  // no asynchronous copy may be outstanding when the CTA exits
-    if (DIST && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (DIST && VB() == 0 && threadIdx.x == 0) {
         *c.comm.seq = cs.seq;
         c.sc[ABIPGPU_SC_COMM_ERR] = cs.failed ? 1.0 : 0.0;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (VB() == 0 && threadIdx.x == 0) {
         c.sc[ABIPGPU_SC_CG_ITS] = (double)its1;
         c.sc[ABIPGPU_SC_CG_ITS2] = (double)its2;
     }
@@ -314,7 +312,7 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
     dev_solve_lin_sys<false, DIST>(c, R, grid, cs, b, s, iter, so);
     R.ws.drain();
     if (post_g) {
-        grid.sync();
+        grid_sync(grid);
         const int m = c.m, lm1 = c.m + c.n;
         double a[2] = {0.0, 0.0};
         GRID_STRIDE(i, lm1) {
@@ -324,20 +322,20 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
             a[slot] = fma(__ldg(c.h + i), gi, a[slot]);
         }
         R.block_store<2>(a);
-        grid.sync();
+        grid_sync(grid);
         R.finish<2>(a);
         if constexpr (DIST) {
             double x[1] = {a[1]};
             comm_sum_scalars<1>(c.comm, cs, grid, x);
             a[1] = x[0];
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0) c.sc[ABIPGPU_SC_VEC_NORM2] = a[0] + a[1];
+        if (VB() == 0 && threadIdx.x == 0) c.sc[ABIPGPU_SC_VEC_NORM2] = a[0] + a[1];
     }
-    if (DIST && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (DIST && VB() == 0 && threadIdx.x == 0) {
         *c.comm.seq = cs.seq;
         c.sc[ABIPGPU_SC_COMM_ERR] = cs.failed ? 1.0 : 0.0;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (VB() == 0 && threadIdx.x == 0) {
         c.sc[ABIPGPU_SC_CG_ITS] = (double)so.its;
         c.sc[ABIPGPU_SC_CG_TOL] = so.tol;
         c.sc[ABIPGPU_SC_CG_RES] = so.res;
@@ -354,10 +352,14 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
 }
 
 // min / sum of u_i v_i over the (x, tau) tail: update_barrier_dynamic, src/abip.c:957-960
-__global__ void __launch_bounds__(kBlock) k_mu_stats(const double* u, const double* v, int m, int l, double* partials,
-                                                     double* sc, Comm comm) {
+struct MuArgs {
+    const double *u, *v;
+};
+__device__ __forceinline__ void body_mu_stats(const double* u, const double* v, int m, int l, double* partials, double* sc,
+                                              const Comm& comm, bool batched) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double s_sum[kWarps], s_min[kWarps];
+    vgrid_init(batched);
     double sum = 0.0, mn = 1e10;
     GRID_STRIDE(i, l) {
         if (i >= m) {
@@ -376,25 +378,25 @@ __global__ void __launch_bounds__(kBlock) k_mu_stats(const double* u, const doub
     if (threadIdx.x == 0) {
         double s = 0.0, q = 1e10;
         for (int i = 0; i < kWarps; ++i) { s += s_sum[i]; q = fmin(q, s_min[i]); }
-        partials[blockIdx.x] = s;
-        partials[gridDim.x + blockIdx.x] = q;
+        partials[VB()] = s;
+        partials[VG() + VB()] = q;
     }
-    grid.sync();
+    grid_sync(grid);
     double s = 0.0, q = 1e10;
-    if (comm.G > 1 || (blockIdx.x == 0 && threadIdx.x == 0))
-        for (int i = 0; i < (int)gridDim.x; ++i) { s += __ldcg(partials + i); q = fmin(q, __ldcg(partials + gridDim.x + i)); }
+    if (comm.G > 1 || (VB() == 0 && threadIdx.x == 0))
+        for (int i = 0; i < VG(); ++i) { s += __ldcg(partials + i); q = fmin(q, __ldcg(partials + VG() + i)); }
     if (comm.G > 1) {
         // the tau entry (index l-1) is replicated: take it out of the local sums, exchange, add it back once
         const double xt = u[l - 1] * v[l - 1];
         CommState cs{*comm.seq, false};
         double* mine = comm.scal[comm.rank] + ((cs.seq + 1) & 1ull) * kCommScalars;
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (VB() == 0 && threadIdx.x == 0) {
             // local min over the x shard only (recompute without tau is not possible from the partials: min is
             // idempotent, so including tau on every rank is harmless); the sum must drop it
             mine[0] = s - xt;
             mine[1] = q;
         }
-        grid.sync();
+        grid_sync(grid);
         comm_exchange(comm, cs, grid);
         const long off = (long)(cs.seq & 1ull) * kCommScalars;
         s = xt;
@@ -403,15 +405,62 @@ __global__ void __launch_bounds__(kBlock) k_mu_stats(const double* u, const doub
             s += __ldcv(comm.scal[r] + off);
             q = fmin(q, __ldcv(comm.scal[r] + off + 1));
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (VB() == 0 && threadIdx.x == 0) {
             *comm.seq = cs.seq;
             sc[ABIPGPU_SC_COMM_ERR] = cs.failed ? 1.0 : 0.0;
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (VB() == 0 && threadIdx.x == 0) {
         sc[ABIPGPU_SC_SUM_XS] = s;
         sc[ABIPGPU_SC_MIN_XS] = q;
     }
+}
+
+// ---- launch wrappers -------------------------------------------------------------------------------------------
+template <bool DIST>
+__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_admm_iter(LpCtx c, IterArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    body_admm_iter<DIST>(c, a, smem_raw, false);
+}
+template <bool DIST>
+__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_bb_round(LpCtx c, BBArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    body_bb_round<DIST>(c, a, smem_raw, false);
+}
+__global__ void __launch_bounds__(kBlock) k_mu_stats(const double* u, const double* v, int m, int l, double* partials,
+                                                     double* sc, Comm comm) {
+    body_mu_stats(u, v, m, l, partials, sc, comm, false);
+}
+
+// Batched step (BASELINE.json configs[4]: thousands of small independent LPs): ONE launch advances every problem of the
+// batch by one step of its own kind -- CTA b runs item b (an ADMM iteration, a BB round or the mu statistics of one
+// engine) as block 0 of a one-block virtual grid, then copies the engine's scalar block to the host-mapped output.
+// Replaces one launch + one copy + one synchronisation per problem and step by one launch + one synchronisation per
+// batch and step (the per-context driver lock serialised the per-problem calls at ~13 us each).
+enum { BATCH_ADMM = 0, BATCH_BB = 1, BATCH_MU = 2 };
+struct BatchItem {
+    LpCtx c;
+    int kind;
+    int pad_;
+    IterArgs it;
+    BBArgs bb;
+    MuArgs mu;
+};
+__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_batch(const BatchItem* items, double* sc_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(16) BatchItem s_item;
+    {
+        const int* src = reinterpret_cast<const int*>(items + blockIdx.x);
+        int* dst = reinterpret_cast<int*>(&s_item);
+        for (int i = threadIdx.x; i < (int)(sizeof(BatchItem) / sizeof(int)); i += kBlock) dst[i] = src[i];
+    }
+    __syncthreads();
+    const BatchItem& it = s_item;
+    if (it.kind == BATCH_ADMM) body_admm_iter<false>(it.c, it.it, smem_raw, true);
+    else if (it.kind == BATCH_BB) body_bb_round<false>(it.c, it.bb, smem_raw, true);
+    else body_mu_stats(it.mu.u, it.mu.v, it.c.m, it.c.m + it.c.n + 1, it.c.partials, it.c.sc, it.c.comm, true);
+    __syncthreads();
+    if (threadIdx.x < ABIPGPU_SC_COUNT) sc_out[(size_t)blockIdx.x * ABIPGPU_SC_COUNT + threadIdx.x] = it.c.sc[threadIdx.x];
 }
 
 // reinitialize_vars, src/abip.c:996-1075
@@ -603,6 +652,9 @@ struct ABIPGPU_LP {
     double B_A = 0, B_AT = 0;  // algorithmic bytes of one SpMV pass
     char desc[768];
     bool restart_synced = false;
+    struct BatchExec* batch = nullptr;  // lock-step batch executor this engine belongs to
+    bool own_stream = true;             // batch engines borrow the stream of their worker thread
+    bool dirty = false;                 // batch engines: asynchronous work was queued on the stream since the last step
     // multi-GPU (column-block partition)
     int dist_G = 1, dist_rank = 0;
     long n_global = 0;
@@ -627,7 +679,10 @@ static int coop_grid(const void* kernel, int num_sms, size_t smem, int* out) {
 template <class... Args>
 static int launch_coop(abipgpu_lp* e, const void* kernel, int grid, size_t smem, Args... args) {
     void* argv[] = {(void*)&args...};
-    CK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kBlock), argv, smem, e->stream));
+    // a one-CTA engine never reaches a grid barrier (grid_sync): an ordinary launch lets the engines of a batch run
+    // concurrently (cooperative launches of different streams were observed to serialise)
+    if (grid == 1) CK(cudaLaunchKernel(kernel, dim3(1), dim3(kBlock), argv, smem, e->stream));
+    else CK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kBlock), argv, smem, e->stream));
     e->stats.n_kernel_launches++;
     return 0;
 }
@@ -647,11 +702,207 @@ static int read_sc(abipgpu_lp* e, abip_float* sc) {
 template <class T>
 static int upload(T** dst, const std::vector<T>& src, abipgpu_lp* e) {
     const size_t bytes = (src.size() + kPad) * sizeof(T);  // fixed-size staging windows over-read behind the arrays
-    CK(cudaMalloc((void**)dst, bytes));
+    CK(dev_alloc((void**)dst, bytes, e->stream));
     CK(cudaMemsetAsync(*dst, 0, bytes, e->stream));
     if (!src.empty()) CK(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, e->stream));
     e->stats.h2d_bytes += src.size() * sizeof(T);
     return 0;
+}
+
+// pinned host copies of the scalar block, recycled between engines (cudaMallocHost / cudaFreeHost synchronise)
+#include <mutex>
+static std::mutex g_pinned_mu;
+static std::vector<double*> g_pinned_free;
+static double* pinned_acquire() {
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        if (!g_pinned_free.empty()) {
+            double* p = g_pinned_free.back();
+            g_pinned_free.pop_back();
+            return p;
+        }
+    }
+    double* p = nullptr;
+    if (cudaMallocHost((void**)&p, sizeof(double) * ABIPGPU_SC_COUNT) != cudaSuccess) return nullptr;
+    return p;
+}
+static void pinned_release(double* p) {
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    g_pinned_free.push_back(p);
+}
+
+// =========================================================================================================
+// Lock-step batch executor (BASELINE.json configs[4]).  Every problem in flight has its own host thread running the
+// unchanged host solver (lp_host.cpp); a blocking step (ADMM iteration, BB round, mu statistics) is not launched by
+// the thread itself but handed to the executor, which launches ONE k_batch for all requests that are waiting and wakes
+// the threads when it has finished.  All engines of a batch share the executor's stream, so their occasional
+// asynchronous operations (memsets, copies, small kernels) stay ordered with the batched steps.
+// =========================================================================================================
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <thread>
+#include <semaphore.h>
+struct BatchReq {
+    abipgpu_lp* e;
+    BatchItem item;
+    bool done = false;
+    int rc = 0;
+    sem_t sem;                   // per-request wake-up: no contention on the executor's mutex when a batch completes
+    BatchReq() { sem_init(&sem, 0, 0); }
+    ~BatchReq() { sem_destroy(&sem); }
+};
+struct BatchExec {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    BatchItem* items = nullptr;  // host-mapped pinned memory, read by the kernel
+    double* sc_out = nullptr;    // host-mapped pinned memory, written by the kernel
+    int cap = 0;
+    int wait_us = 5000;
+    std::mutex mu;
+    std::condition_variable cv_req, cv_done;
+    std::vector<BatchReq*> pending;
+    int n_solving = 0;
+    bool stop = false;
+    std::thread launcher;
+    long n_launches = 0, n_items = 0;
+    double t_wait_ms = 0, t_kernel_ms = 0;
+
+    // launch as soon as this many requests wait: a fraction of the threads inside a solve (100 %: strict lock-step,
+    // measured best -- 343 LP/s at cfg5 with 296 problems in flight; 50 %: two alternating groups, 315 LP/s)
+    int frac_pct = 100;
+    int threshold() const { return std::max(1, n_solving * frac_pct / 100); }
+    int start(int dev, int capacity) {
+        device = dev;
+        cap = capacity;
+        wait_us = std::max(20, env_int("ABIP_GPU_BATCH_WAIT_US", 5000));
+        frac_pct = std::min(100, std::max(1, env_int("ABIP_GPU_BATCH_FRAC", 100)));
+        CK(cudaSetDevice(dev));
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaHostAlloc((void**)&items, sizeof(BatchItem) * cap, cudaHostAllocMapped));
+        CK(cudaHostAlloc((void**)&sc_out, sizeof(double) * ABIPGPU_SC_COUNT * cap, cudaHostAllocMapped));
+        CK(cudaFuncSetAttribute((const void*)k_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        launcher = std::thread([this] { run(); });
+        return 0;
+    }
+    void run() {
+        cudaSetDevice(device);
+        std::vector<BatchReq*> batch;
+        std::unique_lock<std::mutex> lk(mu);
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double t_mark = now();
+        for (;;) {
+            // launch when every thread that is inside a solve is waiting; a short timeout keeps the batch moving
+            // while some threads are busy with host work between two steps
+            cv_req.wait_for(lk, std::chrono::microseconds(wait_us),
+                            [&] { return stop || (!pending.empty() && (int)pending.size() >= threshold()); });
+            if (stop && pending.empty()) break;
+            if (pending.empty()) continue;
+            batch.clear();
+            const size_t take = std::min(pending.size(), (size_t)cap);
+            batch.assign(pending.begin(), pending.begin() + take);
+            pending.erase(pending.begin(), pending.begin() + take);
+            lk.unlock();
+            const double t_go = now();
+            t_wait_ms += t_go - t_mark;
+            const int n = (int)batch.size();
+            for (int i = 0; i < n; ++i) items[i] = batch[i]->item;
+            k_batch<<<n, kBlock, kSmemBytes, stream>>>(items, sc_out);
+            cudaError_t err = cudaGetLastError();
+            if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
+            if (err != cudaSuccess) fprintf(stderr, "[abip_gpu] batched step failed: %s\n", cudaGetErrorString(err));
+            for (int i = 0; i < n; ++i) {
+                memcpy(batch[i]->e->hsc, sc_out + (size_t)i * ABIPGPU_SC_COUNT, sizeof(double) * ABIPGPU_SC_COUNT);
+                batch[i]->rc = (err == cudaSuccess) ? 0 : -1;
+            }
+            n_launches++;
+            n_items += n;
+            t_mark = now();
+            t_kernel_ms += t_mark - t_go;
+            // (a 4-ary wake-up tree, woken threads waking their children, was measured slower: 185-270 vs 343 LP/s)
+            for (int i = 0; i < n; ++i) sem_post(&batch[i]->sem);  // the request may be gone right after this
+            lk.lock();
+        }
+    }
+    int submit(BatchReq* r) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            pending.push_back(r);
+            if ((int)pending.size() >= threshold()) cv_req.notify_one();
+        }
+        while (sem_wait(&r->sem) != 0) {
+        }
+        return r->rc;
+    }
+    void solving(int delta) {
+        std::lock_guard<std::mutex> lk(mu);
+        n_solving += delta;
+        if (!pending.empty() && (int)pending.size() >= threshold()) cv_req.notify_one();
+    }
+    void finish() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_req.notify_one();
+        if (launcher.joinable()) launcher.join();
+        cudaSetDevice(device);
+        if (stream) {
+            cudaStreamSynchronize(stream);
+            cudaStreamDestroy(stream);
+        }
+        if (items) cudaFreeHost(items);
+        if (sc_out) cudaFreeHost(sc_out);
+    }
+};
+static thread_local BatchExec* t_batch = nullptr;  // engines created by this thread join this executor
+// Per-worker stream for everything that is not a batched step (set-up, equilibration, copies, small kernels): these
+// must not queue behind the batched kernels of the other problems.  Ordering with the batched steps is by the host: a
+// step is only submitted after the worker's stream has drained (BatchExec::submit_step), and the worker only
+// continues after the executor has synchronised the batched launch.
+static thread_local cudaStream_t t_worker_stream = nullptr;
+
+extern "C" void* abipgpu_batch_begin(int device, int capacity) {
+    BatchExec* b = new BatchExec();
+    if (b->start(device, std::max(capacity, 1)) != 0) {
+        delete b;
+        return nullptr;
+    }
+    return b;
+}
+extern "C" void abipgpu_batch_attach(void* b) {
+    t_batch = (BatchExec*)b;
+    if (b && !t_worker_stream) {
+        cudaSetDevice(t_batch->device);
+        cudaStreamCreateWithFlags(&t_worker_stream, cudaStreamNonBlocking);
+    } else if (!b && t_worker_stream) {
+        cudaStreamSynchronize(t_worker_stream);
+        cudaStreamDestroy(t_worker_stream);
+        t_worker_stream = nullptr;
+    }
+}
+extern "C" void abipgpu_batch_end(void* b, long* launches, long* items) {
+    BatchExec* x = (BatchExec*)b;
+    if (!x) return;
+    x->finish();
+    if (getenv("ABIP_GPU_BATCH_VERBOSE"))
+        printf("[abip_gpu] batch executor: %.1f ms waiting for requests, %.1f ms in launches (fill + kernel + sync)\n",
+               x->t_wait_ms, x->t_kernel_ms);
+    if (launches) *launches = x->n_launches;
+    if (items) *items = x->n_items;
+    delete x;
+}
+static int batch_step(abipgpu_lp* e, BatchReq* r, abip_float* sc) {
+    if (e->dirty) {  // copies / memsets / small kernels queued by this thread must have finished
+        CK(cudaStreamSynchronize(e->stream));
+        e->dirty = false;
+    }
+    if (e->batch->submit(r)) return -1;
+    if (sc) memcpy(sc, e->hsc, sizeof(double) * ABIPGPU_SC_COUNT);
+    return 0;
+}
+void abipgpu_lp_batch_solving(abipgpu_lp* e, int delta) {
+    if (e && e->batch) e->batch->solving(delta);
 }
 
 static thread_local int t_grid_request = 0;  // CTAs per engine (batch mode); 0 = whole device
@@ -684,11 +935,18 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         return -1;
     }
     e->num_sms = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&e->ev0));
-    CK(cudaEventCreate(&e->ev1));
-    CK(cudaEventCreate(&e->ev_solve0));
-    CK(cudaEventCreate(&e->ev_solve1));
+    if (t_batch && t_worker_stream) {  // lock-step batch: one CTA per problem, the worker thread's stream, no events
+        e->batch = t_batch;
+        e->stream = t_worker_stream;
+        e->own_stream = false;
+        e->dirty = true;
+    } else {
+        CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&e->ev0));
+        CK(cudaEventCreate(&e->ev1));
+        CK(cudaEventCreate(&e->ev_solve0));
+        CK(cudaEventCreate(&e->ev_solve1));
+    }
 
     // CSR(A') is the caller's CSC; CSR(A) by counting sort (the reference's transpose(), indirect.c:81-139)
     std::vector<int> at_ptr(n + 1), at_idx(nnz), a_ptr(m + 1, 0), a_idx(nnz), perm;
@@ -720,7 +978,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         int g1, g2, g3, g4;
         int h1, h2, h3;
         // page cache of the gathered vectors: whole-device engines only (batch engines share the SMs)
-        e->pc_slots = t_grid_request > 0 ? 0 : std::max(0, std::min(env_int("ABIP_GPU_PC_SLOTS", kPcSlotsMax), kPcSlotsMax));
+        e->pc_slots = (t_grid_request > 0 || t_batch) ? 0 : std::max(0, std::min(env_int("ABIP_GPU_PC_SLOTS", kPcSlotsMax), kPcSlotsMax));
 #if !ABIP_PAGE_CACHE
         e->pc_slots = 0;
 #endif
@@ -734,10 +992,13 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
             coop_grid((const void*)k_mu_stats, e->num_sms, 0, &g4))
             return -1;
         g1 = std::min(g1, h1); g2 = std::min(g2, h2); g3 = std::min(g3, h3);
-        CK(cudaFuncSetAttribute((const void*)k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMaxOptin));
+        CK(cudaFuncSetAttribute((const void*)k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
         e->grid = std::min(g1, std::min(g2, g3));
         e->grid_mu = g4;
-        if (t_grid_request > 0) {  // batch mode: several small engines share the device
+        if (e->batch) {
+            e->grid = 1;
+            e->grid_mu = 1;
+        } else if (t_grid_request > 0) {  // batch mode: several small engines share the device
             e->grid = std::min(e->grid, t_grid_request);
             e->grid_mu = std::min(e->grid_mu, t_grid_request);
         }
@@ -758,7 +1019,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
 
     if (scale_out) a_val.assign(1, 0.0);  // placeholder; the values are gathered on the device below
     if (upload(&e->A_ptr, a_ptr, e) || upload(&e->A_idx, a_idx, e) ||
-        (scale_out ? (cudaMalloc((void**)&e->A_val, (nnz + kPad) * sizeof(double)) != cudaSuccess ||
+        (scale_out ? (dev_alloc((void**)&e->A_val, (nnz + kPad) * sizeof(double), e->stream) != cudaSuccess ||
                       cudaMemsetAsync(e->A_val, 0, (nnz + kPad) * sizeof(double), e->stream) != cudaSuccess)
                    : upload(&e->A_val, a_val, e)) ||
         upload(&e->AT_ptr, at_ptr, e) || upload(&e->AT_idx, at_idx, e) || upload(&e->AT_val, at_val, e) ||
@@ -776,7 +1037,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     const size_t Mm = ((size_t)m + 31) & ~(size_t)31, Nn = ((size_t)n + 31) & ~(size_t)31;
     const size_t n_l_vecs = 21 + 2;  // ids 0..20 + xin + yout
     const size_t total = n_l_vecs * L + 7 * Mm + 3 * Nn + (size_t)2 * kMaxRed * gmax + 64 + ABIPGPU_SC_COUNT + 32 + 2 * (size_t)gmax * kWarps;
-    CK(cudaMalloc((void**)&e->slab, total * sizeof(double)));
+    CK(dev_alloc((void**)&e->slab, total * sizeof(double), e->stream));
     CK(cudaMemsetAsync(e->slab, 0, total * sizeof(double), e->stream));
     e->slab_doubles = total;
     double* q = e->slab;
@@ -803,7 +1064,8 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     e->partials = take((size_t)2 * kMaxRed * gmax + 64);
     e->dsc = take(ABIPGPU_SC_COUNT);
     e->dphase = take(32 + 2 * (size_t)gmax * kWarps);
-    CK(cudaMallocHost((void**)&e->hsc, sizeof(double) * ABIPGPU_SC_COUNT));
+    e->hsc = pinned_acquire();
+    if (!e->hsc) return -1;
 
     LpCtx& c = e->ctx;
     c.m = (int)m;
@@ -881,8 +1143,8 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         CK(cudaMemcpyAsync(scale_out->E, e->dE, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(e->stream));
-        cudaFree(d_perm);
-        cudaFree(d_raw);
+        dev_free(d_perm, e->stream);
+        dev_free(d_raw, e->stream);
         e->stats.d2h_bytes += 8.0 * 2 * (m + n);
     }
     k_precond<<<(unsigned)((m + 255) / 256), 256, 0, e->stream>>>(c.A, e->dM);
@@ -947,21 +1209,23 @@ void abipgpu_lp_destroy(abipgpu_lp* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    cudaFree(e->A_ptr); cudaFree(e->A_idx); cudaFree(e->A_val);
-    cudaFree(e->AT_ptr); cudaFree(e->AT_idx); cudaFree(e->AT_val);
-    cudaFree(e->A_pcn); cudaFree(e->A_pcp); cudaFree(e->AT_pcn); cudaFree(e->AT_pcp);
-    cudaFree(e->A_cl); cudaFree(e->AT_cl); cudaFree(e->A_lr); cudaFree(e->AT_lr); cudaFree(e->A_lp); cudaFree(e->AT_lp);
-    cudaFree(e->A_wc); cudaFree(e->AT_wc); cudaFree(e->A_chunk); cudaFree(e->AT_chunk);
+    {
+        void* ptrs[] = {e->A_ptr, e->A_idx, e->A_val, e->AT_ptr, e->AT_idx, e->AT_val, e->A_pcn, e->A_pcp, e->AT_pcn,
+                        e->AT_pcp, e->A_cl, e->AT_cl, e->A_lr, e->AT_lr, e->A_lp, e->AT_lp, e->A_wc, e->AT_wc,
+                        e->A_chunk, e->AT_chunk, e->slab};
+        for (void* q : ptrs) {
+            if (e->stream) dev_free(q, e->stream);  // stream-ordered: no device-wide synchronisation
+        }
+    }
     for (int q = 0; q < kMaxRanks; ++q)
         if (e->peer_bufs[q] && q != e->dist_rank) cudaIpcCloseMemHandle(e->peer_bufs[q]);
-    cudaFree(e->comm_buf);
-    cudaFree(e->slab);
-    if (e->hsc) cudaFreeHost(e->hsc);
+    if (e->comm_buf) cudaFree(e->comm_buf);
+    if (e->hsc) pinned_release(e->hsc);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_solve0) cudaEventDestroy(e->ev_solve0);
     if (e->ev_solve1) cudaEventDestroy(e->ev_solve1);
-    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream && e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
 }
 
@@ -994,6 +1258,7 @@ int abipgpu_lp_set_problem(abipgpu_lp* e, const abip_float* b, const abip_float*
 abip_float abipgpu_lp_g_th(const abipgpu_lp* e) { return e->ctx.g_th; }
 
 int abipgpu_lp_cold_start(abipgpu_lp* e, abip_float mu, abip_float beta) {
+    e->dirty = true;
     CK(cudaSetDevice(e->device));
     k_cold_start<<<(e->l + 255) / 256, 256, 0, e->stream>>>(e->vec[ABIPGPU_VEC_U], e->vec[ABIPGPU_VEC_V], e->m, e->l,
                                                              sqrt(mu / beta));
@@ -1002,6 +1267,7 @@ int abipgpu_lp_cold_start(abipgpu_lp* e, abip_float mu, abip_float beta) {
 }
 
 int abipgpu_lp_outer_prologue(abipgpu_lp* e, int avg_criterion) {
+    e->dirty = true;
     CK(cudaSetDevice(e->device));
     const size_t bytes = sizeof(double) * e->l;
     CK(cudaMemsetAsync(e->vec[ABIPGPU_VEC_USUM], 0, bytes, e->stream));
@@ -1042,6 +1308,7 @@ int abipgpu_lp_admm_iter(abipgpu_lp* e, abip_int j, abip_int k, abip_float mu, a
     if (a.restart_active) {
         if (e->restart_synced && j > 0) {
             const size_t bytes = sizeof(double) * e->l;
+            e->dirty = true;
             CK(cudaMemcpyAsync(a.u_avg, a.u_sum, bytes, cudaMemcpyDeviceToDevice, e->stream));
             CK(cudaMemcpyAsync(a.v_avg, a.v_sum, bytes, cudaMemcpyDeviceToDevice, e->stream));
         }
@@ -1050,13 +1317,22 @@ int abipgpu_lp_admm_iter(abipgpu_lp* e, abip_int j, abip_int k, abip_float mu, a
     // fre_old is 0 until the first restart of this outer iteration and fre afterwards (abip.c:628, 2116):
     // both give the same residue class, so the firing rule reduces to (j+1) % fre == 0
     if (a.restart_active && e->stgs.restart_fre > 0 && (j + 1) % e->stgs.restart_fre == 0) a.restart_fire = 1;
-    CK(cudaEventRecord(e->ev0, e->stream));
-    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_admm_iter<true> : (const void*)k_admm_iter<false>, e->grid, e->smem, e->ctx, a)) return -1;
-    CK(cudaEventRecord(e->ev1, e->stream));
-    if (read_sc(e, sc)) return -1;
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
-    e->stats.admm_kernel_ms += ms;
+    if (e->batch) {  // lock-step batch: the executor launches this step together with those of the other problems
+        BatchReq r;
+        r.e = e;
+        r.item.c = e->ctx;
+        r.item.kind = BATCH_ADMM;
+        r.item.it = a;
+        if (batch_step(e, &r, sc)) return -1;
+    } else {
+        CK(cudaEventRecord(e->ev0, e->stream));
+        if (launch_coop(e, e->dist_G > 1 ? (const void*)k_admm_iter<true> : (const void*)k_admm_iter<false>, e->grid, e->smem, e->ctx, a)) return -1;
+        CK(cudaEventRecord(e->ev1, e->stream));
+        if (read_sc(e, sc)) return -1;
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        e->stats.admm_kernel_ms += ms;
+    }
     e->stats.n_admm_launch++;
     double bytes = account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], true);
     const double nq = e->hsc[ABIPGPU_SC_HAS_AVG] != 0 ? 2.0 : 1.0;
@@ -1073,11 +1349,21 @@ int abipgpu_lp_mu_stats(abipgpu_lp* e, int avg_criterion, abip_float* sc) {
     CK(cudaSetDevice(e->device));
     const double* u = e->vec[avg_criterion ? ABIPGPU_VEC_UAVGC : ABIPGPU_VEC_U];
     const double* v = e->vec[avg_criterion ? ABIPGPU_VEC_VAVGC : ABIPGPU_VEC_V];
+    if (e->batch) {
+        BatchReq r;
+        r.e = e;
+        r.item.c = e->ctx;
+        r.item.kind = BATCH_MU;
+        r.item.mu.u = u;
+        r.item.mu.v = v;
+        return batch_step(e, &r, sc);
+    }
     if (launch_coop(e, (const void*)k_mu_stats, e->grid_mu, (size_t)0, u, v, e->m, e->l, e->partials, e->dsc, e->ctx.comm)) return -1;
     return read_sc(e, sc);
 }
 
 int abipgpu_lp_reinit(abipgpu_lp* e, int indx, abip_float sigma, int avg_criterion) {
+    e->dirty = true;
     CK(cudaSetDevice(e->device));
     double* u = e->vec[avg_criterion ? ABIPGPU_VEC_UAVGC : ABIPGPU_VEC_U];
     double* v = e->vec[avg_criterion ? ABIPGPU_VEC_VAVGC : ABIPGPU_VEC_V];
@@ -1088,6 +1374,7 @@ int abipgpu_lp_reinit(abipgpu_lp* e, int indx, abip_float sigma, int avg_criteri
 }
 
 int abipgpu_lp_clamp_v(abipgpu_lp* e) {
+    e->dirty = true;
     CK(cudaSetDevice(e->device));
     k_clamp_v<<<(e->l + 255) / 256, 256, 0, e->stream>>>(e->vec[ABIPGPU_VEC_V], e->l);
     CK(cudaGetLastError());
@@ -1096,6 +1383,7 @@ int abipgpu_lp_clamp_v(abipgpu_lp* e) {
 }
 
 int abipgpu_lp_bb_begin(abipgpu_lp* e) {
+    e->dirty = true;
     CK(cudaSetDevice(e->device));
     const size_t bytes = sizeof(double) * e->l;
     CK(cudaMemcpyAsync(e->vec[ABIPGPU_VEC_BB_UPREV], e->vec[ABIPGPU_VEC_U], bytes, cudaMemcpyDeviceToDevice, e->stream));
@@ -1118,13 +1406,22 @@ int abipgpu_lp_bb_round(abipgpu_lp* e, int carry, abip_int k, abip_float mu, abi
     a.k = k;
     a.mu = mu;
     a.beta_prev = beta_prev;
-    CK(cudaEventRecord(e->ev0, e->stream));
-    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_bb_round<true> : (const void*)k_bb_round<false>, e->grid, e->smem, e->ctx, a)) return -1;
-    CK(cudaEventRecord(e->ev1, e->stream));
-    if (read_sc(e, sc)) return -1;
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
-    e->stats.bb_kernel_ms += ms;
+    if (e->batch) {
+        BatchReq r;
+        r.e = e;
+        r.item.c = e->ctx;
+        r.item.kind = BATCH_BB;
+        r.item.bb = a;
+        if (batch_step(e, &r, sc)) return -1;
+    } else {
+        CK(cudaEventRecord(e->ev0, e->stream));
+        if (launch_coop(e, e->dist_G > 1 ? (const void*)k_bb_round<true> : (const void*)k_bb_round<false>, e->grid, e->smem, e->ctx, a)) return -1;
+        CK(cudaEventRecord(e->ev1, e->stream));
+        if (read_sc(e, sc)) return -1;
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        e->stats.bb_kernel_ms += ms;
+    }
     e->stats.n_bb_launch++;
     double bytes = account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], true);
     bytes += account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS2], true);
@@ -1298,6 +1595,7 @@ extern "C" int abipgpu_lp_spmv_prof(abipgpu_lp* e, unsigned long long* out16, in
 }
 #endif
 int abipgpu_lp_solve_timer(abipgpu_lp* e, int stop) {  // CUDA events on the engine stream around a whole solve
+    if (e->batch) return 0;  // batched steps run on the executor's stream; the host clock times the batch
     CK(cudaSetDevice(e->device));
     if (!stop) {
         CK(cudaEventRecord(e->ev_solve0, e->stream));

@@ -16,3 +16,8 @@ extern "C" int abipgpu_lp_comm_export(abipgpu_lp* e, void* handle64);
 extern "C" int abipgpu_lp_comm_connect(abipgpu_lp* e, int G, int rank, const void* handles);
 extern "C" void abipgpu_lp_set_global_n(abipgpu_lp* e, long n_global);
 extern "C" void abipgpu_lp_request_grid(int ctas);
+// lock-step batch executor (lp_engine.cu: BatchExec)
+extern "C" void* abipgpu_batch_begin(int device, int capacity);
+extern "C" void abipgpu_batch_attach(void* b);
+extern "C" void abipgpu_batch_end(void* b, long* launches, long* items);
+void abipgpu_lp_batch_solving(abipgpu_lp* e, int delta);

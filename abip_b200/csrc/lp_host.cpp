@@ -12,6 +12,8 @@
 #include <cstring>
 #include <ctime>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -818,6 +820,11 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
         return ABIP_FAILED;
     }
     const abip_int m = w->m, n = w->n;
+    struct SolvingGuard {  // lock-step batches: the executor launches when every thread inside a solve is waiting
+        abipgpu_lp* e;
+        explicit SolvingGuard(abipgpu_lp* e_) : e(e_) { abipgpu_lp_batch_solving(e, +1); }
+        ~SolvingGuard() { abipgpu_lp_batch_solving(e, -1); }
+    } solving_guard(w->eng);
     w->stgs = w->stgs0;
     ABIPSettings& s = w->stgs;
     const double t0 = now_ms();
@@ -984,28 +991,82 @@ abip_int abip_gpu_main(const ABIPData* d, ABIPSolution* sol, ABIPInfo* info) {  
 void abip_gpu_get_stats(const ABIPGpuWork* w, ABIPGpuStats* out) { *out = w->last_stats; }
 
 // Batch of independent LPs on ONE GPU (BASELINE.json configs[4]; the reference equivalent is a loop of ABIP(main)
-// calls, one process per core).  `concurrency` host threads pull problems from a shared counter; every problem gets
-// its own engine with a persistent grid of `ctas_per_problem` CTAs on its own stream, so several cooperative kernels
-// share the 148 SMs (concurrency * ctas_per_problem <= SM count keeps all of them co-resident).
+// calls, one process per core).  `concurrency` host threads pull problems from a shared counter.
+//   ctas_per_problem >= 2: every problem gets its own engine with a persistent grid of that many CTAs on its own
+//     stream (several cooperative kernels share the SMs); one launch + one synchronisation per problem and step.
+//   ctas_per_problem <= 1 (lock-step mode): one CTA per problem; the blocking steps of all problems in flight are
+//     launched together by the batch executor of lp_engine.cu (one k_batch launch per step for the whole batch).
 abip_int abip_gpu_batch_main(const ABIPData* const* problems, ABIPSolution* sols, ABIPInfo* infos, abip_int count,
                              abip_int concurrency, abip_int ctas_per_problem) {
     if (!problems || !sols || !infos || count <= 0) return -1;
     if (concurrency < 1) concurrency = 1;
+    if (concurrency > count) concurrency = count;
     std::atomic<long> next{0};
     std::atomic<long> failed{0};
+    void* exec = nullptr;
+    if (ctas_per_problem <= 1) {
+        const char* dev = getenv("ABIP_GPU_DEVICE");
+        exec = abipgpu_batch_begin(dev ? atoi(dev) : 0, (int)concurrency);
+        if (!exec) return -1;
+    }
+    // lock-step mode: set-up and tear-down of a problem are ~150 driver calls under the per-context lock; letting all
+    // threads fight for it at once starves the executor's own launch + synchronise, so only a few threads at a time
+    // may be in set-up / tear-down
+    const char* gate_env = getenv("ABIP_GPU_BATCH_SETUP_GATE");
+    int gate_free = gate_env ? std::max(1, atoi(gate_env)) : 3;
+    std::mutex gate_mu;
+    std::condition_variable gate_cv;
+    auto gate_enter = [&] {
+        std::unique_lock<std::mutex> lk(gate_mu);
+        gate_cv.wait(lk, [&] { return gate_free > 0; });
+        --gate_free;
+    };
+    auto gate_leave = [&] {
+        {
+            std::lock_guard<std::mutex> lk(gate_mu);
+            ++gate_free;
+        }
+        gate_cv.notify_one();
+    };
     auto worker = [&]() {
-        abipgpu_lp_request_grid((int)ctas_per_problem);
+        if (exec) abipgpu_batch_attach(exec);
+        else abipgpu_lp_request_grid((int)ctas_per_problem);
         for (;;) {
             const long i = next.fetch_add(1);
             if (i >= count) break;
-            const abip_int st = abip_gpu_main(problems[i], &sols[i], &infos[i]);
+            abip_int st;
+            if (exec) {
+                gate_enter();
+                ABIPGpuWork* w = abip_gpu_init(problems[i], &infos[i]);
+                gate_leave();
+                if (w) {
+                    abip_gpu_solve(w, problems[i], &sols[i], &infos[i]);
+                    st = infos[i].status_val;
+                } else {
+                    st = failure(problems[i] ? problems[i]->m : -1, problems[i] ? problems[i]->n : -1, &sols[i], &infos[i],
+                                 ABIP_FAILED, "could not initialize work", "Failure");
+                }
+                gate_enter();
+                abip_gpu_finish(w);
+                gate_leave();
+            } else {
+                st = abip_gpu_main(problems[i], &sols[i], &infos[i]);
+            }
             if (st == ABIP_FAILED) failed.fetch_add(1);
         }
         abipgpu_lp_request_grid(0);
+        abipgpu_batch_attach(nullptr);
     };
     std::vector<std::thread> pool;
     for (abip_int t = 0; t < concurrency; ++t) pool.emplace_back(worker);
     for (auto& th : pool) th.join();
+    if (exec) {
+        long launches = 0, items = 0;
+        abipgpu_batch_end(exec, &launches, &items);
+        if (getenv("ABIP_GPU_BATCH_VERBOSE"))
+            printf("[abip_gpu] lock-step batch: %ld problems, %ld batched launches, %.1f steps per launch\n", (long)count,
+                   launches, launches ? (double)items / launches : 0.0);
+    }
     return (abip_int)failed.load();
 }
 

@@ -54,7 +54,7 @@ __device__ __forceinline__ int dev_hinv_general(const QcpCtx& c, Reducer& R, cg:
         s1[0] = fma(vj, vj, s1[0]);
     }
     R.block_store<1>(s1);
-    grid.sync();
+    grid_sync(grid);
     R.finish<1>(s1);
     const double tol = 1e-13 * sqrt(s1[0]);
     double s2[2] = {0.0, 0.0};
@@ -67,7 +67,7 @@ __device__ __forceinline__ int dev_hinv_general(const QcpCtx& c, Reducer& R, cg:
         s2[1] = fma(rj, zj, s2[1]);
     });
     R.block_store<2>(s2);
-    grid.sync();
+    grid_sync(grid);
     R.finish<2>(s2);
     double rr = s2[0], rz = s2[1];
     int its = 0;
@@ -80,7 +80,7 @@ __device__ __forceinline__ int dev_hinv_general(const QcpCtx& c, Reducer& R, cg:
             d1[0] = fma(pj, hp, d1[0]);
         });
         R.block_store<1>(d1);
-        grid.sync();
+        grid_sync(grid);
         R.finish<1>(d1);
         const double al = rz / d1[0];
         double d2[2] = {0.0, 0.0};
@@ -93,14 +93,14 @@ __device__ __forceinline__ int dev_hinv_general(const QcpCtx& c, Reducer& R, cg:
             d2[1] = fma(rj, zj, d2[1]);
         }
         R.block_store<2>(d2);
-        grid.sync();
+        grid_sync(grid);
         R.finish<2>(d2);
         const double be = d2[1] / rz;
         rr = d2[0];
         rz = d2[1];
         ++its;
         GRID_STRIDE(j, n) c.ip[j] = fma(be, c.ip[j], c.ir[j] / __ldg(c.Hd + j));
-        grid.sync();
+        grid_sync(grid);
     }
     return its;
 }
@@ -124,7 +124,7 @@ __device__ __forceinline__ void dev_qcp_solve(const QcpCtx& c, Reducer& R, cg::g
     // 1. hb = H^-1 b_x
     if (diag) {
         GRID_STRIDE(j, n) c.hb[j] = bx[j] / __ldg(c.Hd + j);
-        grid.sync();
+        grid_sync(grid);
     } else {
         inner += dev_hinv_general(c, R, grid, bx, c.hb);
     }
@@ -138,7 +138,7 @@ __device__ __forceinline__ void dev_qcp_solve(const QcpCtx& c, Reducer& R, cg::g
     if (warm)
         spmv_rows(c.AT, warm, R.ws, nullptr, [&](int row, double a) { c.tn2[row] = diag ? a / __ldg(c.Hd + row) : a; });
     R.block_store<1>(a1);
-    grid.sync();
+    grid_sync(grid);
     R.finish<1>(a1);
     const double tol = rtol * sqrt(a1[0]);
     double* t1 = c.tn2;
@@ -170,7 +170,7 @@ __device__ __forceinline__ void dev_qcp_solve(const QcpCtx& c, Reducer& R, cg::g
         }
     }
     R.block_store<2>(a2);
-    grid.sync();
+    grid_sync(grid);
     R.finish<2>(a2);
     double rn = sqrt(a2[0]);
     double ipzr = a2[1];
@@ -180,7 +180,7 @@ __device__ __forceinline__ void dev_qcp_solve(const QcpCtx& c, Reducer& R, cg::g
         for (int it = 0; it < max_its; ++it) {
             spmv_rows(c.AT, c.cg_p, R.ws, &c.A,
                       [&](int row, double a) { c.tn2[row] = diag ? a / __ldg(c.Hd + row) : a; });
-            grid.sync();
+            grid_sync(grid);
             t1 = c.tn2;
             if (!diag) {
                 inner += dev_hinv_general(c, R, grid, c.tn2, c.tn1);
@@ -194,7 +194,7 @@ __device__ __forceinline__ void dev_qcp_solve(const QcpCtx& c, Reducer& R, cg::g
                 d1[0] = fma(pi, gp, d1[0]);
             });
             R.block_store<1>(d1);
-            grid.sync();
+            grid_sync(grid);
             R.finish<1>(d1);
             const double al = ipzr / d1[0];
             double d2[2] = {0.0, 0.0};
@@ -207,7 +207,7 @@ __device__ __forceinline__ void dev_qcp_solve(const QcpCtx& c, Reducer& R, cg::g
                 d2[1] = fma(zi, ri, d2[1]);
             }
             R.block_store<2>(d2);
-            grid.sync();
+            grid_sync(grid);
             R.finish<2>(d2);
             its = it + 1;
             rn = sqrt(d2[0]);
@@ -215,19 +215,19 @@ __device__ __forceinline__ void dev_qcp_solve(const QcpCtx& c, Reducer& R, cg::g
             const double be = d2[1] / ipzr;
             ipzr = d2[1];
             GRID_STRIDE(i, m) c.cg_p[i] = fma(be, c.cg_p[i], __ldg(c.Ms + i) * c.cg_r[i]);
-            grid.sync();
+            grid_sync(grid);
         }
     }
     // 5. x = hb + H^-1 A'y
     if (diag) {
         spmv_rows(c.AT, by, R.ws, &c.A, [&](int row, double a) { bx[row] = c.hb[row] + a / __ldg(c.Hd + row); });
-        grid.sync();
+        grid_sync(grid);
     } else {
         spmv_rows(c.AT, by, R.ws, nullptr, [&](int row, double a) { c.tn2[row] = a; });
-        grid.sync();
+        grid_sync(grid);
         inner += dev_hinv_general(c, R, grid, c.tn2, c.tn1);
         GRID_STRIDE(j, n) bx[j] = c.hb[j] + c.tn1[j];
-        grid.sync();
+        grid_sync(grid);
     }
     out.its = its;
     out.inner = inner;
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_qcp_iter(Qcp
         s1[0] = fma(__ldg(c.r + i), mui, s1[0]);
     }
     R.block_store<1>(s1);
-    grid.sync();
+    grid_sync(grid);
     R.finish<1>(s1);
     const double r_mu = s1[0];
     QcpSolveOut so;
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_qcp_iter(Qcp
     if (c.has_q)
         spmv_rows(c.Q, p + m, R.ws, nullptr, [&](int row, double q) { s2[1] = fma(p[m + row], q, s2[1]); });
     R.block_store<2>(s2);
-    grid.sync();
+    grid_sync(grid);
     R.finish<2>(s2);
     const double bq = r_mu - 2 * s2[0] - eta, cq = -s2[1];
     const double tau_t = a.k > 0 ? (-bq + sqrt(fmax(0.0, bq * bq - 4 * c.a_coef * cq))) / (2 * c.a_coef) : 1.0;
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_qcp_iter(Qcp
             }
         }
     }
-    grid.sync();
+    grid_sync(grid);
 
     // ---- inner_conv_check + calc_residuals sums on the new (u, v)
     const double tau = u[mn];
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_qcp_iter(Qcp
     if (c.has_q) spmv_rows(c.Q, u + m, R.ws, &c.AT, [&](int row, double q) { c.tn1[row] = q; });
     // (tn1 rows are produced and consumed by the same warp partition only if the plans coincide -- they do not,
     //  so a barrier is required between the Q pass and the A' pass)
-    if (c.has_q) grid.sync();
+    if (c.has_q) grid_sync(grid);
     double sX[7] = {0, 0, 0, 0, 0, 0, 0};  // S_DIFF_x, S_QU_x, S_VO_x, UMU_x, XC, XQX, QXE2 | ATYS_E2 below
     double sX2[1] = {0};
     double mX[3] = {0, 0, 0};  // RESD_INF, RESD_E_INF, QX_E_INF
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_qcp_iter(Qcp
     R.block_store<1>(sX2, 12);
     R.block_store_max<3>(mA, 13);
     R.block_store_max<3>(mX, 16);
-    grid.sync();
+    grid_sync(grid);
     double t[19];
     R.finish<19, 0x7E000u>(t);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -495,14 +495,14 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_qcp_precalc(
     Reducer R = make_reducer(smem_raw, c.partials);
     const int m = c.m, mn = c.m + c.n;
     GRID_STRIDE(i, mn) rvec[i] = i < m ? -__ldg(c.b + i) : __ldg(c.c + i - m);
-    grid.sync();
+    grid_sync(grid);
     QcpSolveOut so;
     dev_qcp_solve(c, R, grid, rvec, nullptr, 1e-12, so);
     R.ws.drain();
     double s[1] = {0.0};
     GRID_STRIDE(i, mn) s[0] = fma((i < m ? c.rho_y : c.rho_x) * rvec[i], rvec[i], s[0]);
     R.block_store<1>(s);
-    grid.sync();
+    grid_sync(grid);
     R.finish<1>(s);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         c.sc[ABIPGPU_QSC_A_COEF] = c.rho_tau + s[0];

@@ -18,6 +18,26 @@
         }                                                                                                \
     } while (0)
 
+// Stream-ordered device allocations (cudaMallocAsync / cudaFreeAsync): cudaMalloc and cudaFree synchronise the whole
+// device, which serialised the concurrent engines of a batch of small LPs.  The pool keeps freed memory.
+static inline cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t s) {
+    static thread_local int pool_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (pool_dev != dev) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_dev = dev;
+    }
+    return cudaMallocAsync(p, bytes, s);
+}
+static inline void dev_free(void* p, cudaStream_t s) {
+    if (p) cudaFreeAsync(p, s);
+}
+
 static inline int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
@@ -210,9 +230,9 @@ struct DevCsr {
     Csr view() const {
         return Csr{ptr, idx, val, nrows, wc, chunk, plan.lanes_log2, 0, 0, nullptr, nullptr, cta_long, long_rows, long_part, 0};
     }
-    void release() {
-        cudaFree(ptr); cudaFree(idx); cudaFree(wc); cudaFree(chunk); cudaFree(val);
-        cudaFree(cta_long); cudaFree(long_rows); cudaFree(long_part);
+    void release(cudaStream_t s = nullptr) {
+        dev_free(ptr, s); dev_free(idx, s); dev_free(wc, s); dev_free(chunk, s); dev_free(val, s);
+        dev_free(cta_long, s); dev_free(long_rows, s); dev_free(long_part, s);
         ptr = idx = wc = cta_long = nullptr; chunk = long_rows = nullptr; val = long_part = nullptr;
     }
 };
@@ -220,7 +240,7 @@ struct DevCsr {
 template <class T>
 static inline int upload_padded(T** dst, const std::vector<T>& src, cudaStream_t stream) {
     const size_t bytes = (src.size() + kPad) * sizeof(T);  // fixed-size staging windows over-read behind the arrays
-    CK(cudaMalloc((void**)dst, bytes));
+    CK(dev_alloc((void**)dst, bytes, stream));
     CK(cudaMemsetAsync(*dst, 0, bytes, stream));
     if (!src.empty()) CK(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
     return 0;
@@ -233,7 +253,7 @@ static inline int upload_long_rows(const SpmvPlan& P, int** cta_long, int4** lon
     *long_part = nullptr;
     if (P.n_long == 0) return 0;
     if (upload_padded(cta_long, P.cta_long, stream) || upload_padded(long_rows, P.long_rows, stream)) return -1;
-    CK(cudaMalloc((void**)long_part, sizeof(double) * (P.n_pieces + 8)));
+    CK(dev_alloc((void**)long_part, sizeof(double) * (P.n_pieces + 8), stream));
     CK(cudaMemsetAsync(*long_part, 0, sizeof(double) * (P.n_pieces + 8), stream));
     return 0;
 }

@@ -335,3 +335,22 @@ def test_device_equilibration_is_bit_identical_to_host(kw):
     assert L.abipgpu_lp_spmv(e, 0, api._fp(x), api._fp(out2)) == 0
     assert rel(out2, As @ x) < 1e-13
     L.abipgpu_lp_destroy(e)
+
+
+@pytest.mark.parametrize("mode", ["lockstep", "grids"])
+def test_batch_of_small_lps_matches_oracle(mode):
+    """abip_gpu_batch_main (BASELINE.json configs[4] family): lock-step mode (one CTA per problem, all problems of the
+    batch advanced by one k_batch launch per step) and the older one-grid-per-problem mode, each problem against the
+    oracle (status, ADMM iterations within 5 %, objective 1e-6) and against residuals recomputed on the CPU."""
+    from abip_b200 import lp_solve_batch
+    probs = [problems.random_lp(60 + 7 * i, 200 + 31 * i, 4, seed=900 + i) for i in range(10)]
+    probs.append(problems.mcf_lp(3, 20, 80, 4, 100, seed=11))      # long rows inside a one-CTA engine
+    conc, ctas = (len(probs), 1) if mode == "lockstep" else (4, 8)
+    res = lp_solve_batch(probs, dict(tol=1e-4, verbose=0), concurrency=conc, ctas_per_problem=ctas)
+    assert len(res) == len(probs)
+    for p, (x, y, s, info) in zip(probs, res):
+        o = O.solve(p.csc(), p.b, p.c, O.Settings(eps=1e-4))
+        assert info["status"] == o.status == "Solved", (p.name, info["status"], o.status)
+        assert abs(info["admm_iter"] - o.admm_iter) <= max(2, 0.05 * o.admm_iter)
+        assert abs(info["pobj"] - o.pobj) <= 1e-6 * (1 + abs(o.pobj))
+        _check_solution(p, x, y, s, info, 1e-4)

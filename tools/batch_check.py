@@ -6,7 +6,8 @@ from abip_b200 import problems, lp_solve_batch, lp_solve
 count = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 probs = [problems.random_lp(500, 2000, 5, seed=5000 + i) for i in range(count)]
 t = time.time(); x, y, s, info = lp_solve(probs[0].csc(), probs[0].b, probs[0].c, dict(tol=1e-4, verbose=0)); print('single full-grid solve: %.3fs' % (time.time() - t), info['status'], info['admm_iter'], info['pobj'], flush=True)
-for conc, ctas in [(1, 148), (1, 8), (8, 16), (16, 8), (18, 8), (32, 4), (36, 4), (64, 2)]:
+cfgs = [tuple(int(v) for v in a.split('x')) for a in sys.argv[2:]] or [(1, 148), (1, 8), (8, 16), (16, 8), (18, 8), (32, 4), (36, 4), (64, 2)]
+for conc, ctas in cfgs:
     t = time.time()
     res = lp_solve_batch(probs, dict(tol=1e-4, verbose=0), concurrency=conc, ctas_per_problem=ctas)
     dt = time.time() - t
