@@ -176,10 +176,12 @@ class LpSolver:
             pass
 
 
-def lp_solve_batch(problems, params: dict | None = None, concurrency: int = 16, ctas_per_problem: int = 8,
+def lp_solve_batch(problems, params: dict | None = None, concurrency: int = 296, ctas_per_problem: int = 1,
                    **raw_settings):
     """Batch of independent LPs on the current GPU (abip_gpu_batch_main).  problems: iterable of objects with
-    csc()/m/n/b/c (abip_b200.problems.LPProblem) or (A, b, c) tuples.  Returns a list of (x, y, s, info)."""
+    csc()/m/n/b/c (abip_b200.problems.LPProblem) or (A, b, c) tuples.  Returns a list of (x, y, s, info).
+    ctas_per_problem <= 1 (default): lock-step mode, `concurrency` problems in flight, one CTA each, one batched launch
+    per step; >= 2: one persistent grid of that many CTAs per problem, `concurrency` host threads."""
     L = _capi.lib()
     p, st0 = _lp_settings(params, **raw_settings)
     keep, datas = [], []

@@ -50,7 +50,7 @@ def peaks():
 
 def ncu_traffic():
     """DRAM bytes of one k_admm_iter launch from the committed ncu --set full capture (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r01_k_admm_iter_ncu.txt")
+    path = os.path.join(ROOT, "profiles", "r01_k_admm_iter_ncu_v2.txt")
     if not os.path.exists(path):
         return None
     rd = wr = None
@@ -62,8 +62,8 @@ def ncu_traffic():
     if rd is None or wr is None:
         return None
     return {"dram_bytes_per_launch": rd + wr,
-            "note": "ncu --set full capture of one k_admm_iter launch with 28 CG iterations (5.17 GB algorithmic), "
-                    "profiles/r01_k_admm_iter_ncu.txt"}
+            "note": "ncu --set full capture of one k_admm_iter launch with 26 CG iterations (~5.0 GB algorithmic), "
+                    "profiles/r01_k_admm_iter_ncu_v2.txt"}
 
 
 class ClockSampler:

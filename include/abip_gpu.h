@@ -181,8 +181,11 @@ abip_int abip_gpu_comm_connect(ABIPGpuWork *w, const void *handles /* world x 64
 void abip_gpu_partition(const ABIPGpuWork *w, abip_int *c0, abip_int *nl);
 void abip_gpu_column_partition(abip_int n, const abip_int *Ap, abip_int world, abip_int rank, abip_int *c0, abip_int *nl);
 
-/* Batch of independent LPs on one GPU (configs[4]): `concurrency` host threads, each problem on its own stream with a
- * persistent grid of `ctas_per_problem` CTAs.  Returns the number of failed problems (< 0: bad arguments).
+/* Batch of independent LPs on one GPU (configs[4]); `concurrency` = problems in flight (one host thread each).
+ *   ctas_per_problem <= 1: lock-step mode -- one CTA per problem, the steps of all problems in flight are launched
+ *     together (one k_batch launch per step for the whole batch; use ~2 x SM count problems in flight);
+ *   ctas_per_problem >= 2: each problem on its own stream with a persistent grid of that many CTAs.
+ * Returns the number of failed problems (< 0: bad arguments).
  * The reference equivalent is a loop of ABIP(main) calls (one process per core). */
 abip_int abip_gpu_batch_main(const ABIPData *const *problems, ABIPSolution *sols, ABIPInfo *infos, abip_int count,
                              abip_int concurrency, abip_int ctas_per_problem);
