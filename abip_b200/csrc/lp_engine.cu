@@ -438,14 +438,91 @@ __global__ void __launch_bounds__(kBlock) k_mu_stats(const double* u, const doub
 // Replaces one launch + one copy + one synchronisation per problem and step by one launch + one synchronisation per
 // batch and step (the per-context driver lock serialised the per-problem calls at ~13 us each).
 enum { BATCH_ADMM = 0, BATCH_BB = 1, BATCH_MU = 2 };
+// Deferred vector operations of a batch engine (cold start, outer-iteration prologue, re-initialisation, clamp, BB
+// hand-over, restart copy): the host functions only record them, the next batched step of the problem executes them
+// in order before its own work -- no launch, no copy, no synchronisation of their own (they were ~8 driver calls per
+// outer iteration and problem).
+enum { PRE_COLD = 1, PRE_PROLOGUE, PRE_REINIT, PRE_CLAMP, PRE_BB_BEGIN, PRE_RESTART_COPY };
+struct PreOp {
+    int code, i0, i1, pad_;
+    double d0, d1;
+};
+constexpr int kMaxPre = 8;
 struct BatchItem {
     LpCtx c;
     int kind;
-    int pad_;
+    int n_pre;
     IterArgs it;
     BBArgs bb;
     MuArgs mu;
+    PreOp pre[kMaxPre];
+    double* vec[21];
 };
+__device__ __forceinline__ void apply_pre_ops(const BatchItem& it) {
+    const int m = it.c.m, l = it.c.m + it.c.n + 1;
+    for (int q = 0; q < it.n_pre; ++q) {
+        const PreOp op = it.pre[q];
+        if (op.code == PRE_COLD) {  // cold_start_vars, src/abip.c:361-381
+            const double val = sqrt(op.d0 / op.d1);
+            double *u = it.vec[ABIPGPU_VEC_U], *v = it.vec[ABIPGPU_VEC_V];
+            for (int i = threadIdx.x; i < l; i += kBlock) {
+                u[i] = (i < m) ? 0.0 : val;
+                v[i] = (i < m) ? 0.0 : val;
+            }
+        } else if (op.code == PRE_PROLOGUE) {  // start of an outer iteration (abipgpu_lp_outer_prologue)
+            double *us = it.vec[ABIPGPU_VEC_USUM], *vs = it.vec[ABIPGPU_VEC_VSUM], *ua = it.vec[ABIPGPU_VEC_UAVG],
+                   *va = it.vec[ABIPGPU_VEC_VAVG];
+            for (int i = threadIdx.x; i < l; i += kBlock) {
+                us[i] = 0.0;
+                vs[i] = 0.0;
+                ua[i] = 0.0;
+                va[i] = 0.0;
+            }
+            if (op.i0) {
+                double *u = it.vec[ABIPGPU_VEC_U], *v = it.vec[ABIPGPU_VEC_V];
+                const double *uc = it.vec[ABIPGPU_VEC_UAVGC], *vc = it.vec[ABIPGPU_VEC_VAVGC];
+                for (int i = threadIdx.x; i < l; i += kBlock) {
+                    u[i] = uc[i];
+                    v[i] = vc[i];
+                }
+            }
+        } else if (op.code == PRE_REINIT) {  // reinitialize_vars, src/abip.c:996-1075
+            double* u = it.vec[op.i1 ? ABIPGPU_VEC_UAVGC : ABIPGPU_VEC_U];
+            double* v = it.vec[op.i1 ? ABIPGPU_VEC_VAVGC : ABIPGPU_VEC_V];
+            const int indx = op.i0;
+            const double sigma = op.d0;
+            for (int i = m + threadIdx.x; i < l; i += kBlock) {
+                if (indx == 0) {
+                    if (u[i] > v[i]) v[i] = sigma * v[i];
+                    else u[i] = sigma * u[i];
+                } else {
+                    const double f = (indx == 1) ? sqrt(sigma) : sqrt(1.0 / sigma);
+                    u[i] = f * u[i];
+                    v[i] = f * v[i];
+                }
+            }
+        } else if (op.code == PRE_CLAMP) {  // src/abip.c:2175-2186
+            double* v = it.vec[ABIPGPU_VEC_V];
+            for (int i = threadIdx.x; i < l; i += kBlock)
+                if (v[i] < 0) v[i] = 1e-6;
+        } else if (op.code == PRE_BB_BEGIN) {
+            double *up = it.vec[ABIPGPU_VEC_BB_UPREV], *vp = it.vec[ABIPGPU_VEC_BB_VPREV];
+            const double *u = it.vec[ABIPGPU_VEC_U], *v = it.vec[ABIPGPU_VEC_V];
+            for (int i = threadIdx.x; i < l; i += kBlock) {
+                up[i] = u[i];
+                vp[i] = v[i];
+            }
+        } else if (op.code == PRE_RESTART_COPY) {
+            double *ua = it.vec[ABIPGPU_VEC_UAVG], *va = it.vec[ABIPGPU_VEC_VAVG];
+            const double *us = it.vec[ABIPGPU_VEC_USUM], *vs = it.vec[ABIPGPU_VEC_VSUM];
+            for (int i = threadIdx.x; i < l; i += kBlock) {
+                ua[i] = us[i];
+                va[i] = vs[i];
+            }
+        }
+        __syncthreads();
+    }
+}
 __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_batch(const BatchItem* items, double* sc_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(16) BatchItem s_item;
@@ -456,6 +533,7 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_batch(const 
     }
     __syncthreads();
     const BatchItem& it = s_item;
+    apply_pre_ops(it);
     if (it.kind == BATCH_ADMM) body_admm_iter<false>(it.c, it.it, smem_raw, true);
     else if (it.kind == BATCH_BB) body_bb_round<false>(it.c, it.bb, smem_raw, true);
     else body_mu_stats(it.mu.u, it.mu.v, it.c.m, it.c.m + it.c.n + 1, it.c.partials, it.c.sc, it.c.comm, true);
@@ -628,7 +706,8 @@ struct ABIPGPU_LP {
     // matrix
     int *A_ptr = nullptr, *A_idx = nullptr, *AT_ptr = nullptr, *AT_idx = nullptr, *A_wc = nullptr, *AT_wc = nullptr;
     int *A_pcn = nullptr, *A_pcp = nullptr, *AT_pcn = nullptr, *AT_pcp = nullptr;  // page-cache plan (per CTA)
-    int *A_cl = nullptr, *AT_cl = nullptr;       // long-row tables (spmv_host.h: upload_long_rows)
+    unsigned char* arena = nullptr;              // all matrix / plan arrays live in this one allocation
+    int *A_cl = nullptr, *AT_cl = nullptr;       // long-row tables
     int4 *A_lr = nullptr, *AT_lr = nullptr;
     double *A_lp = nullptr, *AT_lp = nullptr;
     size_t smem = kSmemBytes;  // dynamic shared memory of the persistent kernels (+ page cache)
@@ -655,6 +734,8 @@ struct ABIPGPU_LP {
     struct BatchExec* batch = nullptr;  // lock-step batch executor this engine belongs to
     bool own_stream = true;             // batch engines borrow the stream of their worker thread
     bool dirty = false;                 // batch engines: asynchronous work was queued on the stream since the last step
+    int n_pend = 0;                     // batch engines: deferred vector operations (PreOp), executed by the next step
+    PreOp pend[kMaxPre];
     // multi-GPU (column-block partition)
     int dist_G = 1, dist_rank = 0;
     long n_global = 0;
@@ -892,7 +973,18 @@ extern "C" void abipgpu_batch_end(void* b, long* launches, long* items) {
     if (items) *items = x->n_items;
     delete x;
 }
+static int flush_pending(abipgpu_lp* e);
+// record a deferred operation (batch engines); falls back to executing everything directly when the list is full
+static int defer(abipgpu_lp* e, PreOp op) {
+    if (e->n_pend == kMaxPre && flush_pending(e)) return -1;
+    e->pend[e->n_pend++] = op;
+    return 0;
+}
 static int batch_step(abipgpu_lp* e, BatchReq* r, abip_float* sc) {
+    r->item.n_pre = e->n_pend;
+    for (int q = 0; q < e->n_pend; ++q) r->item.pre[q] = e->pend[q];
+    e->n_pend = 0;
+    for (int id = 0; id <= 20; ++id) r->item.vec[id] = e->vec[id];
     if (e->dirty) {  // copies / memsets / small kernels queued by this thread must have finished
         CK(cudaStreamSynchronize(e->stream));
         e->dirty = false;
@@ -912,6 +1004,17 @@ struct ScaleOut {  // host outputs of the device-side equilibration
     double *D, *E, *mean_row, *mean_col;
 };
 
+// Device properties and the occupancy-derived persistent grids are the same for every engine of a process: query them
+// once per device (cudaGetDeviceProperties alone costs more than a whole ADMM iteration of a small LP).
+struct DevInfo {
+    bool ok = false;
+    int coop = 0, num_sms = 0;
+    char name[256] = {0};
+    int g_main = 0, g_mu = 0;  // grids for smem = kSmemBytes (no page cache)
+};
+static std::mutex g_devinfo_mu;
+static DevInfo g_devinfo[64];
+
 static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap, const abip_int* Ai,
                        const abip_float* Ax, const ABIPSettings* stgs, int device, const ScaleOut* scale_out = nullptr) {
     const long nnz = Ap[n];
@@ -928,8 +1031,20 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     e->stgs = *stgs;
     memset(&e->stats, 0, sizeof(e->stats));
     CK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
+    if (device < 0 || device >= 64) return -1;
+    DevInfo& di = g_devinfo[device];
+    {
+        std::lock_guard<std::mutex> lk(g_devinfo_mu);
+        if (!di.ok) {
+            cudaDeviceProp p0;
+            CK(cudaGetDeviceProperties(&p0, device));
+            di.coop = p0.cooperativeLaunch;
+            di.num_sms = p0.multiProcessorCount;
+            snprintf(di.name, sizeof(di.name), "%s", p0.name);
+            di.ok = true;
+        }
+    }
+    struct { int cooperativeLaunch, multiProcessorCount; const char* name; } prop = {di.coop, di.num_sms, di.name};
     if (!prop.cooperativeLaunch) {
         fprintf(stderr, "[abip_gpu] device lacks cooperative launch\n");
         return -1;
@@ -983,7 +1098,17 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         e->pc_slots = 0;
 #endif
         e->smem = kSmemBytes + (size_t)e->pc_slots * kPageDoubles * sizeof(double);
-        if (coop_grid((const void*)k_admm_iter<false>, e->num_sms, e->smem, &g1) ||
+        bool cached = false;
+        if (e->pc_slots == 0) {
+            std::lock_guard<std::mutex> lk(g_devinfo_mu);
+            if (di.g_main > 0) {
+                g1 = g2 = g3 = h1 = h2 = h3 = di.g_main;
+                g4 = di.g_mu;
+                cached = true;
+            }
+        }
+        if (cached) {
+        } else if (coop_grid((const void*)k_admm_iter<false>, e->num_sms, e->smem, &g1) ||
             coop_grid((const void*)k_bb_round<false>, e->num_sms, e->smem, &g2) ||
             coop_grid((const void*)k_solve_vec<false>, e->num_sms, e->smem, &g3) ||
             coop_grid((const void*)k_admm_iter<true>, e->num_sms, e->smem, &h1) ||
@@ -995,6 +1120,11 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         CK(cudaFuncSetAttribute((const void*)k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
         e->grid = std::min(g1, std::min(g2, g3));
         e->grid_mu = g4;
+        if (!cached && e->pc_slots == 0) {
+            std::lock_guard<std::mutex> lk(g_devinfo_mu);
+            di.g_main = e->grid;
+            di.g_mu = e->grid_mu;
+        }
         if (e->batch) {
             e->grid = 1;
             e->grid_mu = 1;
@@ -1017,19 +1147,61 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         build_page_cache(planAT, at_idx, m, e->grid, e->pc_slots, min_refs, &pcAT);
     }
 
-    if (scale_out) a_val.assign(1, 0.0);  // placeholder; the values are gathered on the device below
-    if (upload(&e->A_ptr, a_ptr, e) || upload(&e->A_idx, a_idx, e) ||
-        (scale_out ? (dev_alloc((void**)&e->A_val, (nnz + kPad) * sizeof(double), e->stream) != cudaSuccess ||
-                      cudaMemsetAsync(e->A_val, 0, (nnz + kPad) * sizeof(double), e->stream) != cudaSuccess)
-                   : upload(&e->A_val, a_val, e)) ||
-        upload(&e->AT_ptr, at_ptr, e) || upload(&e->AT_idx, at_idx, e) || upload(&e->AT_val, at_val, e) ||
-        upload(&e->A_wc, planA.warp_chunk, e) || upload(&e->AT_wc, planAT.warp_chunk, e) ||
-        upload(&e->A_chunk, planA.chunk, e) || upload(&e->AT_chunk, planAT.chunk, e) ||
-        upload(&e->A_pcn, pcA.npages, e) || upload(&e->A_pcp, pcA.pages, e) ||
-        upload(&e->AT_pcn, pcAT.npages, e) || upload(&e->AT_pcp, pcAT.pages, e) ||
-        upload_long_rows(planA, &e->A_cl, &e->A_lr, &e->A_lp, e->stream) ||
-        upload_long_rows(planAT, &e->AT_cl, &e->AT_lr, &e->AT_lp, e->stream))
-        return -1;
+    // One device arena for all matrix and plan arrays: packed on the host (zero padding of kPad elements behind every
+    // array included) and uploaded with ONE allocation and ONE copy -- 14 arrays x (malloc + memset + copy) were a
+    // third of the driver calls of an engine set-up, which is what limits a batch of small LPs.
+    // (large problems skip the host staging copy: one memset of the arena, then one copy per array)
+    std::vector<unsigned char> stage;
+    struct Seg { size_t off; const void* src; size_t bytes; };
+    std::vector<Seg> segs;
+    size_t arena_bytes = 0;
+    auto put = [&](const void* src, size_t bytes, size_t elem) -> size_t {
+        const size_t off = (arena_bytes + 255) & ~(size_t)255;
+        arena_bytes = off + bytes + (size_t)kPad * elem;
+        if (src && bytes) segs.push_back(Seg{off, src, bytes});
+        return off;
+    };
+    auto put_vec = [&](const auto& v) { return put(v.data(), v.size() * sizeof(v[0]), sizeof(v[0])); };
+    const size_t o_aptr = put_vec(a_ptr), o_aidx = put_vec(a_idx);
+    const size_t o_aval = scale_out ? put(nullptr, nnz * sizeof(double), sizeof(double)) : put_vec(a_val);
+    const size_t o_atptr = put_vec(at_ptr), o_atidx = put_vec(at_idx), o_atval = put_vec(at_val);
+    const size_t o_awc = put_vec(planA.warp_chunk), o_atwc = put_vec(planAT.warp_chunk);
+    const size_t o_ach = put_vec(planA.chunk), o_atch = put_vec(planAT.chunk);
+    const size_t o_apcn = put_vec(pcA.npages), o_apcp = put_vec(pcA.pages);
+    const size_t o_atpcn = put_vec(pcAT.npages), o_atpcp = put_vec(pcAT.pages);
+    size_t o_acl = 0, o_alr = 0, o_alp = 0, o_atcl = 0, o_atlr = 0, o_atlp = 0;
+    if (planA.n_long) {
+        o_acl = put_vec(planA.cta_long);
+        o_alr = put_vec(planA.long_rows);
+        o_alp = put(nullptr, planA.n_pieces * sizeof(double), sizeof(double));
+    }
+    if (planAT.n_long) {
+        o_atcl = put_vec(planAT.cta_long);
+        o_atlr = put_vec(planAT.long_rows);
+        o_atlp = put(nullptr, planAT.n_pieces * sizeof(double), sizeof(double));
+    }
+    CK(dev_alloc((void**)&e->arena, arena_bytes, e->stream));
+    if (arena_bytes <= ((size_t)16 << 20)) {
+        stage.assign(arena_bytes, 0);
+        for (const Seg& sg : segs) memcpy(stage.data() + sg.off, sg.src, sg.bytes);
+        CK(cudaMemcpyAsync(e->arena, stage.data(), arena_bytes, cudaMemcpyHostToDevice, e->stream));
+        e->stats.h2d_bytes += (double)arena_bytes;
+    } else {
+        CK(cudaMemsetAsync(e->arena, 0, arena_bytes, e->stream));
+        for (const Seg& sg : segs) {
+            CK(cudaMemcpyAsync(e->arena + sg.off, sg.src, sg.bytes, cudaMemcpyHostToDevice, e->stream));
+            e->stats.h2d_bytes += (double)sg.bytes;
+        }
+    }
+    unsigned char* ab = e->arena;
+    e->A_ptr = (int*)(ab + o_aptr); e->A_idx = (int*)(ab + o_aidx); e->A_val = (double*)(ab + o_aval);
+    e->AT_ptr = (int*)(ab + o_atptr); e->AT_idx = (int*)(ab + o_atidx); e->AT_val = (double*)(ab + o_atval);
+    e->A_wc = (int*)(ab + o_awc); e->AT_wc = (int*)(ab + o_atwc);
+    e->A_chunk = (int4*)(ab + o_ach); e->AT_chunk = (int4*)(ab + o_atch);
+    e->A_pcn = (int*)(ab + o_apcn); e->A_pcp = (int*)(ab + o_apcp);
+    e->AT_pcn = (int*)(ab + o_atpcn); e->AT_pcp = (int*)(ab + o_atpcp);
+    if (planA.n_long) { e->A_cl = (int*)(ab + o_acl); e->A_lr = (int4*)(ab + o_alr); e->A_lp = (double*)(ab + o_alp); }
+    if (planAT.n_long) { e->AT_cl = (int*)(ab + o_atcl); e->AT_lr = (int4*)(ab + o_atlr); e->AT_lp = (double*)(ab + o_atlp); }
     const int gmax = std::max(e->grid, e->grid_mu);
 
     // one slab for all FP64 vectors, each 256-byte aligned
@@ -1210,9 +1382,7 @@ void abipgpu_lp_destroy(abipgpu_lp* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     {
-        void* ptrs[] = {e->A_ptr, e->A_idx, e->A_val, e->AT_ptr, e->AT_idx, e->AT_val, e->A_pcn, e->A_pcp, e->AT_pcn,
-                        e->AT_pcp, e->A_cl, e->AT_cl, e->A_lr, e->AT_lr, e->A_lp, e->AT_lp, e->A_wc, e->AT_wc,
-                        e->A_chunk, e->AT_chunk, e->slab};
+        void* ptrs[] = {e->arena, e->slab};
         for (void* q : ptrs) {
             if (e->stream) dev_free(q, e->stream);  // stream-ordered: no device-wide synchronisation
         }
@@ -1259,6 +1429,7 @@ abip_float abipgpu_lp_g_th(const abipgpu_lp* e) { return e->ctx.g_th; }
 
 int abipgpu_lp_cold_start(abipgpu_lp* e, abip_float mu, abip_float beta) {
     e->dirty = true;
+    if (e->batch) return defer(e, PreOp{PRE_COLD, 0, 0, 0, mu, beta});
     CK(cudaSetDevice(e->device));
     k_cold_start<<<(e->l + 255) / 256, 256, 0, e->stream>>>(e->vec[ABIPGPU_VEC_U], e->vec[ABIPGPU_VEC_V], e->m, e->l,
                                                              sqrt(mu / beta));
@@ -1268,6 +1439,10 @@ int abipgpu_lp_cold_start(abipgpu_lp* e, abip_float mu, abip_float beta) {
 
 int abipgpu_lp_outer_prologue(abipgpu_lp* e, int avg_criterion) {
     e->dirty = true;
+    if (e->batch) {
+        e->restart_synced = true;
+        return defer(e, PreOp{PRE_PROLOGUE, avg_criterion, 0, 0, 0.0, 0.0});
+    }
     CK(cudaSetDevice(e->device));
     const size_t bytes = sizeof(double) * e->l;
     CK(cudaMemsetAsync(e->vec[ABIPGPU_VEC_USUM], 0, bytes, e->stream));
@@ -1308,9 +1483,12 @@ int abipgpu_lp_admm_iter(abipgpu_lp* e, abip_int j, abip_int k, abip_float mu, a
     if (a.restart_active) {
         if (e->restart_synced && j > 0) {
             const size_t bytes = sizeof(double) * e->l;
-            e->dirty = true;
-            CK(cudaMemcpyAsync(a.u_avg, a.u_sum, bytes, cudaMemcpyDeviceToDevice, e->stream));
-            CK(cudaMemcpyAsync(a.v_avg, a.v_sum, bytes, cudaMemcpyDeviceToDevice, e->stream));
+            if (e->batch) {
+                if (defer(e, PreOp{PRE_RESTART_COPY, 0, 0, 0, 0.0, 0.0})) return -1;
+            } else {
+                CK(cudaMemcpyAsync(a.u_avg, a.u_sum, bytes, cudaMemcpyDeviceToDevice, e->stream));
+                CK(cudaMemcpyAsync(a.v_avg, a.v_sum, bytes, cudaMemcpyDeviceToDevice, e->stream));
+            }
         }
         e->restart_synced = false;
     }
@@ -1364,6 +1542,7 @@ int abipgpu_lp_mu_stats(abipgpu_lp* e, int avg_criterion, abip_float* sc) {
 
 int abipgpu_lp_reinit(abipgpu_lp* e, int indx, abip_float sigma, int avg_criterion) {
     e->dirty = true;
+    if (e->batch) return defer(e, PreOp{PRE_REINIT, indx, avg_criterion, 0, sigma, 0.0});
     CK(cudaSetDevice(e->device));
     double* u = e->vec[avg_criterion ? ABIPGPU_VEC_UAVGC : ABIPGPU_VEC_U];
     double* v = e->vec[avg_criterion ? ABIPGPU_VEC_VAVGC : ABIPGPU_VEC_V];
@@ -1375,6 +1554,7 @@ int abipgpu_lp_reinit(abipgpu_lp* e, int indx, abip_float sigma, int avg_criteri
 
 int abipgpu_lp_clamp_v(abipgpu_lp* e) {
     e->dirty = true;
+    if (e->batch) return defer(e, PreOp{PRE_CLAMP, 0, 0, 0, 0.0, 0.0});
     CK(cudaSetDevice(e->device));
     k_clamp_v<<<(e->l + 255) / 256, 256, 0, e->stream>>>(e->vec[ABIPGPU_VEC_V], e->l);
     CK(cudaGetLastError());
@@ -1384,6 +1564,7 @@ int abipgpu_lp_clamp_v(abipgpu_lp* e) {
 
 int abipgpu_lp_bb_begin(abipgpu_lp* e) {
     e->dirty = true;
+    if (e->batch) return defer(e, PreOp{PRE_BB_BEGIN, 0, 0, 0, 0.0, 0.0});
     CK(cudaSetDevice(e->device));
     const size_t bytes = sizeof(double) * e->l;
     CK(cudaMemcpyAsync(e->vec[ABIPGPU_VEC_BB_UPREV], e->vec[ABIPGPU_VEC_U], bytes, cudaMemcpyDeviceToDevice, e->stream));
@@ -1432,6 +1613,7 @@ int abipgpu_lp_bb_round(abipgpu_lp* e, int carry, abip_int k, abip_float mu, abi
 }
 
 int abipgpu_lp_solve_vec(abipgpu_lp* e, int rhs_id, int warm_id, abip_int iter, abip_float* sc) {
+    if (flush_pending(e)) return -1;
     CK(cudaSetDevice(e->device));
     if (rhs_id < 0 || rhs_id > 20 || warm_id > 20) return -1;
     const double* s = warm_id >= 0 ? e->vec[warm_id] : nullptr;
@@ -1441,7 +1623,39 @@ int abipgpu_lp_solve_vec(abipgpu_lp* e, int rhs_id, int warm_id, abip_int iter, 
     return 0;
 }
 
+}  // extern "C"
+// executes the deferred operations of a batch engine with ordinary launches (needed before anything other than a
+// batched step reads the vectors: get/set_vec, solve_vec)
+static int flush_pending(abipgpu_lp* e) {
+    if (!e->n_pend) return 0;
+    BatchExec* b = e->batch;
+    const bool synced = e->restart_synced;
+    e->batch = nullptr;
+    int rc = 0;
+    const int n = e->n_pend;
+    e->n_pend = 0;
+    for (int q = 0; q < n && !rc; ++q) {
+        const PreOp& op = e->pend[q];
+        if (op.code == PRE_COLD) rc = abipgpu_lp_cold_start(e, op.d0, op.d1);
+        else if (op.code == PRE_PROLOGUE) rc = abipgpu_lp_outer_prologue(e, op.i0);
+        else if (op.code == PRE_REINIT) rc = abipgpu_lp_reinit(e, op.i0, op.d0, op.i1);
+        else if (op.code == PRE_CLAMP) rc = abipgpu_lp_clamp_v(e);
+        else if (op.code == PRE_BB_BEGIN) rc = abipgpu_lp_bb_begin(e);
+        else if (op.code == PRE_RESTART_COPY) {
+            const size_t bytes = sizeof(double) * e->l;
+            if (cudaMemcpyAsync(e->vec[ABIPGPU_VEC_UAVG], e->vec[ABIPGPU_VEC_USUM], bytes, cudaMemcpyDeviceToDevice, e->stream) != cudaSuccess ||
+                cudaMemcpyAsync(e->vec[ABIPGPU_VEC_VAVG], e->vec[ABIPGPU_VEC_VSUM], bytes, cudaMemcpyDeviceToDevice, e->stream) != cudaSuccess)
+                rc = -1;
+        }
+    }
+    e->restart_synced = synced;
+    e->batch = b;
+    e->dirty = true;
+    return rc;
+}
+extern "C" {
 int abipgpu_lp_get_vec(abipgpu_lp* e, int id, abip_float* host, abip_int len) {
+    if (flush_pending(e)) return -1;
     CK(cudaSetDevice(e->device));
     if (id < 0 || id > 20 || len > e->vec_len[id]) return -1;
     CK(cudaMemcpyAsync(host, e->vec[id], sizeof(double) * len, cudaMemcpyDeviceToHost, e->stream));
@@ -1451,6 +1665,7 @@ int abipgpu_lp_get_vec(abipgpu_lp* e, int id, abip_float* host, abip_int len) {
 }
 
 int abipgpu_lp_set_vec(abipgpu_lp* e, int id, const abip_float* host, abip_int len) {
+    if (flush_pending(e)) return -1;
     CK(cudaSetDevice(e->device));
     if (id < 0 || id > 20 || len > e->vec_len[id]) return -1;
     CK(cudaMemcpyAsync(e->vec[id], host, sizeof(double) * len, cudaMemcpyHostToDevice, e->stream));
