@@ -140,7 +140,16 @@ def _ref_sample(args, p, which):
     Barzilai-Borwein searches that run between them (early iterations use the loosest CG tolerance, so this
     over-states the CPU's average iteration rate)."""
     from oracle import ref_lp
-    return ref_lp.solve(p, which=which, eps=args.eps, max_admm_iters=args.cpu_sample_iters + 1)
+    # the reference's C code prints progress lines to stdout ("Done the pc rescaling!"): keep stdout to the one JSON
+    # line of the contract by pointing fd 1 at stderr while it runs
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return ref_lp.solve(p, which=which, eps=args.eps, max_admm_iters=args.cpu_sample_iters + 1)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
 
 
 def run_reference(args):
