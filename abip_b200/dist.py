@@ -107,3 +107,34 @@ class LpSolverDist:
             self.close()
         except Exception:
             pass
+
+
+def shard_indices(count: int, world: int, rank: int) -> list:
+    """Problems of a batch owned by `rank`: interleaved, so that every GPU sees the same mix of problem sizes."""
+    return list(range(rank, count, world))
+
+
+def lp_solve_batch_sharded(problems, params: dict | None = None, concurrency: int = 296, ctas_per_problem: int = 1,
+                           group=None, gather: bool = True, solve_fn=None, **raw_settings):
+    """BASELINE.json configs[4]: a batch of independent LPs sharded one problem set per GPU (one process per GPU,
+    no data-path collective).  Every rank calls it with the FULL list; rank r solves problems r, r + world, ... with
+    `lp_solve_batch` on its own GPU.  gather=True: the results are all-gathered (torch.distributed objects) and every
+    rank returns the full list in the original order; gather=False: {index: result} of the local shard.
+    solve_fn(problems, params, concurrency, ctas_per_problem) replaces lp_solve_batch (CPU tests of the plumbing)."""
+    import torch.distributed as dist
+    from .api import lp_solve_batch
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    problems = list(problems)
+    mine = shard_indices(len(problems), world, rank)
+    fn = solve_fn or (lambda ps, prm, cc, ct: lp_solve_batch(ps, prm, concurrency=cc, ctas_per_problem=ct,
+                                                            **raw_settings))
+    local = fn([problems[i] for i in mine], params, min(concurrency, max(len(mine), 1)), ctas_per_problem) if mine else []
+    res = dict(zip(mine, local))
+    if not gather:
+        return res
+    parts = [None] * world
+    dist.all_gather_object(parts, res, group=group)
+    merged = {}
+    for part in parts:
+        merged.update(part)
+    return [merged[i] for i in range(len(problems))]

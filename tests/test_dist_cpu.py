@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from abip_b200 import problems
-from abip_b200.dist import assemble_shards, column_partition, exchange_handles
+from abip_b200.dist import assemble_shards, column_partition, exchange_handles, lp_solve_batch_sharded, shard_indices
 
 
 def _free_port():
@@ -69,3 +69,35 @@ def test_column_partition_properties(world):
         assert c0 == pos and nl >= 0
         pos += nl
     assert pos == p.n
+
+
+def _batch_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        probs = [("problem", i) for i in range(7)]
+        seen = []
+
+        def fake_solve(ps, params, conc, ctas):     # stands in for lp_solve_batch (no GPU here)
+            seen.extend(ps)
+            assert conc <= max(len(ps), 1) and ctas == 1
+            return [(p[1] * 10, rank) for p in ps]
+
+        out = lp_solve_batch_sharded(probs, dict(tol=1e-4), solve_fn=fake_solve)
+        assert [p[1] for p in seen] == shard_indices(7, world, rank)
+        assert [o[0] for o in out] == [10 * i for i in range(7)]           # original order on every rank
+        assert [o[1] for o in out] == [i % world for i in range(7)]       # problem i was solved by rank i % world
+        local = lp_solve_batch_sharded(probs, None, solve_fn=fake_solve, gather=False)
+        assert sorted(local) == shard_indices(7, world, rank)
+        open(os.path.join(out_dir, f"bok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_batch_sharding(tmp_path):
+    """configs[4]: independent LPs sharded one problem set per GPU -- no data-path collective, results gathered."""
+    world = 2
+    mp.spawn(_batch_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"bok{r}") for r in range(world))
+    assert shard_indices(5, 8, 6) == [] and shard_indices(10, 4, 1) == [1, 5, 9]
