@@ -1678,6 +1678,27 @@ int abipgpu_lp_spmv(abipgpu_lp* e, int trans, const abip_float* x, abip_float* y
     return abipgpu_lp_spmv_host(e, trans, x, y, 0);
 }
 
+abip_int abipgpu_plan_debug(abip_int nrows, const int* rowptr, abip_int ctas, abip_int deal, int* chunks4,
+                            abip_int max_chunks, int* warp_chunk, int* info6) {
+    if (nrows <= 0 || !rowptr || ctas <= 0) return 0;
+    std::vector<int> ptr(rowptr, rowptr + nrows + 1);
+    SpmvPlan P;
+    setenv("ABIP_GPU_PLAN_DEAL", deal ? "1" : "0", 1);
+    build_spmv_plan(ptr, (int)nrows, (int)ctas * kWarps, "ABIP_GPU_LANES_DEBUG", &P);
+    unsetenv("ABIP_GPU_PLAN_DEAL");
+    if (info6) {
+        info6[0] = kWarps; info6[1] = kChunk; info6[2] = kChunkRows;
+        info6[3] = P.n_long; info6[4] = P.n_pieces; info6[5] = P.lanes_log2;
+    }
+    if ((abip_int)P.chunk.size() > max_chunks) return -(abip_int)P.chunk.size();
+    for (size_t i = 0; i < P.chunk.size(); ++i) {
+        chunks4[4 * i] = P.chunk[i].x; chunks4[4 * i + 1] = P.chunk[i].y;
+        chunks4[4 * i + 2] = P.chunk[i].z; chunks4[4 * i + 3] = P.chunk[i].w;
+    }
+    if (warp_chunk) memcpy(warp_chunk, P.warp_chunk.data(), sizeof(int) * P.warp_chunk.size());
+    return (abip_int)P.chunk.size();
+}
+
 void abipgpu_lp_describe(const abipgpu_lp* e, char* buf, abip_int buflen) {
     if (buflen > 0) snprintf(buf, (size_t)buflen, "%s", e->desc);
 }

@@ -284,6 +284,12 @@ abip_float abipgpu_lp_g_th(const abipgpu_lp *e);
 int abipgpu_lp_spmv(abipgpu_lp *e, int trans, const abip_float *x, abip_float *y);
 /* launch geometry and SpMV variant chosen from the row-length statistics */
 void abipgpu_lp_describe(const abipgpu_lp *e, char *buf, abip_int buflen);
+/* The SpMV plan of a CSR matrix for a persistent grid of `ctas` CTAs (host-only, no device needed; for tests and
+ * tools).  Outputs: chunk descriptors {row0, nnz0, rows | -(piece slot) - 1, nnz} as 4 ints each (capacity
+ * max_chunks; returns the number of chunks, or -needed when the capacity is too small), warp_chunk [ctas * warps + 1],
+ * info = {warps per CTA, chunk nonzero limit, chunk row limit, long rows, pieces, lanes per row (log2)}. */
+abip_int abipgpu_plan_debug(abip_int nrows, const int *rowptr, abip_int ctas, abip_int deal, int *chunks4,
+                            abip_int max_chunks, int *warp_chunk, int *info6);
 
 /* ------------------------------------------------------------------------------------------------
  * (4) ABIP-QCP: min 1/2 x'Qx + c'x  s.t. Ax = b, x in K (SOC, rotated SOC, free, zero, orthant blocks in this

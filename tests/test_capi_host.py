@@ -102,3 +102,67 @@ def test_no_cpu_fallback_without_gpu():
         api.LinSysPlugin(p.csc())
     with pytest.raises(RuntimeError):
         api.LpEngine(p.csc())
+
+
+@pytest.mark.parametrize("deal", [0, 1])
+@pytest.mark.parametrize("case", ["short", "mixed", "long", "empty_rows", "tiny"])
+def test_spmv_plan_invariants(case, deal):
+    """abipgpu_plan_debug (host-only): the SpMV plan of csrc/spmv_host.h covers every row exactly once -- short rows
+    in chunks within the nonzero / row limits, long rows as consecutive equal pieces with consecutive scratch slots --
+    and deals the chunks to the warps in CTA-contiguous groups."""
+    import ctypes as C
+    import numpy as np
+    from abip_b200 import _capi
+    L = _capi.lib()
+    rng = np.random.default_rng(3)
+    lens = {"short": rng.integers(1, 9, 5000), "mixed": np.where(rng.random(3000) < 0.02, rng.integers(300, 2000, 3000),
+                                                                 rng.integers(0, 40, 3000)),
+            "long": rng.integers(253, 5000, 40), "empty_rows": np.where(rng.random(2000) < 0.5, 0, 7),
+            "tiny": np.array([3, 1, 2])}[case]
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    nrows, nnz, ctas = len(lens), int(ptr[-1]), 5
+    cap = 4 * (nnz // 8 + nrows + 64)
+    chunks = np.zeros(4 * cap, dtype=np.int32)
+    info = np.zeros(6, dtype=np.int32)
+    wc = np.zeros(ctas * 64 + 1, dtype=np.int32)
+    L.abipgpu_plan_debug.restype = C.c_long
+    L.abipgpu_plan_debug.argtypes = [C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
+    n = L.abipgpu_plan_debug(nrows, ptr.ctypes.data, ctas, deal, chunks.ctypes.data, cap, wc.ctypes.data, info.ctypes.data)
+    assert n > 0
+    warps, lim_nnz, lim_rows, n_long, n_pieces, _ = info.tolist()
+    ch = chunks[:4 * n].reshape(n, 4)
+    W = ctas * warps
+    wc = wc[:W + 1]
+    assert wc[0] == 0 and wc[-1] == n and np.all(np.diff(wc) >= 0)
+    row_seen = np.zeros(nrows, dtype=np.int64)
+    nnz_seen = np.zeros(max(nnz, 1), dtype=np.int64)
+    pieces = {}
+    for row0, nnz0, nr, cnt in ch.tolist():
+        assert 0 <= cnt <= lim_nnz and 0 <= nnz0 and nnz0 + cnt <= nnz
+        nnz_seen[nnz0:nnz0 + cnt] += 1
+        if nr > 0:                                   # chunk of whole rows
+            assert nr <= lim_rows and ptr[row0] == nnz0 and ptr[row0 + nr] == nnz0 + cnt
+            assert np.all(lens[row0:row0 + nr] <= lim_nnz)
+            row_seen[row0:row0 + nr] += 1
+        else:                                        # piece of a long row, scratch slot -nr - 1
+            assert lens[row0] > lim_nnz and ptr[row0] <= nnz0 and nnz0 + cnt <= ptr[row0 + 1] and cnt > 0
+            pieces.setdefault(row0, []).append((-nr - 1, nnz0, cnt))
+    assert np.all(row_seen[lens <= lim_nnz] == 1) and np.all(row_seen[lens > lim_nnz] == 0)
+    assert np.all(nnz_seen[:nnz] == 1)               # every nonzero in exactly one chunk
+    assert len(pieces) == n_long == int(np.sum(lens > lim_nnz))
+    slots = sorted(s for ps in pieces.values() for s, _, _ in ps)
+    assert slots == list(range(n_pieces))
+    for row, ps in pieces.items():
+        ps.sort()
+        assert [s for s, _, _ in ps] == list(range(ps[0][0], ps[0][0] + len(ps)))        # consecutive slots
+        assert ps[0][1] == ptr[row] and sum(c for _, _, c in ps) == lens[row]
+        assert all(a[1] + a[2] == b[1] for a, b in zip(ps, ps[1:]))                        # in order, contiguous
+    # the pieces of a long row stay inside one CTA (they are combined after a CTA barrier)
+    cta_of_chunk = np.searchsorted(wc[::warps], np.arange(n), side="right") - 1
+    for row, ps in pieces.items():
+        idx = [i for i, c in enumerate(ch.tolist()) if c[2] <= 0 and c[0] == row]
+        assert len(set(cta_of_chunk[idx].tolist())) == 1
+    if not deal and case != "tiny":                  # contiguous mode: CTA b owns a contiguous range of rows
+        first_rows = [ch[wc[b * warps]:wc[(b + 1) * warps], 0] for b in range(ctas) if wc[(b + 1) * warps] > wc[b * warps]]
+        for a, b in zip(first_rows, first_rows[1:]):
+            assert a.max() < b.min()
