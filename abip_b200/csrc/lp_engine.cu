@@ -841,7 +841,7 @@ struct BatchExec {
     int cap = 0;
     int wait_us = 5000;
     std::mutex mu;
-    std::condition_variable cv_req, cv_done;
+    std::condition_variable cv_req;
     std::vector<BatchReq*> pending;
     int n_solving = 0;
     bool stop = false;
