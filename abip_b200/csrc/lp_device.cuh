@@ -43,11 +43,11 @@ __device__ __forceinline__ void vgrid_init(bool batched) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Asynchronous global -> shared staging of the matrix arrays (cp.async 16 B per lane, SASS LDGSTS, L2-only
-// caching so the stream does not evict the gathered vector from L1).  No registers are tied up by the loads in
-// flight, so the persistent grid can run 32 warps per SM with a kStages-deep ring per warp.
-// (A TMA bulk-copy ring -- cp.async.bulk + mbarrier, three small 1-2 KB copies per chunk -- was measured slower
-//  on this access pattern: 40.6 us vs 24.5 us per A' pass at cfg2; see profiles/ and DESIGN.md.)
+// cp.async helpers (16 / 8 bytes per lane).  The matrix stream itself is staged by TMA bulk copies (WarpSmem below);
+// these are used by the optional page cache of the gathered vector (spmv_load_pages, compiled out by default).
+// History (profiles/r01_spmv_variants.md): the first version staged the matrix arrays with cp.async as well (7 LDGSTS
+// per lane and chunk = 25 % of all L1 data-pipe wavefronts of the kernel); per-warp TMA rings of depth 3 were slower
+// than one buffer per warp because of the shared memory they take from L1.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
@@ -111,7 +111,7 @@ struct Csr {
 
 // Per-warp staging buffer in shared memory: [val window | idx window | row-ptr window].  The value and index windows
 // are FIXED-size (kWin elements) and start at the nonzero index (s & ~3) of the chunk, so one chunk (<= kChunk =
-// kWin - 4 nonzeros) always fits, every copy is a compile-time number of 16-byte cp.async operations, and the inner
+// kWin - 4 nonzeros) always fits, every copy has a compile-time size (three TMA bulk copies per chunk), and the inner
 // loops use 128-bit shared-memory loads without bounds checks.  Elements of the window outside the chunk belong to
 // neighbouring rows (or to the zero padding behind the arrays): their products are computed and never summed.
 constexpr int kWin = 256;
@@ -296,13 +296,16 @@ struct Reducer {
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// K1: CSR SpMV phase ("CSR-stream" per warp, cp.async-staged).  fn(row, dot) is called once per row by one lane with
-// dot = A[row,:] * x.  For each chunk the warp
-//   1. waits for the chunk's cp.async copies (issued kStages chunks ahead, also across grid barriers and across
-//      the switch to the matrix of the next phase, `next`), gathers x and multiplies in shared memory;
-//   2. reduces the rows of the chunk out of shared memory, L lanes per row (L = 1 reproduces the serial
+// K1: CSR SpMV phase ("CSR-stream" per warp, TMA-staged).  fn(row, dot) is called once per row by one thread with
+// dot = A[row,:] * x.  For each of its chunks the warp
+//   1. waits on its mbarrier for the chunk's bulk copies (issued one chunk ahead, also across grid barriers and
+//      across the switch to the matrix of the next phase, `next`);
+//   2. L = 1 (short rows): one lane per row -- index, value, gather, multiply, add in the row's own order (the serial
 //      summation order of the reference, linsys/common.c:624-634);
-//   long rows arrive as consecutive pieces and are accumulated per lane, then tree-reduced.
+//      L > 1: 128-bit loads of indices and values, 8 independent gathers per lane, products back to shared memory,
+//      then L lanes per row reduce the rows of the chunk;
+//   3. a piece of a long row (d.z <= 0) is reduced by the whole warp into the scratch slot -d.z - 1; after the CTA has
+//      finished its chunks one thread per long row adds the pieces in order and calls fn.
 // x may have been written earlier in the same kernel (ordinary coherent loads; L1 is invalidated by the grid
 // barrier's fence).  Replaces _accum_by_Atrans (reference linsys/common.c:598-639) for both A and A'.
 // ---------------------------------------------------------------------------------------------------------
@@ -554,7 +557,7 @@ __device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, WarpSme
     }
 }
 
-// Dynamic shared memory of every persistent kernel: [reducer scratch][per-warp staging rings]
+// Dynamic shared memory of every persistent kernel: [reducer scratch][mbarriers][plan cache][per-warp staging buffers]
 constexpr size_t kRedBytes = sizeof(double) * kMaxRed * kWarps;
 constexpr size_t kBarOff = kRedBytes;                                            // one mbarrier per warp
 constexpr int kPlanSlots = 2;
