@@ -7,8 +7,9 @@ iterations, maximum ADMM iterations, tolerance at position 7, output prefix last
 ignored) next to named options.  The file goes through abip_b200.mps (mpsread + preprocess.m restated), the standard
 form through abip_b200.api.abip -- i.e. through the C ABI of libabip_gpu.so; there is no CPU fallback.
 
-Writes <out>.json (status, iterations, objectives incl. the objective constant, residuals, times) and <out>.sol (x in
-the variables of the file, one value per line).
+Writes <out>.json (status, iterations, objectives incl. the objective constant, residuals, times; with the keys that
+scripts/bench-lp/analyze_abip.py reads for both of the reference's result schemas) and <out>.sol (x in the variables
+of the file, one value per line).
 """
 from __future__ import annotations
 
@@ -58,7 +59,7 @@ def main(argv=None) -> int:
     if a.max_admm_iters is not None:
         params["max_admm_iter"] = a.max_admm_iters
     t1 = time.perf_counter()
-    x, y, s, info = lp_solve(std.A, std.b, std.c, params)
+    x, y, s, info = lp_solve(std.A, std.b, std.c, params, want_stats=True)
     t_solve = time.perf_counter() - t1
     res = dict(problem=std.name or a.mps, m=int(std.A.shape[0]), n=int(std.A.shape[1]), nnz=int(std.A.nnz),
                n_original=int(std.n_orig), status=info["status"], status_val=int(info["status_val"]),
@@ -66,6 +67,12 @@ def main(argv=None) -> int:
                pobj=float(info["pobj"]) + std.objcon, dobj=float(info["dobj"]) + std.objcon, objcon=std.objcon,
                pres=float(info["pres"]), dres=float(info["dres"]), gap=float(info["gap"]),
                read_time_s=t_read, solve_wall_s=t_solve, tol=a.tol, solver="abip-lp-b200")
+    # the keys the reference's result scripts read (scripts/bench-lp/analyze_abip.py:10-60): MATLAB schema
+    # (pres, dres, time, status, pobj, dobj, admm_iter, ipm_iter) and the schema of its C binary
+    res["time"] = float(info["setup_time_ms"] + info["solve_time_ms"]) / 1e3
+    res.update(InnerIter=res["admm_iter"], OuterIter=res["ipm_iter"], PResABIP=res["pres"], DResABIP=res["dres"],
+               ABIPTime=res["time"], PObj=res["pobj"], DObj=res["dobj"],
+               CGIter=int(info.get("stats", {}).get("n_cg_iters", 0)))
     with open(a.out + ".json", "w") as fh:
         json.dump(res, fh, indent=1)
     xo = std.recover(x)

@@ -153,6 +153,10 @@ def test_cli_end_to_end_on_gpu(tmp_path):
     assert pr.returncode == 0, pr.stdout[-2000:] + pr.stderr[-2000:]
     res = json.load(open(out + ".json"))
     assert res["status"] == "Solved"
+    for key in ("pres", "dres", "time", "status", "pobj", "dobj", "admm_iter", "ipm_iter",          # analyze_abip.py:10-28
+                "InnerIter", "OuterIter", "PResABIP", "DResABIP", "ABIPTime", "PObj", "DObj", "CGIter"):  # :33-60
+        assert key in res
+    assert res["CGIter"] > 0 and res["InnerIter"] == res["admm_iter"]
     assert abs(res["pobj"] - (r0.fun + g.objcon)) <= 2e-3 * (1 + abs(r0.fun + g.objcon))
     x = np.loadtxt(out + ".sol")
     assert x.size == g.f.size
