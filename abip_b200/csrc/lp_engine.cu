@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 // =========================================================================================================
@@ -1683,9 +1684,12 @@ abip_int abipgpu_plan_debug(abip_int nrows, const int* rowptr, abip_int ctas, ab
     if (nrows <= 0 || !rowptr || ctas <= 0) return 0;
     std::vector<int> ptr(rowptr, rowptr + nrows + 1);
     SpmvPlan P;
+    const char* prev = getenv("ABIP_GPU_PLAN_DEAL");
+    const std::string saved = prev ? prev : "";
     setenv("ABIP_GPU_PLAN_DEAL", deal ? "1" : "0", 1);
     build_spmv_plan(ptr, (int)nrows, (int)ctas * kWarps, "ABIP_GPU_LANES_DEBUG", &P);
-    unsetenv("ABIP_GPU_PLAN_DEAL");
+    if (prev) setenv("ABIP_GPU_PLAN_DEAL", saved.c_str(), 1);
+    else unsetenv("ABIP_GPU_PLAN_DEAL");
     if (info6) {
         info6[0] = kWarps; info6[1] = kChunk; info6[2] = kChunkRows;
         info6[3] = P.n_long; info6[4] = P.n_pieces; info6[5] = P.lanes_log2;
