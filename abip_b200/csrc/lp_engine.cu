@@ -691,10 +691,25 @@ __global__ void k_gather_perm(const double* src, const int* perm, double* dst, l
     if (q < nnz) dst[q] = src[perm[q]];
 }
 
+// Locality ordering (sjds_host.h: locality_order): the engine works in a permuted index space; vectors are permuted
+// whenever they cross the C ABI.  n2o[i] = caller's index of the engine's entry i.
+__global__ void k_perm_in(const double* src_old, const int* n2o, double* dst_new, int len, int valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) {
+        const int o = n2o[i];
+        if (o < valid) dst_new[i] = src_old[o];
+    }
+}
+__global__ void k_perm_out(const double* src_new, const int* n2o, double* dst_old, int len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) dst_old[n2o[i]] = src_new[i];
+}
+
 // =========================================================================================================
 // Host side of the engine
 // =========================================================================================================
 #include "spmv_host.h"
+#include "sjds_host.h"
 
 struct ABIPGPU_LP {
     int device = 0;
@@ -724,6 +739,10 @@ struct ABIPGPU_LP {
     double *p = nullptr, *r = nullptr, *Gp = nullptr, *tmp = nullptr, *partials = nullptr, *dsc = nullptr;
     double* dphase = nullptr;
     double *xin = nullptr, *yout = nullptr;  // staging for host-pointer plugin calls [l] each
+    double *xin2 = nullptr, *yout2 = nullptr;  // same, engine order (permuted engines only)
+    bool permuted = false;                   // locality ordering active: engine index space != caller's
+    int *d_rn2o = nullptr, *d_cn2o = nullptr, *d_pl = nullptr;  // new -> old maps: rows [m], columns [n], whole l-space
+    double order_ms = 0;
     double* hsc = nullptr;                   // pinned host scalar block
     bool have_scaling = false;
     LpCtx ctx;
@@ -1000,6 +1019,8 @@ void abipgpu_lp_batch_solving(abipgpu_lp* e, int delta) {
 
 static thread_local int t_grid_request = 0;  // CTAs per engine (batch mode); 0 = whole device
 extern "C" void abipgpu_lp_request_grid(int ctas) { t_grid_request = ctas; }
+static thread_local int t_order_request = 1;  // 0: engines created by this thread keep the caller's row / column order
+extern "C" void abipgpu_lp_request_order(int on) { t_order_request = on; }
 
 struct ScaleOut {  // host outputs of the device-side equilibration
     double *D, *E, *mean_row, *mean_col;
@@ -1064,10 +1085,9 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         CK(cudaEventCreate(&e->ev_solve1));
     }
 
-    // CSR(A') is the caller's CSC; CSR(A) by counting sort (the reference's transpose(), indirect.c:81-139)
-    std::vector<int> at_ptr(n + 1), at_idx(nnz), a_ptr(m + 1, 0), a_idx(nnz), perm;
-    std::vector<double> a_val(scale_out ? 0 : nnz);
-    if (scale_out) perm.resize(nnz);
+    // CSR(A') is the caller's CSC; CSR(A) by counting sort (the reference's transpose(), indirect.c:81-139);
+    // perm[q] = position in the CSC arrays of entry q of CSR(A)
+    std::vector<int> at_ptr(n + 1), at_idx(nnz), a_ptr(m + 1, 0), a_idx(nnz), perm(nnz);
     for (long j = 0; j <= n; ++j) at_ptr[j] = (int)Ap[j];
     for (long k = 0; k < nnz; ++k) {
         if (Ai[k] < 0 || Ai[k] >= m) {
@@ -1084,11 +1104,64 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
             for (long k = Ap[j]; k < Ap[j + 1]; ++k) {
                 const int q = fill[Ai[k]]++;
                 a_idx[q] = (int)j;
-                if (scale_out) perm[q] = (int)k;
-                else a_val[q] = Ax[k];
+                perm[q] = (int)k;
             }
     }
-    std::vector<double> at_val(Ax, Ax + nnz);
+    // Locality ordering (sjds_host.h): whole-device engines work in a permuted index space in which structurally
+    // identical rows / columns are neighbours, so the 32 lanes of a gather touch a few lines instead of 32.
+    // e_* : the engine's matrices; e_a_src / e_at_src: position of every entry in the caller's CSC arrays.
+    std::vector<int> row_n2o, col_n2o;
+    bool reorder = env_int("ABIP_GPU_REORDER", 1) != 0 && t_order_request != 0 && !t_batch && t_grid_request == 0;
+    if (reorder) {
+        const auto t_o0 = std::chrono::steady_clock::now();
+        sjds::locality_order((int)m, (int)n, a_ptr, a_idx, at_ptr, at_idx, sjds::kLongRow, &row_n2o, &col_n2o);
+        bool ident = true;
+        for (long i = 0; i < m && ident; ++i) ident = row_n2o[i] == i;
+        for (long j = 0; j < n && ident; ++j) ident = col_n2o[j] == j;
+        if (ident) reorder = false;
+        e->order_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_o0).count();
+    }
+    e->permuted = reorder;
+    std::vector<int> e_a_ptr, e_a_idx, e_a_src, e_at_ptr, e_at_idx, e_at_src;
+    if (reorder) {
+        std::vector<int> row_o2n(m), col_o2n(n);
+        for (long i = 0; i < m; ++i) row_o2n[row_n2o[i]] = (int)i;
+        for (long j = 0; j < n; ++j) col_o2n[col_n2o[j]] = (int)j;
+        e_a_ptr.assign(m + 1, 0);
+        e_a_idx.resize(nnz);
+        e_a_src.resize(nnz);
+        for (long i = 0; i < m; ++i) e_a_ptr[i + 1] = e_a_ptr[i] + (a_ptr[row_n2o[i] + 1] - a_ptr[row_n2o[i]]);
+        for (long i = 0; i < m; ++i) {
+            int q = e_a_ptr[i];
+            for (int k = a_ptr[row_n2o[i]]; k < a_ptr[row_n2o[i] + 1]; ++k, ++q) {
+                e_a_idx[q] = col_o2n[a_idx[k]];
+                e_a_src[q] = perm[k];
+            }
+        }
+        e_at_ptr.assign(n + 1, 0);
+        e_at_idx.resize(nnz);
+        e_at_src.resize(nnz);
+        for (long j = 0; j < n; ++j) e_at_ptr[j + 1] = e_at_ptr[j] + (at_ptr[col_n2o[j] + 1] - at_ptr[col_n2o[j]]);
+        for (long j = 0; j < n; ++j) {
+            int q = e_at_ptr[j];
+            for (int k = at_ptr[col_n2o[j]]; k < at_ptr[col_n2o[j] + 1]; ++k, ++q) {
+                e_at_idx[q] = row_o2n[at_idx[k]];
+                e_at_src[q] = k;
+            }
+        }
+    } else {
+        e_a_ptr = a_ptr;
+        e_a_idx = a_idx;
+        e_a_src = perm;
+        e_at_ptr = at_ptr;
+        e_at_idx = at_idx;
+    }
+    std::vector<double> a_val(scale_out ? 0 : nnz), at_val(scale_out ? 0 : nnz);
+    if (!scale_out) {
+        for (long q = 0; q < nnz; ++q) a_val[q] = Ax[e_a_src[q]];
+        if (reorder) for (long q = 0; q < nnz; ++q) at_val[q] = Ax[e_at_src[q]];
+        else memcpy(at_val.data(), Ax, sizeof(double) * nnz);
+    }
     // persistent grid: a multiple of the SM count, common to all SpMV-bearing kernels
     {
         int g1, g2, g3, g4;
@@ -1136,16 +1209,13 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     }
     const int W = e->grid * kWarps;
     SpmvPlan planA, planAT;
-    build_spmv_plan(a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA);
-    build_spmv_plan(at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT);
-    // page-cache plan; the device-side equilibration needs the raw row indices of the CSC once more
+    build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA);
+    build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT);
     PageCache pcA, pcAT;
-    std::vector<int> at_idx_raw;
-    if (scale_out && e->pc_slots > 0) at_idx_raw = at_idx;
     {
         const int min_refs = std::max(1, env_int("ABIP_GPU_PC_MINREFS", 4));
-        build_page_cache(planA, a_idx, n, e->grid, e->pc_slots, min_refs, &pcA);
-        build_page_cache(planAT, at_idx, m, e->grid, e->pc_slots, min_refs, &pcAT);
+        build_page_cache(planA, e_a_idx, n, e->grid, e->pc_slots, min_refs, &pcA);
+        build_page_cache(planAT, e_at_idx, m, e->grid, e->pc_slots, min_refs, &pcAT);
     }
 
     // One device arena for all matrix and plan arrays: packed on the host (zero padding of kPad elements behind every
@@ -1163,9 +1233,10 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         return off;
     };
     auto put_vec = [&](const auto& v) { return put(v.data(), v.size() * sizeof(v[0]), sizeof(v[0])); };
-    const size_t o_aptr = put_vec(a_ptr), o_aidx = put_vec(a_idx);
+    const size_t o_aptr = put_vec(e_a_ptr), o_aidx = put_vec(e_a_idx);
     const size_t o_aval = scale_out ? put(nullptr, nnz * sizeof(double), sizeof(double)) : put_vec(a_val);
-    const size_t o_atptr = put_vec(at_ptr), o_atidx = put_vec(at_idx), o_atval = put_vec(at_val);
+    const size_t o_atptr = put_vec(e_at_ptr), o_atidx = put_vec(e_at_idx);
+    const size_t o_atval = scale_out ? put(nullptr, nnz * sizeof(double), sizeof(double)) : put_vec(at_val);
     const size_t o_awc = put_vec(planA.warp_chunk), o_atwc = put_vec(planAT.warp_chunk);
     const size_t o_ach = put_vec(planA.chunk), o_atch = put_vec(planAT.chunk);
     const size_t o_apcn = put_vec(pcA.npages), o_apcp = put_vec(pcA.pages);
@@ -1208,7 +1279,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     // one slab for all FP64 vectors, each 256-byte aligned
     const size_t L = ((size_t)e->l + 31) & ~(size_t)31;
     const size_t Mm = ((size_t)m + 31) & ~(size_t)31, Nn = ((size_t)n + 31) & ~(size_t)31;
-    const size_t n_l_vecs = 21 + 2;  // ids 0..20 + xin + yout
+    const size_t n_l_vecs = 21 + 2 + (reorder ? 2 : 0);  // ids 0..20 + xin + yout (+ xin2 + yout2)
     const size_t total = n_l_vecs * L + 7 * Mm + 3 * Nn + (size_t)2 * kMaxRed * gmax + 64 + ABIPGPU_SC_COUNT + 32 + 2 * (size_t)gmax * kWarps;
     CK(dev_alloc((void**)&e->slab, total * sizeof(double), e->stream));
     CK(cudaMemsetAsync(e->slab, 0, total * sizeof(double), e->stream));
@@ -1222,6 +1293,16 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     e->vec_len[ABIPGPU_VEC_H] = e->vec_len[ABIPGPU_VEC_G] = m + n;
     e->xin = take(L);
     e->yout = take(L);
+    if (reorder) {
+        e->xin2 = take(L);
+        e->yout2 = take(L);
+        std::vector<int> pl(e->l);
+        for (long i = 0; i < m; ++i) pl[i] = row_n2o[i];
+        for (long j = 0; j < n; ++j) pl[m + j] = (int)m + col_n2o[j];
+        pl[m + n] = (int)(m + n);
+        if (upload(&e->d_pl, pl, e) || upload(&e->d_rn2o, row_n2o, e) || upload(&e->d_cn2o, col_n2o, e)) return -1;
+        CK(cudaStreamSynchronize(e->stream));  // pl goes out of scope
+    }
     e->dM = take(Mm);
     e->vec[ABIPGPU_VEC_M] = e->dM;  // overrides the l-sized slot: M has its own storage
     e->vec_len[ABIPGPU_VEC_M] = m;
@@ -1273,10 +1354,15 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
 #endif
 
     if (scale_out) {
-        int *d_perm = nullptr, *d_raw = nullptr;
-        if (upload(&d_perm, perm, e)) return -1;
-        if (!at_idx_raw.empty() && upload(&d_raw, at_idx_raw, e)) return -1;
-        const int* at_rows = d_raw ? d_raw : e->AT_idx;
+        // equilibrate in the CALLER's order (bit-identical D, E to abip_normalize_A) on temporary copies of the original
+        // structure, then gather the scaled values into the engine's two matrices
+        int *d_perm = nullptr, *d_atptr = nullptr, *d_atidx = nullptr, *d_aptr = nullptr, *d_asrc = nullptr, *d_atsrc = nullptr;
+        double* d_val = nullptr;
+        std::vector<double> ax_copy(Ax, Ax + nnz);
+        if (upload(&d_perm, perm, e) || upload(&d_atptr, at_ptr, e) || upload(&d_atidx, at_idx, e) || upload(&d_aptr, a_ptr, e) ||
+            upload(&d_val, ax_copy, e))
+            return -1;
+        if (reorder && (upload(&d_asrc, e_a_src, e) || upload(&d_atsrc, e_at_src, e))) return -1;
         const double min_row = 1e-3 * sqrt((double)n), max_row = 1e3 * sqrt((double)n);
         const double min_col = 1e-3 * sqrt((double)m), max_col = 1e3 * sqrt((double)m);
         double* Dt = e->p;  // scratch [m]
@@ -1284,9 +1370,9 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         k_fill<<<gm, 256, 0, e->stream>>>(e->dD, m, 1.0);
         k_fill<<<gn, 256, 0, e->stream>>>(e->dE, n, 1.0);
         auto sweep = [&](int kind) {
-            k_eq_cols<<<gn, 256, 0, e->stream>>>(kind, e->AT_ptr, e->AT_val, (int)n, e->dE, min_col, max_col);
-            k_eq_rows<<<gm, 256, 0, e->stream>>>(kind, e->A_ptr, d_perm, e->AT_val, (int)m, Dt, e->dD, min_row, max_row);
-            k_eq_apply_rows<<<gz, 256, 0, e->stream>>>(at_rows, e->AT_val, nnz, Dt);
+            k_eq_cols<<<gn, 256, 0, e->stream>>>(kind, d_atptr, d_val, (int)n, e->dE, min_col, max_col);
+            k_eq_rows<<<gm, 256, 0, e->stream>>>(kind, d_aptr, d_perm, d_val, (int)m, Dt, e->dD, min_row, max_row);
+            k_eq_apply_rows<<<gz, 256, 0, e->stream>>>(d_atidx, d_val, nnz, Dt);
         };
         if (stgs->pc_ruiz_rescale) sweep(0);
         if (stgs->origin_rescale) sweep(1);
@@ -1296,28 +1382,30 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         // mean row / column norms (summed on the host in index order, like common.c:541-557)
         double* rn = e->vec[ABIPGPU_VEC_UT];  // scratch [l] >= max(m, n)
         std::vector<double> hn(std::max(m, n));
-        k_eq_row_norms<<<gm, 256, 0, e->stream>>>(e->A_ptr, d_perm, e->AT_val, (int)m, rn);
+        k_eq_row_norms<<<gm, 256, 0, e->stream>>>(d_aptr, d_perm, d_val, (int)m, rn);
         CK(cudaMemcpyAsync(hn.data(), rn, sizeof(double) * m, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         double mr = 0.0;
         for (abip_int i = 0; i < m; ++i) mr += hn[i];
-        k_eq_col_norms<<<gn, 256, 0, e->stream>>>(e->AT_ptr, e->AT_val, (int)n, rn);
+        k_eq_col_norms<<<gn, 256, 0, e->stream>>>(d_atptr, d_val, (int)n, rn);
         CK(cudaMemcpyAsync(hn.data(), rn, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         double mc = 0.0;
         for (abip_int j = 0; j < n; ++j) mc += hn[j];
         *scale_out->mean_row = mr;
         *scale_out->mean_col = mc;
-        if (stgs->scale != 1) k_scale_all<<<gz, 256, 0, e->stream>>>(e->AT_val, nnz, stgs->scale);
-        k_gather_perm<<<gz, 256, 0, e->stream>>>(e->AT_val, d_perm, e->A_val, nnz);
+        if (stgs->scale != 1) k_scale_all<<<gz, 256, 0, e->stream>>>(d_val, nnz, stgs->scale);
+        k_gather_perm<<<gz, 256, 0, e->stream>>>(d_val, reorder ? d_asrc : d_perm, e->A_val, nnz);
+        if (reorder) k_gather_perm<<<gz, 256, 0, e->stream>>>(d_val, d_atsrc, e->AT_val, nnz);
+        else CK(cudaMemcpyAsync(e->AT_val, d_val, sizeof(double) * nnz, cudaMemcpyDeviceToDevice, e->stream));
         CK(cudaMemsetAsync(rn, 0, sizeof(double) * e->l, e->stream));
         CK(cudaMemsetAsync(Dt, 0, sizeof(double) * m, e->stream));
         CK(cudaMemcpyAsync(scale_out->D, e->dD, sizeof(double) * m, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaMemcpyAsync(scale_out->E, e->dE, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(e->stream));
-        dev_free(d_perm, e->stream);
-        dev_free(d_raw, e->stream);
+        dev_free(d_perm, e->stream); dev_free(d_atptr, e->stream); dev_free(d_atidx, e->stream); dev_free(d_aptr, e->stream);
+        dev_free(d_val, e->stream); dev_free(d_asrc, e->stream); dev_free(d_atsrc, e->stream);
         e->stats.d2h_bytes += 8.0 * 2 * (m + n);
     }
     k_precond<<<(unsigned)((m + 255) / 256), 256, 0, e->stream>>>(c.A, e->dM);
@@ -1330,10 +1418,10 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     snprintf(e->desc, sizeof(e->desc),
              "device %d (%s, %d SMs) persistent grid %d x %d threads, %zu B smem/block | CSR(A): %d rows, mean %.1f max %d "
              "nnz/row, %zu chunks (%d long rows), %d lane(s)/row | CSR(A'): %d rows, mean %.1f max %d, %zu chunks (%d long), "
-             "%d lane(s)/row | nnz=%ld | page cache %d x 256 B per CTA: %.1f%% of the gathers of A, %.1f%% of A' from shared memory",
+             "%d lane(s)/row | nnz=%ld | locality ordering %s (%.0f ms) | page cache %d x 256 B per CTA: %.1f%% of the gathers of A, %.1f%% of A' from shared memory",
              device, prop.name, e->num_sms, e->grid, kBlock, (size_t)e->smem, (int)m, planA.mean, planA.max_len,
              planA.chunk.size(), planA.n_long, 1 << planA.lanes_log2, (int)n, planAT.mean, planAT.max_len,
-             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, e->pc_slots, 100.0 * pcA.hits / nnz,
+             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, reorder ? "on" : "off", e->order_ms, e->pc_slots, 100.0 * pcA.hits / nnz,
              100.0 * pcAT.hits / nnz);
     return 0;
 }
@@ -1383,9 +1471,9 @@ void abipgpu_lp_destroy(abipgpu_lp* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     {
-        void* ptrs[] = {e->arena, e->slab};
+        void* ptrs[] = {e->arena, e->slab, e->d_pl, e->d_rn2o, e->d_cn2o};
         for (void* q : ptrs) {
-            if (e->stream) dev_free(q, e->stream);  // stream-ordered: no device-wide synchronisation
+            if (e->stream && q) dev_free(q, e->stream);  // stream-ordered: no device-wide synchronisation
         }
     }
     for (int q = 0; q < kMaxRanks; ++q)
@@ -1404,15 +1492,29 @@ int abipgpu_lp_set_problem(abipgpu_lp* e, const abip_float* b, const abip_float*
                            const abip_float* E) {
     CK(cudaSetDevice(e->device));
     const int m = e->m, n = e->n;
-    CK(cudaMemcpyAsync(e->db, b, sizeof(double) * m, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->dc, c, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
-    e->stats.h2d_bytes += 8.0 * (m + n);
     e->have_scaling = (D && E);
-    if (e->have_scaling) {
-        CK(cudaMemcpyAsync(e->dD, D, sizeof(double) * m, cudaMemcpyHostToDevice, e->stream));
-        CK(cudaMemcpyAsync(e->dE, E, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
-        e->stats.h2d_bytes += 8.0 * (m + n);
+    if (!e->permuted) {
+        CK(cudaMemcpyAsync(e->db, b, sizeof(double) * m, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->dc, c, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+        if (e->have_scaling) {
+            CK(cudaMemcpyAsync(e->dD, D, sizeof(double) * m, cudaMemcpyHostToDevice, e->stream));
+            CK(cudaMemcpyAsync(e->dE, E, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+        }
+    } else {  // caller's order -> engine order
+        const unsigned gm = (unsigned)((m + 255) / 256), gn = (unsigned)((n + 255) / 256);
+        CK(cudaMemcpyAsync(e->xin, b, sizeof(double) * m, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->xin + m, c, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+        k_perm_in<<<gm, 256, 0, e->stream>>>(e->xin, e->d_rn2o, e->db, m, m);
+        k_perm_in<<<gn, 256, 0, e->stream>>>(e->xin + m, e->d_cn2o, e->dc, n, n);
+        if (e->have_scaling) {
+            CK(cudaMemcpyAsync(e->yout, D, sizeof(double) * m, cudaMemcpyHostToDevice, e->stream));
+            CK(cudaMemcpyAsync(e->yout + m, E, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+            k_perm_in<<<gm, 256, 0, e->stream>>>(e->yout, e->d_rn2o, e->dD, m, m);
+            k_perm_in<<<gn, 256, 0, e->stream>>>(e->yout + m, e->d_cn2o, e->dE, n, n);
+        }
+        CK(cudaGetLastError());
     }
+    e->stats.h2d_bytes += 8.0 * (m + n) * (e->have_scaling ? 2 : 1);
     e->ctx.D = e->have_scaling ? e->dD : nullptr;
     e->ctx.E = e->have_scaling ? e->dE : nullptr;
     k_build_h<<<(m + n + 255) / 256, 256, 0, e->stream>>>(e->db, e->dc, e->vec[ABIPGPU_VEC_H], e->vec[ABIPGPU_VEC_G], m, n);
@@ -1659,7 +1761,14 @@ int abipgpu_lp_get_vec(abipgpu_lp* e, int id, abip_float* host, abip_int len) {
     if (flush_pending(e)) return -1;
     CK(cudaSetDevice(e->device));
     if (id < 0 || id > 20 || len > e->vec_len[id]) return -1;
-    CK(cudaMemcpyAsync(host, e->vec[id], sizeof(double) * len, cudaMemcpyDeviceToHost, e->stream));
+    if (e->permuted) {  // engine order -> caller's order
+        const int vl = (int)e->vec_len[id];
+        k_perm_out<<<(unsigned)((vl + 255) / 256), 256, 0, e->stream>>>(e->vec[id], id == ABIPGPU_VEC_M ? e->d_rn2o : e->d_pl, e->yout, vl);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(host, e->yout, sizeof(double) * len, cudaMemcpyDeviceToHost, e->stream));
+    } else {
+        CK(cudaMemcpyAsync(host, e->vec[id], sizeof(double) * len, cudaMemcpyDeviceToHost, e->stream));
+    }
     CK(cudaStreamSynchronize(e->stream));
     e->stats.d2h_bytes += 8.0 * len;
     return 0;
@@ -1669,7 +1778,14 @@ int abipgpu_lp_set_vec(abipgpu_lp* e, int id, const abip_float* host, abip_int l
     if (flush_pending(e)) return -1;
     CK(cudaSetDevice(e->device));
     if (id < 0 || id > 20 || len > e->vec_len[id]) return -1;
-    CK(cudaMemcpyAsync(e->vec[id], host, sizeof(double) * len, cudaMemcpyHostToDevice, e->stream));
+    if (e->permuted) {  // caller's order -> engine order (entries beyond len keep their values)
+        const int vl = (int)e->vec_len[id];
+        CK(cudaMemcpyAsync(e->xin, host, sizeof(double) * len, cudaMemcpyHostToDevice, e->stream));
+        k_perm_in<<<(unsigned)((vl + 255) / 256), 256, 0, e->stream>>>(e->xin, id == ABIPGPU_VEC_M ? e->d_rn2o : e->d_pl, e->vec[id], vl, (int)len);
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaMemcpyAsync(e->vec[id], host, sizeof(double) * len, cudaMemcpyHostToDevice, e->stream));
+    }
     CK(cudaStreamSynchronize(e->stream));
     e->stats.h2d_bytes += 8.0 * len;
     return 0;
@@ -1715,7 +1831,16 @@ int abipgpu_lp_spmv_host(abipgpu_lp* e, int trans, const double* x, double* y, i
     const int nin = trans ? e->m : e->n, nout = trans ? e->n : e->m;
     CK(cudaMemcpyAsync(e->xin, x, sizeof(double) * nin, cudaMemcpyHostToDevice, e->stream));
     if (accumulate) CK(cudaMemcpyAsync(e->yout, y, sizeof(double) * nout, cudaMemcpyHostToDevice, e->stream));
-    k_spmv<<<e->grid, kBlock, e->smem, e->stream>>>(trans ? e->ctx.AT : e->ctx.A, e->xin, e->yout, accumulate);
+    if (e->permuted) {
+        const int* pin = trans ? e->d_rn2o : e->d_cn2o;
+        const int* pout = trans ? e->d_cn2o : e->d_rn2o;
+        k_perm_in<<<(unsigned)((nin + 255) / 256), 256, 0, e->stream>>>(e->xin, pin, e->xin2, nin, nin);
+        if (accumulate) k_perm_in<<<(unsigned)((nout + 255) / 256), 256, 0, e->stream>>>(e->yout, pout, e->yout2, nout, nout);
+        k_spmv<<<e->grid, kBlock, e->smem, e->stream>>>(trans ? e->ctx.AT : e->ctx.A, e->xin2, e->yout2, accumulate);
+        k_perm_out<<<(unsigned)((nout + 255) / 256), 256, 0, e->stream>>>(e->yout2, pout, e->yout, nout);
+    } else {
+        k_spmv<<<e->grid, kBlock, e->smem, e->stream>>>(trans ? e->ctx.AT : e->ctx.A, e->xin, e->yout, accumulate);
+    }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(y, e->yout, sizeof(double) * nout, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -1732,9 +1857,22 @@ int abipgpu_lp_solve_host(abipgpu_lp* e, double* b, const double* s, long iter, 
     const int mn = e->m + e->n;
     CK(cudaMemcpyAsync(e->xin, b, sizeof(double) * mn, cudaMemcpyHostToDevice, e->stream));
     if (s) CK(cudaMemcpyAsync(e->yout, s, sizeof(double) * e->m, cudaMemcpyHostToDevice, e->stream));
-    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_solve_vec<true> : (const void*)k_solve_vec<false>, e->grid, e->smem, e->ctx, e->xin, (const double*)(s ? e->yout : nullptr),
+    double* rhs = e->xin;
+    const double* warm = s ? e->yout : nullptr;
+    if (e->permuted) {
+        k_perm_in<<<(unsigned)((mn + 255) / 256), 256, 0, e->stream>>>(e->xin, e->d_pl, e->xin2, mn, mn);
+        if (s) k_perm_in<<<(unsigned)((e->m + 255) / 256), 256, 0, e->stream>>>(e->yout, e->d_rn2o, e->yout2, e->m, e->m);
+        CK(cudaGetLastError());
+        rhs = e->xin2;
+        warm = s ? e->yout2 : nullptr;
+    }
+    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_solve_vec<true> : (const void*)k_solve_vec<false>, e->grid, e->smem, e->ctx, rhs, warm,
                     iter, 0))
         return -1;
+    if (e->permuted) {
+        k_perm_out<<<(unsigned)((mn + 255) / 256), 256, 0, e->stream>>>(e->xin2, e->d_pl, e->xin, mn);
+        CK(cudaGetLastError());
+    }
     CK(cudaMemcpyAsync(b, e->xin, sizeof(double) * mn, cudaMemcpyDeviceToHost, e->stream));
     if (read_sc(e, nullptr)) return -1;
     e->stats.h2d_bytes += 8.0 * (mn + (s ? e->m : 0));

@@ -16,6 +16,7 @@ extern "C" int abipgpu_lp_comm_export(abipgpu_lp* e, void* handle64);
 extern "C" int abipgpu_lp_comm_connect(abipgpu_lp* e, int G, int rank, const void* handles);
 extern "C" void abipgpu_lp_set_global_n(abipgpu_lp* e, long n_global);
 extern "C" void abipgpu_lp_request_grid(int ctas);
+extern "C" void abipgpu_lp_request_order(int on);
 // lock-step batch executor (lp_engine.cu: BatchExec)
 extern "C" void* abipgpu_batch_begin(int device, int capacity);
 extern "C" void abipgpu_batch_attach(void* b);

@@ -784,7 +784,10 @@ static ABIPGpuWork* gpu_init_impl(const ABIPData* d, ABIPInfo* info, int rank, i
         const abip_int p0 = w->A->p[w->c0];
         std::vector<abip_int> lp(w->nl + 1);
         for (abip_int j = 0; j <= w->nl; ++j) lp[j] = w->A->p[w->c0 + j] - p0;
+        // the m-space of a sharded engine is replicated and exchanged by row index: every rank must keep the caller's order
+        if (G > 1) abipgpu_lp_request_order(0);
         w->eng = abipgpu_lp_create(w->m, w->nl, lp.data(), w->A->i + p0, w->A->x + p0, &w->stgs, dev ? atoi(dev) : 0);
+        if (G > 1) abipgpu_lp_request_order(1);
     }
     if (!w->eng) {
         printf("ERROR: init_lin_sys_work failure\n");
