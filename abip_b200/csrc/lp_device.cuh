@@ -24,9 +24,6 @@ namespace cg = cooperative_groups;
 #ifndef ABIP_MIN_BLOCKS_PER_SM
 #define ABIP_MIN_BLOCKS_PER_SM 2
 #endif
-#ifndef ABIP_PAGE_CACHE
-#define ABIP_PAGE_CACHE 0  // shared-memory page cache of the gathered vector (see kPageLog2); measured: no gain yet
-#endif
 constexpr int kBlock = ABIP_BLOCK;
 constexpr int kWarps = kBlock / 32;
 constexpr int kMaxRed = 24;  // max scalars reduced between two grid barriers
@@ -42,29 +39,7 @@ __device__ __forceinline__ void vgrid_init(bool batched) {
     __syncthreads();
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// cp.async helpers (16 / 8 bytes per lane).  The matrix stream itself is staged by TMA bulk copies (WarpSmem below);
-// these are used by the optional page cache of the gathered vector (spmv_load_pages, compiled out by default).
-// History (profiles/r01_spmv_variants.md): the first version staged the matrix arrays with cp.async as well (7 LDGSTS
-// per lane and chunk = 25 % of all L1 data-pipe wavefronts of the kernel); per-warp TMA rings of depth 3 were slower
-// than one buffer per warp because of the shared memory they take from L1.
-// ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-// zero-filling variants for the page-cache loads (src_bytes = 0 => the destination is filled with zeros)
-__device__ __forceinline__ void cp_async16_zfill(unsigned dst, const void* src, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async8_zfill(unsigned dst, const void* src, int src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 
 // CSR matrix + the SpMV plan built on the host from its row-length statistics (lp_engine.cu: build_spmv_plan()).
 //   * every warp of the persistent grid owns a contiguous range of rows with (nearly) equal cost, cut into
@@ -80,28 +55,20 @@ __device__ __forceinline__ void cp_async_wait() {
 #endif
 constexpr int kChunk = ABIP_CHUNK;
 constexpr int kChunkRows = ABIP_CHUNK_ROWS;  // rows per chunk (bounds the row-pointer window)
-
-// Page cache of the gathered vector.  The gathers x[col] are bound by the L1 wavefront rate
-// (one 128-byte line per cycle at best, ~25 distinct lines per warp request on cfg2), not by HBM.  The plan
-// therefore picks, per CTA and per matrix, the 256-byte pages of x that the CTA's rows reference most often; the
-// CTA copies them into shared memory at the start of the phase (coalesced) and the column indices of its slice of
-// the matrix are re-encoded: bit 31 set => offset into the shared-memory copy, otherwise a global column index.
-constexpr int kPageLog2 = 5;                 // 32 doubles = 256 bytes per page
-constexpr int kPageDoubles = 1 << kPageLog2;
-constexpr unsigned kPcFlag = 0x80000000u;
+static_assert(ABIP_CHUNK_ROWS <= 64, "the lane-per-row path takes two rows per lane");
+#ifndef ABIP_L1U
+#define ABIP_L1U 4
+#endif
+constexpr int kL1U = ABIP_L1U;  // gathers in flight per row in the lane-per-row path
 
 struct Csr {
     const int* ptr;         // [nrows+1 (+8)]
-    const int* idx;         // [nnz (+8)] column indices (page-cache encoded when cta_npages != nullptr)
+    const int* idx;         // [nnz (+8)] column indices
     const double* val;      // [nnz (+8)]
     int nrows;
     const int* warp_chunk;  // [W+1] chunk range of each warp of the persistent grid
     const int4* chunk;      // [nchunks] {row0, nnz0, nrows | 0 | -1, nnz}
     int lanes_log2;         // lanes per row in the shared-memory row reduction (1 => reference summation order)
-    int ncols;              // length of the gathered vector (page loads are clipped to it)
-    int pc_stride;          // page-list stride per CTA
-    const int* cta_npages;  // [G] cached pages of each CTA, nullptr => no page cache
-    const int* cta_pages;   // [G * pc_stride] page ids (ascending)
     // rows longer than kChunk ("long rows", nullptr when there are none): cut into pieces, each a chunk of its own
     const int* cta_long;     // [G+1] range of long_rows owned by each CTA
     const int4* long_rows;   // {row, first piece slot, #pieces, 0}
@@ -157,7 +124,6 @@ struct WarpSmem {
     unsigned parity;      // phase parity of the next wait
     const int4* cur;      // matrix (identified by its chunk array) of the chunk in flight, nullptr: nothing in flight
     int cur_c;            // its chunk index
-    double* pc;           // the CTA's page cache (shared by all its warps), generic pointer
     int* plan;            // per-warp plan cache: kPlanSlots x {first descriptor (int4), c0, c1, valid, -}
 
     // this warp's chunk range [c0, c1) of A and the descriptor of its first chunk.  The three dependent global loads
@@ -318,42 +284,6 @@ __device__ __forceinline__ void spmv_prefetch(const Csr& A, WarpSmem& ws) {
     if (c0 < c1) ws.issue(A, c0, d0);
 }
 
-// Copies the CTA's cached pages of x into shared memory (all threads of the CTA; contains __syncthreads()).
-// Thread t copies 16-byte unit (t & 15) of pages (t >> 4) + 64 j: the page ids are fetched first (independent loads,
-// one L2 round trip), then all copies are issued asynchronously (second round trip) -- a dependent id -> copy chain
-// per page was measured at 13 us per phase.
-constexpr int kPcMaxPages = 512;
-__device__ __forceinline__ void spmv_load_pages(const Csr& A, const double* x, WarpSmem& ws) {
-    constexpr int J = kPcMaxPages * (kPageDoubles / 2) / kBlock;  // units per thread
-    constexpr int PJ = kBlock / (kPageDoubles / 2);               // pages per round
-    const int np = __ldg(A.cta_npages + VB());
-    const int* pg = A.cta_pages + (size_t)VB() * A.pc_stride;
-    const int p0 = threadIdx.x / (kPageDoubles / 2), u = threadIdx.x % (kPageDoubles / 2);
-    int id[J];
-#pragma unroll
-    for (int j = 0; j < J; ++j) id[j] = (p0 + PJ * j < np) ? __ldg(pg + p0 + PJ * j) : -1;
-    __syncthreads();  // every warp of the CTA is done with the previous phase's pages
-    const unsigned pc_s = smem_u32(ws.pc);
-    const bool al16 = (reinterpret_cast<unsigned long long>(x) & 15ull) == 0;
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        if (id[j] >= 0) {
-            const int col = (id[j] << kPageLog2) + 2 * u;
-            const unsigned dst = pc_s + 8u * (((p0 + PJ * j) << kPageLog2) + 2 * u);
-            if (al16) {
-                const int nb = min(max(A.ncols - col, 0), 2) * 8;
-                cp_async16_zfill(dst, x + (nb ? col : 0), nb);
-            } else {
-                cp_async8_zfill(dst, x + (col < A.ncols ? col : 0), col < A.ncols ? 8 : 0);
-                cp_async8_zfill(dst + 8, x + (col + 1 < A.ncols ? col + 1 : 0), col + 1 < A.ncols ? 8 : 0);
-            }
-        }
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-}
-
 #ifdef ABIP_PHASE_TIMING
 // debug: SM-clock cycles per warp spent in the sections of the chunk loop, summed over all warps and calls
 // [0] wait for the chunk  [1] gather + multiply  [2] row sums + epilogue  [3] issue of the next chunk  [4] chunks
@@ -376,23 +306,8 @@ __device__ unsigned long long g_spmv_prof[16];  // [0..7] matrices with 1 lane/r
 #define SPROF_FLUSH() do { } while (0)
 #endif
 
-// gather of one element of x: page-cache hit (bit 31 of the encoded index) => shared memory, else global memory.
-// One generic load serves both address spaces, so the warp does not diverge.
-__device__ __forceinline__ double gather_x(const double* x, const double* pc, int ci) {
-#if ABIP_PAGE_CACHE
-    const double* p = ci < 0 ? pc + (ci & 0x7fffffff) : x + ci;
-    return *p;
-#else
-    return x[ci];
-#endif
-}
-
 template <class RowFn>
 __device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, WarpSmem& ws, const Csr* next, RowFn fn) {
-#if ABIP_PAGE_CACHE
-    if (A.cta_npages) spmv_load_pages(A, x, ws);
-#endif
-    const double* pc = ws.pc;
     const int lane = threadIdx.x & 31;
     const int lg = A.lanes_log2;
     const int L = 1 << lg;
@@ -427,26 +342,55 @@ __device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, WarpSme
             const double* vs = vw + off - s;
             const int* is = iw + off - s;
             const int* rp = reinterpret_cast<const int*>(st + kValWin + kIdxWin) + (row0 & 3);
-            for (int rr = lane; rr < nr; rr += 32) {
-                const int a = rp[rr], b = rp[rr + 1];
-                double acc = 0.0;
-#pragma unroll 4
-                for (int k = a; k < b; ++k) acc = __dadd_rn(acc, __dmul_rn(vs[k], gather_x(x, pc, is[k])));
-                fn(row0 + rr, acc);
+            // a chunk holds <= 64 rows: lane l takes rows l and l + 32 together, and all gathers of a batch of kL1U
+            // nonzeros per row are issued before the first product is formed (a serial index -> gather -> add chain per
+            // nonzero was 3/4 of the A' pass: 10 dependent L2 round trips per chunk)
+            int a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+            if (lane < nr) { a0 = rp[lane]; b0 = rp[lane + 1]; }
+            if (lane + 32 < nr) { a1 = rp[lane + 32]; b1 = rp[lane + 33]; }
+            const int mx = __reduce_max_sync(0xffffffffu, max(b0 - a0, b1 - a1));
+            double acc0 = 0.0, acc1 = 0.0;
+            for (int j = 0; j < mx; j += kL1U) {
+                double x0[kL1U], x1[kL1U];
+#pragma unroll
+                for (int u = 0; u < kL1U; ++u) {
+                    const int k = a0 + j + u;
+                    x0[u] = k < b0 ? x[is[k]] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < kL1U; ++u) {
+                    const int k = a1 + j + u;
+                    x1[u] = k < b1 ? x[is[k]] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < kL1U; ++u) {
+                    const int k = a0 + j + u;
+                    if (k < b0) acc0 = __dadd_rn(acc0, __dmul_rn(vs[k], x0[u]));
+                }
+#pragma unroll
+                for (int u = 0; u < kL1U; ++u) {
+                    const int k = a1 + j + u;
+                    if (k < b1) acc1 = __dadd_rn(acc1, __dmul_rn(vs[k], x1[u]));
+                }
             }
             SPROF(1);
             __syncwarp();
-            SPROF(2);
+            // the row sums are in registers: stream in the next chunk first, the epilogue's own global loads overlap with it
             if (c + 1 < c1) ws.issue(A, c + 1, dn);
             else if (next && nx_c < nx_c1) ws.issue(*next, nx_c, dn);
             else ws.cur = nullptr;
             d = dn;
             SPROF(3);
+            if (lane < nr) fn(row0 + lane, acc0);
+            if (lane + 32 < nr) fn(row0 + lane + 32, acc1);
+            SPROF(2);
 #ifdef ABIP_PHASE_TIMING
             ++_pn;
 #endif
             continue;
         }
+        double sum0 = 0.0, sum1 = 0.0;
+        int epi_rows = 0;
         // 1. gather x for the whole window (8 independent loads per lane), multiply
         double xv[2][4];
         int4 ci[2];
@@ -454,10 +398,10 @@ __device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, WarpSme
         for (int u = 0; u < 2; ++u) ci[u] = reinterpret_cast<const int4*>(iw)[lane + 32 * u];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            xv[u][0] = gather_x(x, pc, ci[u].x);
-            xv[u][1] = gather_x(x, pc, ci[u].y);
-            xv[u][2] = gather_x(x, pc, ci[u].z);
-            xv[u][3] = gather_x(x, pc, ci[u].w);
+            xv[u][0] = x[ci[u].x];
+            xv[u][1] = x[ci[u].y];
+            xv[u][2] = x[ci[u].z];
+            xv[u][3] = x[ci[u].w];
         }
         if (nr <= 0) {  // piece of a long row: elements [off, off + n) of the window; slot -nr - 1 of the scratch
             double acc = 0.0;
@@ -493,14 +437,7 @@ __device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, WarpSme
             // 2. row sums out of shared memory, L lanes per row; each sum is parked in the row's first product slot
             double* vs = vw + off - s;  // vs[k]: product of nonzero k (global nonzero index)
             const int* rp = reinterpret_cast<const int*>(st + kValWin + kIdxWin) + (row0 & 3);
-            if (L == 1) {
-                for (int rr = lane; rr < nr; rr += 32) {
-                    const int a = rp[rr], b = rp[rr + 1];
-                    double acc = 0.0;
-                    for (int k = a; k < b; ++k) acc += vs[k];
-                    fn(row0 + rr, acc);
-                }
-            } else {
+            {  // (L == 1 never gets here: lane-per-row path above)
                 for (int base = 0; base < nr; base += rpw) {
                     const int rr = base + sub;
                     const bool ok = rr < nr;
@@ -516,22 +453,23 @@ __device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, WarpSme
                     if (ok && sl == 0 && a < b) vs[a] = acc;
                 }
                 __syncwarp();
-                // 3. epilogue for all rows of the chunk at once (one lane per row: the epilogue's own global loads
-                //    overlap instead of serialising per pass)
-                for (int rr = lane; rr < nr; rr += 32) {
-                    const int a = rp[rr], b = rp[rr + 1];
-                    fn(row0 + rr, a < b ? vs[a] : 0.0);
-                }
+                // 3. the row sums of the chunk (<= 64 rows: lane l holds rows l and l + 32) move to registers ...
+                if (lane < nr) { const int a = rp[lane], b = rp[lane + 1]; sum0 = a < b ? vs[a] : 0.0; }
+                if (lane + 32 < nr) { const int a = rp[lane + 32], b = rp[lane + 33]; sum1 = a < b ? vs[a] : 0.0; }
+                epi_rows = nr;
             }
         }
         __syncwarp();  // every lane is done reading the buffer before it is overwritten
         SPROF(2);
-        // stream in the next chunk: our own, or (across the grid barrier) the first one of the next phase's matrix
+        // ... the next chunk streams in: our own, or (across the grid barrier) the first one of the next phase's matrix ...
         if (c + 1 < c1) ws.issue(A, c + 1, dn);
         else if (next && nx_c < nx_c1) ws.issue(*next, nx_c, dn);
         else ws.cur = nullptr;
         d = dn;
         SPROF(3);
+        // ... and the epilogue (one lane per row, its own global loads in flight together) overlaps with that copy
+        if (lane < epi_rows) fn(row0 + lane, sum0);
+        if (lane + 32 < epi_rows) fn(row0 + lane + 32, sum1);
 #ifdef ABIP_PHASE_TIMING
         ++_pn;
 #endif
@@ -564,9 +502,6 @@ constexpr int kPlanSlots = 2;
 constexpr size_t kPlanOff = ((kBarOff + 8 * kWarps + 15) / 16) * 16;             // per-warp plan cache
 constexpr size_t kStageOff = ((kPlanOff + 32 * kPlanSlots * kWarps + 127) / 128) * 128;
 constexpr size_t kSmemBytes = kStageOff + (size_t)kWarps * kWarpSmemBytes;
-// ... followed by the optional page cache [slots * 256 B] (LP engine; launch with kSmemBytes + slots * 256)
-constexpr int kSmemMaxOptin = 232448 - 1024;  // 227 KB per CTA on sm_100, minus the static shared memory of the kernels
-constexpr int kPcSlotsMax = (kSmemMaxOptin - (int)kSmemBytes) / (kPageDoubles * 8) < 512 ? (kSmemMaxOptin - (int)kSmemBytes) / (kPageDoubles * 8) : 512;
 __device__ __forceinline__ Reducer make_reducer(unsigned char* smem_raw, double* partials, bool batched = false) {
     vgrid_init(batched);
     const int w = threadIdx.x >> 5;
@@ -591,7 +526,6 @@ __device__ __forceinline__ Reducer make_reducer(unsigned char* smem_raw, double*
     R.ws.base_s = smem_u32(wbase);
     R.ws.cur = nullptr;
     R.ws.cur_c = 0;
-    R.ws.pc = reinterpret_cast<double*>(smem_raw + kSmemBytes);  // present only when the launch asked for it
     return R;
 }
 
@@ -805,7 +739,7 @@ struct SolveOut {
 //   b: [m+n] right-hand side, overwritten by the solution;  s: warm start [>= m] or nullptr.
 //   EPI: also reduce hdot = sol[0:m+n] . h (epilogue of project_lin_sys, src/abip.c:560); the caller must
 //   grid.sync() and R.finish<1>() to obtain it.
-// Barriers per solve: 2 + 4 per CG iteration (+1 by the caller).
+// Barriers per solve: 2 + 3 per CG iteration (+1 by the caller).
 // ---------------------------------------------------------------------------------------------------------
 template <bool EPI, bool DIST>
 __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg::grid_group& grid, CommState& cs,
@@ -879,6 +813,11 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
     double ipzr = a2[1];
     int its = 0;
     if (!(rn < fmin(tol, 1e-18))) {
+        // PCG (indirect.c:368-388) with THREE grid barriers per iteration instead of four: the epilogue of the A pass also
+        // reduces r.Gp, Gp.Gp, (Mr).Gp, (M Gp).Gp, so that |r - alpha Gp|^2 and (M r').r' -- and with them the stopping
+        // test and beta -- are known right after alpha (r' = r - alpha Gp expanded); the updates of x, r and p then run as
+        // ONE phase.  The same epilogue re-measures (M r).r and |r|^2 of the current residual, so alpha uses the exact
+        // value as in the reference and the expanded forms never accumulate.
         for (int it = 0; it < m; ++it) {
             // L1: tmp = A' p
             WARP_T0(tw1);
@@ -886,13 +825,20 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
             WARP_T1(c, tw1, 0);
             grid_sync(grid);
             PHASE_MARK(c, tl, 4);
-            // L2: Gp = A tmp + rho p ; p.Gp
-            double d1[1] = {0.0};
+            // L2: Gp = A tmp + rho p ; seven sums
+            double d[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             auto gp_epi = [&](int row, double a) {
-                const double pi = c.p[row];
+                const double pi = c.p[row], ri = c.r[row], Mi = __ldg(c.M + row);
                 const double gp = fma(c.rho_y, pi, a);
                 c.Gp[row] = gp;
-                d1[0] = fma(pi, gp, d1[0]);
+                const double zi = Mi * ri, mg = Mi * gp;
+                d[0] = fma(pi, gp, d[0]);   // p.Gp
+                d[1] = fma(zi, gp, d[1]);   // (M r).Gp
+                d[2] = fma(mg, gp, d[2]);   // (M Gp).Gp
+                d[3] = fma(ri, gp, d[3]);   // r.Gp
+                d[4] = fma(gp, gp, d[4]);   // Gp.Gp
+                d[5] = fma(zi, ri, d[5]);   // (M r).r of the current residual
+                d[6] = fma(ri, ri, d[6]);   // |r|^2 of the current residual
             };
             if constexpr (!DIST) {
                 WARP_T0(tw2);
@@ -903,34 +849,29 @@ __device__ __forceinline__ void dev_solve_lin_sys(const LpCtx& c, Reducer& R, cg
                 spmv_rows(c.A, c.tmp, R.ws, &c.AT, [&](int row, double a) { slot[row] = a; });
                 comm_sum_vec(c.comm, cs, grid, m, gp_epi);
             }
-            R.block_store<1>(d1);
+            R.block_store<7>(d);
             grid_sync(grid);
-            R.finish<1>(d1);
+            R.finish<7>(d);
             PHASE_MARK(c, tl, 5);
-            const double alpha = ipzr / d1[0];
-            // L3: x += alpha p ; r -= alpha Gp ; |r|^2 ; (M r).r
-            double d2[2] = {0.0, 0.0};
+            ipzr = d[5];
+            const double alpha = ipzr / d[0];
+            const double rr_new = fma(alpha, fma(alpha, d[4], -2.0 * d[3]), d[6]);
+            const double zr_new = fma(alpha, fma(alpha, d[2], -2.0 * d[1]), ipzr);
+            its = it + 1;
+            rn = sqrt(fmax(rr_new, 0.0));
+            const bool stop = rn < tol;
+            const double beta = zr_new / ipzr;
+            // L3 + L4: x += alpha p ; r -= alpha Gp ; p = beta p + M r
             GRID_STRIDE(i, m) {
-                by[i] = fma(alpha, c.p[i], by[i]);
+                const double pi = c.p[i];
+                by[i] = fma(alpha, pi, by[i]);
                 const double ri = fma(-alpha, c.Gp[i], c.r[i]);
                 c.r[i] = ri;
-                const double zi = __ldg(c.M + i) * ri;
-                d2[0] = fma(ri, ri, d2[0]);
-                d2[1] = fma(zi, ri, d2[1]);
+                if (!stop) c.p[i] = fma(beta, pi, __ldg(c.M + i) * ri);
             }
-            R.block_store<2>(d2);
             grid_sync(grid);
-            R.finish<2>(d2);
             PHASE_MARK(c, tl, 6);
-            its = it + 1;
-            rn = sqrt(d2[0]);
-            if (rn < tol) break;
-            const double beta = d2[1] / ipzr;
-            ipzr = d2[1];
-            // L4: p = beta p + M r
-            GRID_STRIDE(i, m) c.p[i] = fma(beta, c.p[i], __ldg(c.M + i) * c.r[i]);
-            grid_sync(grid);
-            PHASE_MARK(c, tl, 7);
+            if (stop) break;
         }
     }
     // S4: bx = -bx + A' by   (indirect.c:419-420)

@@ -709,7 +709,7 @@ __global__ void k_perm_out(const double* src_new, const int* n2o, double* dst_ol
 // Host side of the engine
 // =========================================================================================================
 #include "spmv_host.h"
-#include "sjds_host.h"
+#include "order_host.h"
 
 struct ABIPGPU_LP {
     int device = 0;
@@ -721,13 +721,11 @@ struct ABIPGPU_LP {
     int grid = 0, grid_mu = 0;  // every SpMV-bearing kernel uses the same persistent grid (the plan is per warp)
     // matrix
     int *A_ptr = nullptr, *A_idx = nullptr, *AT_ptr = nullptr, *AT_idx = nullptr, *A_wc = nullptr, *AT_wc = nullptr;
-    int *A_pcn = nullptr, *A_pcp = nullptr, *AT_pcn = nullptr, *AT_pcp = nullptr;  // page-cache plan (per CTA)
     unsigned char* arena = nullptr;              // all matrix / plan arrays live in this one allocation
     int *A_cl = nullptr, *AT_cl = nullptr;       // long-row tables
     int4 *A_lr = nullptr, *AT_lr = nullptr;
     double *A_lp = nullptr, *AT_lp = nullptr;
-    size_t smem = kSmemBytes;  // dynamic shared memory of the persistent kernels (+ page cache)
-    int pc_slots = 0;
+    size_t smem = kSmemBytes;  // dynamic shared memory of the persistent kernels
     int4 *A_chunk = nullptr, *AT_chunk = nullptr;
     double *A_val = nullptr, *AT_val = nullptr;
     // everything else lives in one slab
@@ -1166,14 +1164,9 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     {
         int g1, g2, g3, g4;
         int h1, h2, h3;
-        // page cache of the gathered vectors: whole-device engines only (batch engines share the SMs)
-        e->pc_slots = (t_grid_request > 0 || t_batch) ? 0 : std::max(0, std::min(env_int("ABIP_GPU_PC_SLOTS", kPcSlotsMax), kPcSlotsMax));
-#if !ABIP_PAGE_CACHE
-        e->pc_slots = 0;
-#endif
-        e->smem = kSmemBytes + (size_t)e->pc_slots * kPageDoubles * sizeof(double);
+        e->smem = kSmemBytes;
         bool cached = false;
-        if (e->pc_slots == 0) {
+        {
             std::lock_guard<std::mutex> lk(g_devinfo_mu);
             if (di.g_main > 0) {
                 g1 = g2 = g3 = h1 = h2 = h3 = di.g_main;
@@ -1194,7 +1187,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         CK(cudaFuncSetAttribute((const void*)k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
         e->grid = std::min(g1, std::min(g2, g3));
         e->grid_mu = g4;
-        if (!cached && e->pc_slots == 0) {
+        if (!cached) {
             std::lock_guard<std::mutex> lk(g_devinfo_mu);
             di.g_main = e->grid;
             di.g_mu = e->grid_mu;
@@ -1209,15 +1202,8 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     }
     const int W = e->grid * kWarps;
     SpmvPlan planA, planAT;
-    build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA);
-    build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT);
-    PageCache pcA, pcAT;
-    {
-        const int min_refs = std::max(1, env_int("ABIP_GPU_PC_MINREFS", 4));
-        build_page_cache(planA, e_a_idx, n, e->grid, e->pc_slots, min_refs, &pcA);
-        build_page_cache(planAT, e_at_idx, m, e->grid, e->pc_slots, min_refs, &pcAT);
-    }
-
+    build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data());
+    build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data());
     // One device arena for all matrix and plan arrays: packed on the host (zero padding of kPad elements behind every
     // array included) and uploaded with ONE allocation and ONE copy -- 14 arrays x (malloc + memset + copy) were a
     // third of the driver calls of an engine set-up, which is what limits a batch of small LPs.
@@ -1239,8 +1225,6 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     const size_t o_atval = scale_out ? put(nullptr, nnz * sizeof(double), sizeof(double)) : put_vec(at_val);
     const size_t o_awc = put_vec(planA.warp_chunk), o_atwc = put_vec(planAT.warp_chunk);
     const size_t o_ach = put_vec(planA.chunk), o_atch = put_vec(planAT.chunk);
-    const size_t o_apcn = put_vec(pcA.npages), o_apcp = put_vec(pcA.pages);
-    const size_t o_atpcn = put_vec(pcAT.npages), o_atpcp = put_vec(pcAT.pages);
     size_t o_acl = 0, o_alr = 0, o_alp = 0, o_atcl = 0, o_atlr = 0, o_atlp = 0;
     if (planA.n_long) {
         o_acl = put_vec(planA.cta_long);
@@ -1270,8 +1254,6 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     e->AT_ptr = (int*)(ab + o_atptr); e->AT_idx = (int*)(ab + o_atidx); e->AT_val = (double*)(ab + o_atval);
     e->A_wc = (int*)(ab + o_awc); e->AT_wc = (int*)(ab + o_atwc);
     e->A_chunk = (int4*)(ab + o_ach); e->AT_chunk = (int4*)(ab + o_atch);
-    e->A_pcn = (int*)(ab + o_apcn); e->A_pcp = (int*)(ab + o_apcp);
-    e->AT_pcn = (int*)(ab + o_atpcn); e->AT_pcp = (int*)(ab + o_atpcp);
     if (planA.n_long) { e->A_cl = (int*)(ab + o_acl); e->A_lr = (int4*)(ab + o_alr); e->A_lp = (double*)(ab + o_alp); }
     if (planAT.n_long) { e->AT_cl = (int*)(ab + o_atcl); e->AT_lr = (int4*)(ab + o_atlr); e->AT_lp = (double*)(ab + o_atlp); }
     const int gmax = std::max(e->grid, e->grid_mu);
@@ -1325,9 +1307,9 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     c.m = (int)m;
     c.n = (int)n;
     c.A = Csr{e->A_ptr, e->A_idx, e->A_val, (int)m, e->A_wc, e->A_chunk, planA.lanes_log2,
-              (int)n, pcA.stride, e->pc_slots > 0 ? e->A_pcn : nullptr, e->A_pcp, e->A_cl, e->A_lr, e->A_lp, 1};
+              e->A_cl, e->A_lr, e->A_lp, 1};
     c.AT = Csr{e->AT_ptr, e->AT_idx, e->AT_val, (int)n, e->AT_wc, e->AT_chunk, planAT.lanes_log2,
-               (int)m, pcAT.stride, e->pc_slots > 0 ? e->AT_pcn : nullptr, e->AT_pcp, e->AT_cl, e->AT_lr, e->AT_lp, 2};
+               e->AT_cl, e->AT_lr, e->AT_lp, 2};
     c.M = e->dM;
     c.D = nullptr;
     c.E = nullptr;
@@ -1347,6 +1329,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     c.sc = e->dsc;
     memset(&c.comm, 0, sizeof(c.comm));
     c.comm.G = 1;
+
 #ifdef ABIP_PHASE_TIMING
     c.phase_ns = e->dphase;
 #else
@@ -1418,11 +1401,10 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     snprintf(e->desc, sizeof(e->desc),
              "device %d (%s, %d SMs) persistent grid %d x %d threads, %zu B smem/block | CSR(A): %d rows, mean %.1f max %d "
              "nnz/row, %zu chunks (%d long rows), %d lane(s)/row | CSR(A'): %d rows, mean %.1f max %d, %zu chunks (%d long), "
-             "%d lane(s)/row | nnz=%ld | locality ordering %s (%.0f ms) | page cache %d x 256 B per CTA: %.1f%% of the gathers of A, %.1f%% of A' from shared memory",
+             "%d lane(s)/row | nnz=%ld | locality ordering %s (%.0f ms)",
              device, prop.name, e->num_sms, e->grid, kBlock, (size_t)e->smem, (int)m, planA.mean, planA.max_len,
              planA.chunk.size(), planA.n_long, 1 << planA.lanes_log2, (int)n, planAT.mean, planAT.max_len,
-             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, reorder ? "on" : "off", e->order_ms, e->pc_slots, 100.0 * pcA.hits / nnz,
-             100.0 * pcAT.hits / nnz);
+             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, reorder ? "on" : "off", e->order_ms);
     return 0;
 }
 

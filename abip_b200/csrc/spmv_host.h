@@ -66,10 +66,55 @@ struct SpmvPlan {
     int max_len = 0;
 };
 
-static inline void build_spmv_plan(const std::vector<int>& ptr, int nrows, int W, const char* env_lanes, SpmvPlan* P) {
+// Cost of a row for the balance of the CTAs: nnz + 2 (stream + row overhead) + kLineCost per 128-byte line of the gathered
+// vector that the row is the first of its neighbourhood (~ one chunk) to touch.  A gather costs L1 tag look-ups and L2
+// sectors per distinct line, not per element: after the locality ordering a chunk of 20 structurally identical rows
+// touches ~25 lines, a piece of a long random row ~220 -- measured 16.5 vs 34 us per pass for CTAs holding the same
+// number of nonzeros; the weight was then tuned on the whole solve (profiles/r02_spmv.md: 0.5-0.7 best, > 1 worse).
+constexpr double kLineCost = 0.5;
+static inline void row_line_costs(const std::vector<int>& ptr, const int* idx, int nrows, std::vector<double>* cost) {
+    cost->resize(nrows);
+    constexpr int kSet = 2048;  // open addressing, epoch-tagged: reset = epoch increment
+    std::vector<int> key(kSet, -1), tag(kSet, -1);
+    int epoch = 0, window = 0;
+    const char* wenv = getenv("ABIP_GPU_LINE_COST");  // tuning knob
+    const double w = (wenv && *wenv) ? atof(wenv) : kLineCost;
+    for (int r = 0; r < nrows; ++r) {
+        const int a = ptr[r], b = ptr[r + 1];
+        int fresh = 0;
+        if (b - a > kChunk) {
+            fresh = b - a;  // long rows: every piece is a chunk of its own, assume no reuse
+        } else {
+            for (int k = a; k < b; ++k) {
+                const int line = idx[k] >> 4;
+                unsigned h = ((unsigned)line * 2654435761u) >> 21;  // 11 bits
+                for (;;) {
+                    if (tag[h] != epoch) { tag[h] = epoch; key[h] = line; ++fresh; break; }
+                    if (key[h] == line) break;
+                    h = (h + 1) & (kSet - 1);
+                }
+            }
+            window += b - a;
+            if (window >= kChunk) { window = 0; ++epoch; }
+        }
+        (*cost)[r] = (double)(b - a) + 2.0 + w * fresh;
+    }
+}
+
+static inline void build_spmv_plan(const std::vector<int>& ptr, int nrows, int W, const char* env_lanes, SpmvPlan* P,
+                                   const int* idx = nullptr) {
     const long nnz = ptr[nrows];
     const int G = std::max(1, W / kWarps);
-    const double total_cost = (double)nnz + 2.0 * nrows;
+    // prefix of the row costs (contiguous ranges, deal == 0)
+    std::vector<double> cum(nrows + 1, 0.0);
+    if (idx && G > 1) {
+        std::vector<double> rc;
+        row_line_costs(ptr, idx, nrows, &rc);
+        for (int r = 0; r < nrows; ++r) cum[r + 1] = cum[r] + rc[r];
+    } else {
+        for (int r = 0; r < nrows; ++r) cum[r + 1] = (double)ptr[r + 1] + 2.0 * (r + 1);
+    }
+    const double total_cost = cum[nrows];
     P->warp_chunk.assign(W + 1, 0);
     P->chunk.clear();
     P->cta_long.assign(G + 1, 0);
@@ -77,13 +122,76 @@ static inline void build_spmv_plan(const std::vector<int>& ptr, int nrows, int W
     P->n_pieces = 0;
     P->n_long = 0;
     P->max_len = 0;
-    // ABIP_GPU_PLAN_DEAL=0 (default): contiguous, cost-balanced row range per CTA (keeps the L1 locality of
-    // neighbouring rows); =1: chunks are dealt round-robin over the CTAs of the grid, so every CTA gets the same mix of
-    // row kinds.  Measured at cfg2 (profiles/r01_spmv_variants.md): 156.4 vs 150.1 ADMM it/s.
-    const bool deal = env_int("ABIP_GPU_PLAN_DEAL", 0) != 0;
+    // ABIP_GPU_PLAN_DEAL: how rows are assigned to the CTAs of the persistent grid.
+    //   0 (default): contiguous range of rows per CTA, balanced by the locality-aware row costs above;
+    //   2: long rows go to the least-loaded CTA, longest first (they have no locality); the chunks of the
+    //      short rows are dealt in groups of kDealGroup consecutive chunks, each group to the least-loaded CTA -- every
+    //      CTA gets the same mix of row kinds (phase time = slowest CTA; with contiguous ranges the CTAs that held the
+    //      long rows took 2x the mean after the locality ordering), all CTAs walk through the matrix region by region,
+    //      and neighbouring rows still share a CTA (L1 reuse of the gathered lines) -- measured slower at cfg2: the random
+    //      gathers of the long rows then disturb the L1 reuse of the structured rows in EVERY CTA (mean busy time per
+    //      pass 25.5 -> 33.6 us);
+    //   1: single chunks dealt round-robin over the CTAs.
+    // Measured at cfg2: profiles/r01_spmv_variants.md, profiles/r02_spmv.md.
+    const int deal = env_int("ABIP_GPU_PLAN_DEAL", 0);
     std::vector<std::vector<int4>> cta_units(G);
     std::vector<std::vector<int4>> cta_lr(G);
-    {
+    auto emit_long = [&](int owner, int q) {
+        const int len0 = ptr[q + 1] - ptr[q];
+        const int np = (len0 + kChunk - 1) / kChunk;
+        const int per = (len0 + np - 1) / np;
+        cta_lr[owner].push_back(make_int4(q, 0, np, 0));
+        for (int i = 0, off = 0; i < np; ++i, off += per)
+            cta_units[owner].push_back(make_int4(q, ptr[q] + off, -i - 1, std::min(per, len0 - off)));
+        P->n_long++;
+    };
+    if (deal == 2) {
+        constexpr int kDealGroup = 4;
+        const long rounds = std::max(1L, (nnz + (long)W * kChunk - 1) / ((long)W * kChunk));
+        const int want = (int)std::min<long>(kChunk, std::max<long>(32, (nnz + rounds * W - 1) / (rounds * W)));
+        std::vector<double> load(G, 0.0);
+        auto least = [&]() {
+            int bb = 0;
+            for (int b = 1; b < G; ++b)
+                if (load[b] < load[bb]) bb = b;
+            return bb;
+        };
+        std::vector<int> longs;
+        for (int q = 0; q < nrows; ++q)
+            if (ptr[q + 1] - ptr[q] > kChunk) longs.push_back(q);
+        std::stable_sort(longs.begin(), longs.end(), [&](int x, int y) { return ptr[x + 1] - ptr[x] > ptr[y + 1] - ptr[y]; });
+        for (int q : longs) {
+            const int b = least();
+            emit_long(b, q);
+            load[b] += 1.25 * (ptr[q + 1] - ptr[q]) + 64.0;
+        }
+        std::vector<int4> grp;
+        double grp_cost = 0;
+        auto flush = [&]() {
+            if (grp.empty()) return;
+            const int b = least();
+            for (const int4& u : grp) cta_units[b].push_back(u);
+            load[b] += grp_cost;
+            grp.clear();
+            grp_cost = 0;
+        };
+        int q = 0;
+        while (q < nrows) {
+            if (ptr[q + 1] - ptr[q] > kChunk) { ++q; continue; }
+            int q1 = q, n = 0;
+            while (q1 < nrows && (q1 - q) < kChunkRows && n < want) {
+                const int len = ptr[q1 + 1] - ptr[q1];
+                if (len > kChunk || n + len > kChunk) break;
+                n += len;
+                ++q1;
+            }
+            grp.push_back(make_int4(q, ptr[q], q1 - q, n));
+            grp_cost += n + 2.0 * (q1 - q) + 48.0;
+            if ((int)grp.size() == kDealGroup) flush();
+            q = q1;
+        }
+        flush();
+    } else {
         const long rounds = std::max(1L, (nnz + (long)W * kChunk - 1) / ((long)W * kChunk));
         const int want_all = (int)std::min<long>(kChunk, std::max<long>(32, (nnz + rounds * W - 1) / (rounds * W)));
         int r = 0;
@@ -95,7 +203,7 @@ static inline void build_spmv_plan(const std::vector<int>& ptr, int nrows, int W
                 r = nrows;
             } else {
                 const double target = total_cost * (double)(b + 1) / (double)G;
-                while (r < nrows && ((double)ptr[r + 1] + 2.0 * (r + 1) <= target || b == G - 1)) ++r;
+                while (r < nrows && (cum[r + 1] <= target || b == G - 1)) ++r;
                 const long nnz_cta = (long)ptr[r] - ptr[ra];
                 const long rc = std::max(1L, (nnz_cta + (long)kWarps * kChunk - 1) / ((long)kWarps * kChunk));
                 want = (int)std::min<long>(kChunk, std::max<long>(32, (nnz_cta + rc * kWarps - 1) / (rc * kWarps)));
@@ -106,12 +214,7 @@ static inline void build_spmv_plan(const std::vector<int>& ptr, int nrows, int W
                 ++group;
                 const int len0 = ptr[q + 1] - ptr[q];
                 if (len0 > kChunk) {  // long row: equal pieces, all in one CTA
-                    const int np = (len0 + kChunk - 1) / kChunk;
-                    const int per = (len0 + np - 1) / np;
-                    cta_lr[owner].push_back(make_int4(q, 0, np, 0));
-                    for (int i = 0, off = 0; i < np; ++i, off += per)
-                        cta_units[owner].push_back(make_int4(q, ptr[q] + off, -i - 1, std::min(per, len0 - off)));
-                    P->n_long++;
+                    emit_long(owner, q);
                     ++q;
                     continue;
                 }
@@ -162,63 +265,6 @@ static inline void build_spmv_plan(const std::vector<int>& ptr, int nrows, int W
 }
 
 
-// Page cache plan (see kPageLog2 in lp_device.cuh): for every CTA of the persistent grid count the references of
-// its slice of the matrix to each 256-byte page of the gathered vector, keep the `slots` most referenced pages with
-// at least `min_refs` references (a page costs two coalesced wavefronts to load and saves about one wavefront per
-// reference), and re-encode the column indices of the slice that fall into a kept page as kPcFlag | (slot * 32 +
-// offset).  Deterministic: ties are broken by page id.
-struct PageCache {
-    std::vector<int> npages;  // [G]
-    std::vector<int> pages;   // [G * stride]
-    int stride = 0;
-    long hits = 0;            // nonzeros whose gather goes to shared memory
-};
-
-static inline void build_page_cache(const SpmvPlan& P, std::vector<int>& idx, long ncols, int G, int slots, int min_refs,
-                                    PageCache* out) {
-    out->stride = slots;
-    out->npages.assign(G, 0);
-    out->pages.assign((size_t)G * slots, 0);
-    out->hits = 0;
-    if (slots <= 0) return;
-    const long npg = (ncols + kPageDoubles - 1) >> kPageLog2;
-    std::vector<int> cnt(npg, 0), slot_of(npg, -1), touched;
-    std::vector<std::pair<int, int>> cand;  // (-count, page)
-    for (int b = 0; b < G; ++b) {
-        const int c0 = P.warp_chunk[(size_t)b * kWarps], c1 = P.warp_chunk[(size_t)(b + 1) * kWarps];
-        if (c0 >= c1) continue;
-        touched.clear();
-        for (int c = c0; c < c1; ++c)
-            for (long k = P.chunk[c].y, e = k + P.chunk[c].w; k < e; ++k) {
-                const int pg = idx[k] >> kPageLog2;
-                if (cnt[pg]++ == 0) touched.push_back(pg);
-            }
-        cand.clear();
-        for (int pg : touched)
-            if (cnt[pg] >= min_refs) cand.emplace_back(-cnt[pg], pg);
-        if ((int)cand.size() > slots) {
-            std::nth_element(cand.begin(), cand.begin() + slots, cand.end());
-            cand.resize(slots);
-        }
-        std::sort(cand.begin(), cand.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b2) { return a.second < b2.second; });
-        int* pl = out->pages.data() + (size_t)b * slots;
-        for (size_t i = 0; i < cand.size(); ++i) {
-            pl[i] = cand[i].second;
-            slot_of[cand[i].second] = (int)i;
-        }
-        out->npages[b] = (int)cand.size();
-        for (int c = c0; c < c1; ++c)
-            for (long k = P.chunk[c].y, e = k + P.chunk[c].w; k < e; ++k) {
-                const int col = idx[k], sl = slot_of[col >> kPageLog2];
-                if (sl >= 0) {
-                    idx[k] = (int)(kPcFlag | (unsigned)((sl << kPageLog2) | (col & (kPageDoubles - 1))));
-                    out->hits++;
-                }
-            }
-        for (int pg : touched) { cnt[pg] = 0; slot_of[pg] = -1; }
-    }
-}
-
 // device copy of a CSR matrix + its plan
 struct DevCsr {
     int *ptr = nullptr, *idx = nullptr, *wc = nullptr, *cta_long = nullptr;
@@ -228,7 +274,7 @@ struct DevCsr {
     int nrows = 0;
     long nnz = 0;
     Csr view() const {
-        return Csr{ptr, idx, val, nrows, wc, chunk, plan.lanes_log2, 0, 0, nullptr, nullptr, cta_long, long_rows, long_part, 0};
+        return Csr{ptr, idx, val, nrows, wc, chunk, plan.lanes_log2, cta_long, long_rows, long_part, 0};
     }
     void release(cudaStream_t s = nullptr) {
         dev_free(ptr, s); dev_free(idx, s); dev_free(wc, s); dev_free(chunk, s); dev_free(val, s);

@@ -31,7 +31,7 @@ if hasattr(L, 'abipgpu_lp_phase_times'):
     out = np.zeros(32)
     L.abipgpu_lp_phase_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
     L.abipgpu_lp_phase_times(e.e, out.ctypes.data_as(C.POINTER(C.c_double)), 0)
-    names = ['rhs', 'rhsB', 'S1(A+AT)', 'S2(A)', 'L1(AT)', 'L2(A)', 'L3(upd)', 'L4(p)', 'S4(AT)', 'prox', 'qnorm']
+    names = ['rhs', 'rhsB', 'S1(A+AT)', 'S2(A)', 'L1(AT)', 'L2(A)', 'L3+L4(upd)', '-', 'S4(AT)', 'prox', 'qnorm']
     if out[16:].sum() > 0:
         for i, nm in enumerate(names):
             if out[16 + i] > 0:

@@ -2,7 +2,7 @@
 // multicommodity-flow matrix, with the SJDS layout + locality ordering of abip_b200/csrc/sjds_host.h, in a persistent
 // cooperative grid.  Variants: natural / reordered matrix, cg::grid.sync / counter barrier, 4-barrier classic CG phase
 // structure / 3-barrier fused structure, unroll depth.  `--cpu` only prints the gather model (no GPU needed).
-//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -I abip_b200/csrc tools/ubench/sjds_bench.cu -o build/sjds_bench
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -I abip_b200/csrc -I tools/ubench tools/ubench/sjds_bench.cu -o build/sjds_bench
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

@@ -1,103 +1,14 @@
-// sjds_host.h -- host side of the SpMV data layout of the engine: locality ordering + sliced-JDS ("SJDS") builder.
-//
-// Why (profiles/r02_*): on B200 the FP64 gathers x[col] of a CSR SpMV are bound by the number of
-// distinct 128-byte lines one 32-lane load touches and by the 32-byte sectors they pull over the L2 -> SM path, not by
-// HBM.  Two measures, both decided at plan time (pure functions of the sparsity structure => bit-reproducible):
-//   1. locality_order(): a permutation of the rows and of the columns that makes structurally identical ("shift-copy")
-//      rows / columns neighbours -- block-replicated LPs (multi-commodity, multi-period, scenario trees) then put the
-//      copies of one row on the 32 lanes of a warp and the copies of one column at consecutive addresses, so a gather
-//      touches 2-4 lines instead of 32.  Matrices without replicated structure keep their order.
-//   2. SJDS: rows are handled one lane per row in slices of 32 consecutive rows; inside a slice the rows are sorted by
-//      length (descending) and the nonzeros are stored step-major ("jagged diagonals"): step j of the slice holds the
-//      j-th nonzero of every row that has one, packed.  Every load of values / indices is a fully coalesced 32-lane
-//      access straight from global memory (no staging through shared memory, no row-pointer array, no padding beyond
-//      the 4-element alignment of a slice), all loads of a slice are independent, and each row is summed in its own
-//      order (the serial order of the reference, linsys/common.c:624-634).
-//      Rows longer than kLongRow are cut into pieces of <= kPiece nonzeros that whole warps reduce (coalesced loads,
-//      shuffle tree); the piece sums are added in piece order.
+// sjds_host.h -- EXPERIMENT (round 2, not part of the product): sliced-JDS layout + plan for tools/ubench/sjds_bench.cu.
+// See profiles/r02_spmv.md for what was measured and why the engine keeps its CSR-stream kernel.
 #pragma once
-#include <algorithm>
-#include <cstdint>
-#include <cstring>
-#include <numeric>
-#include <vector>
+#include "order_host.h"
 
 namespace sjds {
-
-constexpr int kLongRow = 96;   // rows longer than this are "long": whole-warp pieces instead of one lane
 #ifndef ABIP_CH
 #define ABIP_CH 256
 #endif
 constexpr int kPiece = ABIP_CH;  // nonzeros per piece of a long row (one stage of the device ring)
 constexpr int kSkipLane = 0xff;  // meta high byte: this lane of the slice has no row (padding or long row)
-
-static inline uint64_t mix64(uint64_t x) {
-    x += 0x9e3779b97f4a7c15ull;
-    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
-    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
-    return x ^ (x >> 31);
-}
-
-// stable order of 0..n-1 by (group representative = smallest member index of the element's key class, index)
-static inline void order_by_class(const std::vector<uint64_t>& key, std::vector<int>* new2old) {
-    const int n = (int)key.size();
-    std::vector<int> ord(n);
-    std::iota(ord.begin(), ord.end(), 0);
-    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return key[a] < key[b]; });
-    std::vector<int> rep(n);
-    for (int i = 0; i < n;) {
-        int j = i;
-        while (j < n && key[ord[j]] == key[ord[i]]) ++j;
-        for (int q = i; q < j; ++q) rep[ord[q]] = ord[i];  // ord is stable: ord[i] is the smallest index of the class
-        i = j;
-    }
-    new2old->resize(n);
-    std::iota(new2old->begin(), new2old->end(), 0);
-    std::stable_sort(new2old->begin(), new2old->end(), [&](int a, int b) { return rep[a] < rep[b]; });
-}
-
-// Locality ordering (see file header).  Inputs: CSR(A) (m rows) and CSR(A') (n rows), column indices ascending.
-//   a. row signature = hash(length, column differences to the first column): shift-copies of a row share it;
-//   b. column key = multiset of the signatures of its (non-dense) rows; columns with equal keys are copies of each
-//      other: classes are laid out in the order of their first member, members in index order;
-//   c. row key = multiset of the classes of its (non-dense) columns; same layout rule.
-// Dense rows / columns (longer than dense_thr) take no part in the keys and keep their relative place.
-static inline void locality_order(int m, int n, const std::vector<int>& a_ptr, const std::vector<int>& a_idx,
-                                  const std::vector<int>& at_ptr, const std::vector<int>& at_idx, int dense_thr,
-                                  std::vector<int>* row_new2old, std::vector<int>* col_new2old) {
-    std::vector<uint64_t> rsig(m), ckey(n), rkey(m);
-    for (int r = 0; r < m; ++r) {
-        const int a = a_ptr[r], b = a_ptr[r + 1];
-        if (b - a > dense_thr || b == a) { rsig[r] = 0; continue; }
-        uint64_t h = mix64((uint64_t)(b - a));
-        for (int k = a + 1; k < b; ++k) h = mix64(h ^ (uint64_t)(uint32_t)(a_idx[k] - a_idx[a]));
-        rsig[r] = h | 1ull;
-    }
-    for (int c = 0; c < n; ++c) {
-        const int a = at_ptr[c], b = at_ptr[c + 1];
-        if (b - a > dense_thr) { ckey[c] = mix64(0xc0ffeeull + (uint64_t)c); continue; }
-        uint64_t h = 0;
-        int cnt = 0;
-        for (int k = a; k < b; ++k) {
-            const uint64_t s = rsig[at_idx[k]];
-            if (s) { h += mix64(s); ++cnt; }
-        }
-        ckey[c] = mix64(h ^ ((uint64_t)cnt << 56));
-    }
-    order_by_class(ckey, col_new2old);
-    // class id of a column = its key (collisions only merge classes, which is harmless)
-    for (int r = 0; r < m; ++r) {
-        const int a = a_ptr[r], b = a_ptr[r + 1];
-        if (b - a > dense_thr) { rkey[r] = mix64(0xabcdefull + (uint64_t)r); continue; }
-        uint64_t h = 0;
-        for (int k = a; k < b; ++k) {
-            const int c = a_idx[k];
-            if (at_ptr[c + 1] - at_ptr[c] <= dense_thr) h += mix64(ckey[c]);
-        }
-        rkey[r] = mix64(h ^ ((uint64_t)(b - a) << 56));
-    }
-    order_by_class(rkey, row_new2old);
-}
 
 // B = P_r A P_c in CSR: row i of B is row row_new2old[i] of A, column indices mapped through col_old2new; entries of a
 // row keep the order of A (its summation order does not change).
