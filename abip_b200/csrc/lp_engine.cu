@@ -741,6 +741,7 @@ struct ABIPGPU_LP {
     bool permuted = false;                   // locality ordering active: engine index space != caller's
     int *d_rn2o = nullptr, *d_cn2o = nullptr, *d_pl = nullptr;  // new -> old maps: rows [m], columns [n], whole l-space
     double order_ms = 0;
+    double setup_ms[8] = {0};             // host set-up laps: transpose, ordering, permuted CSR, plans, upload, scaling, rest
     double* hsc = nullptr;                   // pinned host scalar block
     bool have_scaling = false;
     LpCtx ctx;
@@ -1083,36 +1084,68 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         CK(cudaEventCreate(&e->ev_solve1));
     }
 
+    auto lap_t = std::chrono::steady_clock::now();
+    auto lap = [&](int slot) {
+        const auto t = std::chrono::steady_clock::now();
+        e->setup_ms[slot] += std::chrono::duration<double, std::milli>(t - lap_t).count();
+        lap_t = t;
+    };
     // CSR(A') is the caller's CSC; CSR(A) by counting sort (the reference's transpose(), indirect.c:81-139);
     // perm[q] = position in the CSC arrays of entry q of CSR(A)
+    const int host_threads = (nnz < 200000 || t_batch) ? 1 : std::max(1, std::min(env_int("ABIP_GPU_HOST_THREADS", 8), (int)std::thread::hardware_concurrency()));
+    auto par = [&](long cnt, auto fn) { parallel_for(cnt, host_threads, fn); };
     std::vector<int> at_ptr(n + 1), at_idx(nnz), a_ptr(m + 1, 0), a_idx(nnz), perm(nnz);
     for (long j = 0; j <= n; ++j) at_ptr[j] = (int)Ap[j];
-    for (long k = 0; k < nnz; ++k) {
-        if (Ai[k] < 0 || Ai[k] >= m) {
-            fprintf(stderr, "[abip_gpu] row index out of range\n");
-            return -1;
-        }
-        at_idx[k] = (int)Ai[k];
-        a_ptr[Ai[k] + 1]++;
-    }
-    for (long i = 0; i < m; ++i) a_ptr[i + 1] += a_ptr[i];
     {
-        std::vector<int> fill(a_ptr.begin(), a_ptr.end() - 1);
-        for (long j = 0; j < n; ++j)
-            for (long k = Ap[j]; k < Ap[j + 1]; ++k) {
-                const int q = fill[Ai[k]]++;
-                a_idx[q] = (int)j;
-                perm[q] = (int)k;
+        // every thread takes a range of columns: counts per row first, then fills its entries behind those of the
+        // threads before it, so that every row lists its columns in ascending order whatever the thread count
+        std::vector<std::vector<int>> cnt(host_threads);
+        std::vector<int> bad(host_threads, 0);
+        par(n, [&](long j0, long j1, int t) {
+            std::vector<int>& c = cnt[t];
+            c.assign(m, 0);
+            for (long k = Ap[j0]; k < Ap[j1]; ++k) {
+                const long r = Ai[k];
+                if (r < 0 || r >= m) { bad[t] = 1; return; }
+                at_idx[k] = (int)r;
+                c[r]++;
             }
+        });
+        for (int t = 0; t < host_threads; ++t)
+            if (bad[t]) {
+                fprintf(stderr, "[abip_gpu] row index out of range\n");
+                return -1;
+            }
+        for (long i = 0; i < m; ++i) {
+            int tot = 0;
+            for (int t = 0; t < host_threads; ++t) {
+                if (cnt[t].empty()) continue;  // (fewer ranges than threads)
+                const int c = cnt[t][i];
+                cnt[t][i] = tot;
+                tot += c;
+            }
+            a_ptr[i + 1] = a_ptr[i] + tot;
+        }
+        par(n, [&](long j0, long j1, int t) {
+            std::vector<int>& off = cnt[t];
+            for (long j = j0; j < j1; ++j)
+                for (long k = Ap[j]; k < Ap[j + 1]; ++k) {
+                    const int r = at_idx[k];
+                    const int q = a_ptr[r] + off[r]++;
+                    a_idx[q] = (int)j;
+                    perm[q] = (int)k;
+                }
+        });
     }
     // Locality ordering (sjds_host.h): whole-device engines work in a permuted index space in which structurally
     // identical rows / columns are neighbours, so the 32 lanes of a gather touch a few lines instead of 32.
     // e_* : the engine's matrices; e_a_src / e_at_src: position of every entry in the caller's CSC arrays.
+    lap(0);
     std::vector<int> row_n2o, col_n2o;
     bool reorder = env_int("ABIP_GPU_REORDER", 1) != 0 && t_order_request != 0 && !t_batch && t_grid_request == 0;
     if (reorder) {
         const auto t_o0 = std::chrono::steady_clock::now();
-        sjds::locality_order((int)m, (int)n, a_ptr, a_idx, at_ptr, at_idx, sjds::kLongRow, &row_n2o, &col_n2o);
+        sjds::locality_order((int)m, (int)n, a_ptr, a_idx, at_ptr, at_idx, sjds::kLongRow, &row_n2o, &col_n2o, par);
         bool ident = true;
         for (long i = 0; i < m && ident; ++i) ident = row_n2o[i] == i;
         for (long j = 0; j < n && ident; ++j) ident = col_n2o[j] == j;
@@ -1120,6 +1153,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         e->order_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_o0).count();
     }
     e->permuted = reorder;
+    lap(1);
     std::vector<int> e_a_ptr, e_a_idx, e_a_src, e_at_ptr, e_at_idx, e_at_src;
     if (reorder) {
         std::vector<int> row_o2n(m), col_o2n(n);
@@ -1129,24 +1163,28 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         e_a_idx.resize(nnz);
         e_a_src.resize(nnz);
         for (long i = 0; i < m; ++i) e_a_ptr[i + 1] = e_a_ptr[i] + (a_ptr[row_n2o[i] + 1] - a_ptr[row_n2o[i]]);
-        for (long i = 0; i < m; ++i) {
-            int q = e_a_ptr[i];
-            for (int k = a_ptr[row_n2o[i]]; k < a_ptr[row_n2o[i] + 1]; ++k, ++q) {
-                e_a_idx[q] = col_o2n[a_idx[k]];
-                e_a_src[q] = perm[k];
+        par(m, [&](long i0, long i1, int) {
+            for (long i = i0; i < i1; ++i) {
+                int q = e_a_ptr[i];
+                for (int k = a_ptr[row_n2o[i]]; k < a_ptr[row_n2o[i] + 1]; ++k, ++q) {
+                    e_a_idx[q] = col_o2n[a_idx[k]];
+                    e_a_src[q] = perm[k];
+                }
             }
-        }
+        });
         e_at_ptr.assign(n + 1, 0);
         e_at_idx.resize(nnz);
         e_at_src.resize(nnz);
         for (long j = 0; j < n; ++j) e_at_ptr[j + 1] = e_at_ptr[j] + (at_ptr[col_n2o[j] + 1] - at_ptr[col_n2o[j]]);
-        for (long j = 0; j < n; ++j) {
-            int q = e_at_ptr[j];
-            for (int k = at_ptr[col_n2o[j]]; k < at_ptr[col_n2o[j] + 1]; ++k, ++q) {
-                e_at_idx[q] = row_o2n[at_idx[k]];
-                e_at_src[q] = k;
+        par(n, [&](long j0, long j1, int) {
+            for (long j = j0; j < j1; ++j) {
+                int q = e_at_ptr[j];
+                for (int k = at_ptr[col_n2o[j]]; k < at_ptr[col_n2o[j] + 1]; ++k, ++q) {
+                    e_at_idx[q] = row_o2n[at_idx[k]];
+                    e_at_src[q] = k;
+                }
             }
-        }
+        });
     } else {
         e_a_ptr = a_ptr;
         e_a_idx = a_idx;
@@ -1156,10 +1194,13 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     }
     std::vector<double> a_val(scale_out ? 0 : nnz), at_val(scale_out ? 0 : nnz);
     if (!scale_out) {
-        for (long q = 0; q < nnz; ++q) a_val[q] = Ax[e_a_src[q]];
-        if (reorder) for (long q = 0; q < nnz; ++q) at_val[q] = Ax[e_at_src[q]];
-        else memcpy(at_val.data(), Ax, sizeof(double) * nnz);
+        par(nnz, [&](long q0, long q1, int) {
+            for (long q = q0; q < q1; ++q) a_val[q] = Ax[e_a_src[q]];
+            if (reorder) for (long q = q0; q < q1; ++q) at_val[q] = Ax[e_at_src[q]];
+            else memcpy(at_val.data() + q0, Ax + q0, sizeof(double) * (q1 - q0));
+        });
     }
+    lap(2);
     // persistent grid: a multiple of the SM count, common to all SpMV-bearing kernels
     {
         int g1, g2, g3, g4;
@@ -1202,8 +1243,15 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     }
     const int W = e->grid * kWarps;
     SpmvPlan planA, planAT;
-    build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data());
-    build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data());
+    if (host_threads > 1) {
+        std::thread tp([&] { build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data()); });
+        build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data());
+        tp.join();
+    } else {
+        build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data());
+        build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data());
+    }
+    lap(3);
     // One device arena for all matrix and plan arrays: packed on the host (zero padding of kPad elements behind every
     // array included) and uploaded with ONE allocation and ONE copy -- 14 arrays x (malloc + memset + copy) were a
     // third of the driver calls of an engine set-up, which is what limits a batch of small LPs.
@@ -1336,6 +1384,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     c.phase_ns = nullptr;
 #endif
 
+    lap(4);
     if (scale_out) {
         // equilibrate in the CALLER's order (bit-identical D, E to abip_normalize_A) on temporary copies of the original
         // structure, then gather the scaled values into the engine's two matrices
@@ -1391,9 +1440,11 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         dev_free(d_val, e->stream); dev_free(d_asrc, e->stream); dev_free(d_atsrc, e->stream);
         e->stats.d2h_bytes += 8.0 * 2 * (m + n);
     }
+    lap(5);
     k_precond<<<(unsigned)((m + 255) / 256), 256, 0, e->stream>>>(c.A, e->dM);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
+    lap(6);
 
     const double V = 8, I = 4;
     e->B_A = (double)nnz * (V + I) + (m + 1.0) * I + n * V + m * V;
@@ -1401,10 +1452,10 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     snprintf(e->desc, sizeof(e->desc),
              "device %d (%s, %d SMs) persistent grid %d x %d threads, %zu B smem/block | CSR(A): %d rows, mean %.1f max %d "
              "nnz/row, %zu chunks (%d long rows), %d lane(s)/row | CSR(A'): %d rows, mean %.1f max %d, %zu chunks (%d long), "
-             "%d lane(s)/row | nnz=%ld | locality ordering %s (%.0f ms)",
+             "%d lane(s)/row | nnz=%ld | locality ordering %s | set-up ms: transpose %.0f, ordering %.0f, permuted CSR %.0f, grid+plans %.0f, arena+upload %.0f, scaling %.0f, precond %.0f",
              device, prop.name, e->num_sms, e->grid, kBlock, (size_t)e->smem, (int)m, planA.mean, planA.max_len,
              planA.chunk.size(), planA.n_long, 1 << planA.lanes_log2, (int)n, planAT.mean, planAT.max_len,
-             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, reorder ? "on" : "off", e->order_ms);
+             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, reorder ? "on" : "off", e->setup_ms[0], e->setup_ms[1], e->setup_ms[2], e->setup_ms[3], e->setup_ms[4], e->setup_ms[5], e->setup_ms[6]);
     return 0;
 }
 

@@ -25,22 +25,28 @@ static inline uint64_t mix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-// stable order of 0..n-1 by (group representative = smallest member index of the element's key class, index)
+// stable order of 0..n-1 by (group representative = smallest member index of the element's key class, index).
+// O(n): the representative of a class is its first occurrence (open-addressing table key -> first index), the final
+// order is a counting sort by representative.
 static inline void order_by_class(const std::vector<uint64_t>& key, std::vector<int>* new2old) {
     const int n = (int)key.size();
-    std::vector<int> ord(n);
-    std::iota(ord.begin(), ord.end(), 0);
-    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return key[a] < key[b]; });
-    std::vector<int> rep(n);
-    for (int i = 0; i < n;) {
-        int j = i;
-        while (j < n && key[ord[j]] == key[ord[i]]) ++j;
-        for (int q = i; q < j; ++q) rep[ord[q]] = ord[i];  // ord is stable: ord[i] is the smallest index of the class
-        i = j;
+    size_t cap = 16;
+    while (cap < (size_t)n * 2) cap <<= 1;
+    std::vector<int> slot(cap, -1);
+    std::vector<int> rep(n), cnt(n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        size_t h = (size_t)(mix64(key[i]) & (cap - 1));
+        for (;;) {
+            const int j = slot[h];
+            if (j < 0) { slot[h] = i; rep[i] = i; break; }
+            if (key[j] == key[i]) { rep[i] = j; break; }
+            h = (h + 1) & (cap - 1);
+        }
+        cnt[rep[i] + 1]++;
     }
+    for (int i = 0; i < n; ++i) cnt[i + 1] += cnt[i];
     new2old->resize(n);
-    std::iota(new2old->begin(), new2old->end(), 0);
-    std::stable_sort(new2old->begin(), new2old->end(), [&](int a, int b) { return rep[a] < rep[b]; });
+    for (int i = 0; i < n; ++i) (*new2old)[cnt[rep[i]]++] = i;
 }
 
 // Locality ordering (see file header).  Inputs: CSR(A) (m rows) and CSR(A') (n rows), column indices ascending.
@@ -49,18 +55,22 @@ static inline void order_by_class(const std::vector<uint64_t>& key, std::vector<
 //      other: classes are laid out in the order of their first member, members in index order;
 //   c. row key = multiset of the classes of its (non-dense) columns; same layout rule.
 // Dense rows / columns (longer than dense_thr) take no part in the keys and keep their relative place.
+template <class ParFor>
 static inline void locality_order(int m, int n, const std::vector<int>& a_ptr, const std::vector<int>& a_idx,
                                   const std::vector<int>& at_ptr, const std::vector<int>& at_idx, int dense_thr,
-                                  std::vector<int>* row_new2old, std::vector<int>* col_new2old) {
+                                  std::vector<int>* row_new2old, std::vector<int>* col_new2old, ParFor par) {
     std::vector<uint64_t> rsig(m), ckey(n), rkey(m);
-    for (int r = 0; r < m; ++r) {
+    par(m, [&](long r0, long r1, int) {
+    for (long r = r0; r < r1; ++r) {
         const int a = a_ptr[r], b = a_ptr[r + 1];
         if (b - a > dense_thr || b == a) { rsig[r] = 0; continue; }
         uint64_t h = mix64((uint64_t)(b - a));
         for (int k = a + 1; k < b; ++k) h = mix64(h ^ (uint64_t)(uint32_t)(a_idx[k] - a_idx[a]));
         rsig[r] = h | 1ull;
     }
-    for (int c = 0; c < n; ++c) {
+    });
+    par(n, [&](long c0, long c1, int) {
+    for (long c = c0; c < c1; ++c) {
         const int a = at_ptr[c], b = at_ptr[c + 1];
         if (b - a > dense_thr) { ckey[c] = mix64(0xc0ffeeull + (uint64_t)c); continue; }
         uint64_t h = 0;
@@ -71,9 +81,11 @@ static inline void locality_order(int m, int n, const std::vector<int>& a_ptr, c
         }
         ckey[c] = mix64(h ^ ((uint64_t)cnt << 56));
     }
+    });
     order_by_class(ckey, col_new2old);
     // class id of a column = its key (collisions only merge classes, which is harmless)
-    for (int r = 0; r < m; ++r) {
+    par(m, [&](long r0, long r1, int) {
+    for (long r = r0; r < r1; ++r) {
         const int a = a_ptr[r], b = a_ptr[r + 1];
         if (b - a > dense_thr) { rkey[r] = mix64(0xabcdefull + (uint64_t)r); continue; }
         uint64_t h = 0;
@@ -83,6 +95,7 @@ static inline void locality_order(int m, int n, const std::vector<int>& a_ptr, c
         }
         rkey[r] = mix64(h ^ ((uint64_t)(b - a) << 56));
     }
+    });
     order_by_class(rkey, row_new2old);
 }
 

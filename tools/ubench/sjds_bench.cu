@@ -269,7 +269,7 @@ int main(int argc, char** argv) {
         std::vector<int> rn2o(m), cn2o(n);
         for (int i = 0; i < m; ++i) rn2o[i] = i;
         for (int j = 0; j < n; ++j) cn2o[j] = j;
-        if (reorder) sjds::locality_order(m, n, a_ptr, a_idx, at_ptr, at_idx, sjds::kLongRow, &rn2o, &cn2o);
+        if (reorder) sjds::locality_order(m, n, a_ptr, a_idx, at_ptr, at_idx, sjds::kLongRow, &rn2o, &cn2o, [](long nn, auto fn) { fn(0L, nn, 0); });
         std::vector<int> ro2n(m), co2n(n);
         for (int i = 0; i < m; ++i) ro2n[rn2o[i]] = i;
         for (int j = 0; j < n; ++j) co2n[cn2o[j]] = j;
