@@ -1,15 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- ADMM iterations/sec and time-to-1e-4 of the ABIP-LP hot path (BASELINE.json metric).
+"""bench.py -- ADMM iterations/sec and time-to-1e-4 of the ABIP hot path (BASELINE.json metric), all five configs.
 
-  python bench.py --gpus N --steps K --warmup W              # our arm (GPU engine)
-  python bench.py --impl reference --gpus N --steps K --warmup W   # reference's own C solver on the host cores
+  python bench.py --gpus N --steps K --warmup W                       # our arm (GPU engine)
+  python bench.py --impl reference --gpus N --steps K --warmup W      # the reference's own C solver on the host cores
 
-A "step" is one complete solve to eps = 1e-4 of one synthetic LP of BASELINE.json configs[1]
-(m=200k, n=1M, nnz=5M, multicommodity-flow structure).  `value` times abip_gpu_solve with A, b, c already
-resident in HBM (abip_gpu_init done before the timed region); `e2e` times the reference-facing entry
-abip_gpu_main (init + solve + finish) from HOST buffers, i.e. including equilibration, CSR build, all H2D
-copies and the D2H of x, y, s.  For N > 1 each rank solves its own instance (independent LPs sharded one per
-GPU, no data-path collective): weak scaling.
+Headline (`metric`, `value`, `e2e`, `roofline`): BASELINE.json configs[1], "cfg2" -- one complete solve to eps = 1e-4 of
+the synthetic multicommodity-flow LP m=200k, n=1M, nnz=5M per step.  `value` times abip_gpu_solve with A, b, c resident in
+HBM (CUDA events); `e2e` times the reference-facing entry abip_gpu_main (init + solve + finish) from HOST buffers, i.e.
+CSR build, ordering, H2D copies, device equilibration, solve and the D2H of x, y, s.  For N > 1 every rank solves the
+SAME instance (replicas; weak scaling, no data-path collective).
+
+Further blocks of the same JSON line (BASELINE.json configs[2..4]; each measured with CUDA events / device-synchronised
+host clocks, max over ranks):
+  cfg3_qcp      N = 1: ABIP-QCP, SOCP with 10k second-order cones, n=500k, nnz(A)=10M + Q          (it/s, time, roofline)
+  cfg4          m=2M n=10M nnz=60M.  N = 1: single-GPU solve; N > 1: ONE instance sharded over the N GPUs (column blocks,
+                in-kernel NVLink peer-memory exchange), with set-up time and a parity block against the single-GPU solve
+  cfg5_batch    512 independent LPs (m=500, n=2000) per GPU = 4,096 on 8 GPUs, sharded one problem set per GPU (LP/s)
+  sharded_single_instance (N > 1): cfg2 as ONE instance over the N GPUs + parity against the replica solve
+The reference arm runs a bounded sample of the cfg2 solve with all host threads (OMP_NUM_THREADS set explicitly).
 """
 from __future__ import annotations
 
@@ -34,10 +42,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=float(os.environ.get("ABIP_BENCH_SCALE", "1.0")),
-                    help="shrink cfg2 (debug only; the reported config is scale=1)")
+                    help="shrink every config (debug only; the reported configs are scale=1)")
     ap.add_argument("--eps", type=float, default=1e-4)
-    ap.add_argument("--cpu-sample-iters", type=int, default=4)
+    ap.add_argument("--cpu-sample-iters", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", default=os.environ.get("ABIP_BENCH_ONLY", ""),
+                    help="comma list of extra blocks to run (cfg3,cfg4,cfg5,sharded); default: all")
     return ap.parse_args()
 
 
@@ -49,8 +59,9 @@ def peaks():
 
 
 def ncu_traffic():
-    """DRAM bytes of one k_admm_iter launch from the committed ncu --set full capture (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r01_k_admm_iter_ncu_v2.txt")
+    """DRAM bytes of one k_bb_round launch, from the committed `ncu --set full` capture of the shipped build (profiles/):
+    a constant taken from that capture, NOT a measurement of this run."""
+    path = os.path.join(ROOT, "profiles", "r02_k_bb_round_ncu.txt")
     if not os.path.exists(path):
         return None
     rd = wr = None
@@ -62,8 +73,8 @@ def ncu_traffic():
     if rd is None or wr is None:
         return None
     return {"dram_bytes_per_launch": rd + wr,
-            "note": "ncu --set full capture of one k_admm_iter launch with 26 CG iterations (~5.0 GB algorithmic), "
-                    "profiles/r01_k_admm_iter_ncu_v2.txt"}
+            "note": "from profiles/r02_k_bb_round_ncu.txt: ncu --set full of ONE k_bb_round launch of the shipped build "
+                    "(two solves, 47 CG iterations, ~10.4 GB algorithmic); not re-measured in this run"}
 
 
 class ClockSampler:
@@ -115,68 +126,100 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload(args, rank):
+def workload(args):
     from abip_b200 import problems
-    p = problems.cfg2(seed=2 + rank, scale=args.scale)
+    p = problems.cfg2(seed=2, scale=args.scale)
     name = (f"cfg2: ABIP-LP synthetic multicommodity-flow LP m={p.m} n={p.n} nnz={p.nnz}, eps={args.eps:g}"
             + ("" if args.scale == 1.0 else f" (DEBUG scale={args.scale})"))
     return p, name
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baselines (the only places that execute oracle/)
+# ---------------------------------------------------------------------------------------------------------------
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        return os.cpu_count() or 1
+
+
 def _ref_kind():
-    """Prefer the OpenMP build of the reference (only the SpMV loop is parallel, linsys/common.c:620-622)."""
+    """Prefer the OpenMP build of the reference (only the SpMV loop is parallel, linsys/common.c:620-622).  torchrun
+    exports OMP_NUM_THREADS=1: the thread count is set EXPLICITLY here (environment before the library is loaded, and
+    omp_set_num_threads afterwards)."""
+    cores = _host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     from oracle import ref_lp
-    cores = os.cpu_count() or 1
     if ref_lp.available("indirect_omp"):
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-        return "indirect_omp", int(os.environ["OMP_NUM_THREADS"]), "reference indirect.c + OpenMP SpMV"
+        try:
+            import ctypes
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(cores))
+        except Exception:  # noqa: BLE001
+            pass
+        return "indirect_omp", cores, "reference indirect.c + OpenMP SpMV"
     if ref_lp.available("indirect"):
         return "indirect", 1, "reference indirect.c, single thread as shipped"
     return None, 0, "oracle/_ref not built"
 
 
-def _ref_sample(args, p, which):
-    """Bounded sample of the cfg2 solve on the host cores: the first `cpu_sample_iters` ADMM iterations, with the
-    Barzilai-Borwein searches that run between them (early iterations use the loosest CG tolerance, so this
-    over-states the CPU's average iteration rate)."""
-    from oracle import ref_lp
-    # the reference's C code prints progress lines to stdout ("Done the pc rescaling!"): keep stdout to the one JSON
-    # line of the contract by pointing fd 1 at stderr while it runs
+def _quiet(fn):
+    """The reference's C code prints progress lines to stdout: keep stdout to the one JSON line of the contract."""
     sys.stdout.flush()
     saved = os.dup(1)
     os.dup2(2, 1)
     try:
-        return ref_lp.solve(p, which=which, eps=args.eps, max_admm_iters=args.cpu_sample_iters + 1)
+        return fn()
     finally:
+        sys.stdout.flush()
         os.dup2(saved, 1)
         os.close(saved)
 
 
+def _ref_sample(args, p, which, iters):
+    """Bounded sample of the cfg2 solve on the host cores: the first `iters` ADMM iterations with the Barzilai-Borwein
+    searches that run between them.  The complete solve (196 ADMM iterations) is pinned by
+    tests/golden/lp_golden_large.json["cfg2_full"] (451 s on 6 threads of the build container = 0.43 it/s)."""
+    from oracle import ref_lp
+    return _quiet(lambda: ref_lp.solve(p, which=which, eps=args.eps, max_admm_iters=iters + 1))
+
+
+def _full_solve_fixture():
+    try:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "lp_golden_large.json")))["cfg2_full"]
+        return {"admm_iter": g["admm_iter"], "solve_time_s": g["solve_time_ms"] / 1e3, "threads": g.get("threads"),
+                "iter_per_s": g["admm_iter"] / (g["solve_time_ms"] / 1e3),
+                "note": "complete reference solve of this workload, run once in the build container (tests/golden/make_golden_large.py)"}
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation (oracle/_ref, compiled unmodified from its sources)
-    with all the host threads it can use.  Rank 0 only."""
+    """Reference arm: the reference's own CPU implementation (oracle/_ref, compiled unmodified from its sources) with all
+    the host threads it can use.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     which, cores, desc = _ref_kind()
     if which is None:
         print(json.dumps({"impl": "reference", "unavailable": desc}))
         return
-    p, name = workload(args, 0)
+    p, name = workload(args)
     its_total, ms_total, per_step = 0, 0.0, []
     for step in range(args.warmup + args.steps):
-        r = _ref_sample(args, p, which)
+        r = _ref_sample(args, p, which, 1 if step < args.warmup else args.cpu_sample_iters)
         if step >= args.warmup:
             its_total += r["admm_iter"]
             ms_total += r["solve_time_ms"]
             per_step.append(r["solve_time_ms"])
     value = its_total / (ms_total / 1e3)
-    sample = (f"first {args.cpu_sample_iters} ADMM iterations (incl. BB searches) of the cfg2 solve per step; {desc}; "
-              f"{cores} thread(s)")
+    sample = (f"first {args.cpu_sample_iters} ADMM iterations (incl. BB searches) of the cfg2 solve per step "
+              f"(warm-up steps: 1 iteration); {desc}; {cores} thread(s)")
     line = {"impl": "reference", "metric": "ADMM iters/sec", "value": value, "unit": "iter/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(per_step)),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": name},
-            "cpu_baseline": {"value": value, "unit": "iter/s", "cores": cores, "kind": "reference", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "iter/s", "cores": cores, "kind": "reference", "sample": sample,
+                             "full_solve_fixture": _full_solve_fixture()},
             "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -186,19 +229,70 @@ def cpu_baseline(args, p):
     if which is None:
         return {"value": None, "unit": "iter/s", "cores": 0, "kind": "reference", "sample": desc}
     try:
-        r = _ref_sample(args, p, which)
+        r = _ref_sample(args, p, which, args.cpu_sample_iters)
         return {"value": r["admm_iter"] / (r["solve_time_ms"] / 1e3), "unit": "iter/s", "cores": cores,
                 "kind": "reference",
                 "sample": f"first {args.cpu_sample_iters} ADMM iterations (incl. BB searches) of the same cfg2 solve; "
-                          f"{desc}; {r['solve_time_ms'] / 1e3:.1f} s of CPU work"}
+                          f"{desc}; {r['solve_time_ms'] / 1e3:.1f} s of CPU work",
+                "full_solve_fixture": _full_solve_fixture()}
     except Exception as ex:  # noqa: BLE001
         return {"value": None, "unit": "iter/s", "cores": cores, "kind": "reference", "sample": f"failed: {ex}"}
 
 
+def _cfg5_ref_one(seed):
+    from abip_b200 import problems
+    from oracle import ref_lp
+    p = problems.random_lp(500, 2000, 5, seed=seed, name="cfg5")
+    r = ref_lp.solve(p, which="indirect", eps=1e-4)
+    return r["admm_iter"]
+
+
+def cfg5_cpu_baseline(count):
+    """the reference looped over the problems, one process per core"""
+    import multiprocessing as mp
+    cores = _host_cores()
+    n = max(cores, min(count, 4 * cores))
+    try:
+        def run_pool():  # fork INSIDE the redirection: the children inherit stderr as their fd 1
+            ctx = mp.get_context("fork")
+            with ctx.Pool(cores) as pool:
+                t0 = time.perf_counter()
+                pool.map(_cfg5_ref_one, [5000 + i for i in range(n)])
+                return time.perf_counter() - t0
+        dt = _quiet(run_pool)
+        return {"value": n / dt, "unit": "LP/s", "cores": cores, "kind": "reference",
+                "sample": f"{n} of the cfg5 problems, reference ABIP(main) looped, one process per core"}
+    except Exception as ex:  # noqa: BLE001
+        return {"value": None, "unit": "LP/s", "cores": cores, "kind": "reference", "sample": f"failed: {ex}"}
+
+
+def cfg3_cpu_baseline(args):
+    """reference direct path (QDLDL; its PCG path does not run) at the largest scale the factorisation
+    survives in seconds"""
+    try:
+        from abip_b200 import problems
+        from oracle import ref_qcp
+        sc = 0.01 * min(1.0, args.scale)
+        q = problems.cfg3(scale=sc)
+        t0 = time.perf_counter()
+        r = _quiet(lambda: ref_qcp.solve(q, eps_p=args.eps, eps_d=args.eps, eps_g=args.eps))
+        dt = time.perf_counter() - t0
+        st = r.get("solve_time_ms", dt * 1e3) / 1e3
+        return {"value": r["admm_iter"] / max(st, 1e-9), "unit": "iter/s", "cores": 1, "kind": "reference",
+                "sample": f"cfg3 at scale {sc:g} (n={q.n}, nnz(A)={q.A.nnz}): reference abip() with linsys_solver=1 (QDLDL), "
+                          f"{r['admm_iter']} ADMM iterations, set-up {r.get('setup_time_ms', 0) / 1e3:.1f} s + solve {st:.2f} s; "
+                          "the full size does not factor in reasonable time"}
+    except Exception as ex:  # noqa: BLE001
+        return {"value": None, "unit": "iter/s", "cores": 1, "kind": "reference", "sample": f"failed: {ex}"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from abip_b200 import LpSolver, lp_solve
+    from abip_b200 import LpSolver, lp_solve, problems
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,17 +302,33 @@ def run_ours(args):
     torch.cuda.set_device(local)
     os.environ["ABIP_GPU_DEVICE"] = str(local)
     dev = torch.device("cuda", local)
+    only = set(x for x in args.only.split(",") if x) or {"cfg3", "cfg4", "cfg5", "sharded"}
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    p, name = workload(args, rank)
+    def allmax(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item()
+
+    def allsum(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t[0].item()
+
+    p, name = workload(args)
     A = p.csc()
     params = dict(tol=args.eps, verbose=0)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    # ---- cfg2, device-resident -------------------------------------------------------------------------------
     solver = LpSolver(A, params)
     for _ in range(args.warmup):
         solver.solve(p.b, p.c)
@@ -228,7 +338,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     its = 0
-    solve_ms, event_ms, per_step = 0.0, 0.0, []
+    event_ms, per_step = 0.0, []
     agg = {}
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -236,7 +346,6 @@ def run_ours(args):
         torch.cuda.synchronize()
         x, y, s, info = solver.solve(p.b, p.c)
         its += info["admm_iter"]
-        solve_ms += info["solve_time_ms"]
         event_ms += info["stats"]["solve_event_ms"]
         per_step.append(info["stats"]["solve_event_ms"])
         for k, v in info["stats"].items():
@@ -245,93 +354,203 @@ def run_ours(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     last = info
+    x_single, pobj_single, its_single = x.copy(), info["pobj"], info["admm_iter"]
     solver.close()
 
-    # end-to-end through the reference-facing entry with host buffers (init + solve + finish per step)
+    # ---- cfg2, end to end through the reference-facing entry with host buffers -------------------------------
     del flush
     torch.cuda.empty_cache()
     barrier()
     e2e_its, e2e_s, h2d, d2h = 0, 0.0, 0.0, 0.0
     lp_solve(A, p.b, p.c, params)  # untimed warm-up of this code path
-    for _ in range(max(1, min(args.steps, 2))):
+    n_e2e = max(1, min(args.steps, 3))
+    for _ in range(n_e2e):
         t1 = time.perf_counter()
         x, y, s, inf2 = lp_solve(A, p.b, p.c, params, want_stats=True)
         e2e_s += time.perf_counter() - t1
         e2e_its += inf2["admm_iter"]
-        h2d = inf2["stats"]["h2d_bytes"] + 12.0 * p.nnz * 2 + 4.0 * (p.m + p.n + 2)  # + CSR(A), CSR(A') uploads
+        h2d = inf2["stats"]["h2d_bytes"] + 12.0 * p.nnz * 2 + 4.0 * (p.m + p.n + 2)  # + CSR(A), CSR(A') uploads (init)
         d2h = inf2["stats"]["d2h_bytes"]
     barrier()
+    event_ms_max, its_all = allmax(event_ms), allsum(its)
+    e2e_max, e2e_its_all = allmax(e2e_s), allsum(e2e_its)
 
-    # N > 1: the same workload as ONE instance sharded over the GPUs (column blocks of A, in-kernel NVLink
-    # peer-memory all-reduce; abip_b200/dist.py) -- strong scaling, reported beside the weak-scaling value
-    sharded = None
-    if world > 1:
+    extra = {}
+
+    def guarded(key, fn):
+        try:
+            extra[key] = fn()
+        except Exception as ex:  # noqa: BLE001
+            extra[key] = {"error": f"{type(ex).__name__}: {ex}"}
+        barrier()
+
+    # ---- N > 1: cfg2 as ONE instance sharded over the GPUs ----------------------------------------------------
+    def block_sharded(pp, label, x_ref, pobj_ref, its_ref):
         from abip_b200.dist import LpSolverDist
-        from abip_b200 import problems as _pb
-        p0 = _pb.cfg2(seed=2, scale=args.scale)
-        ds = LpSolverDist(p0.csc(), params)
-        ds.solve(p0.b, p0.c)  # warm-up
+        barrier()
+        t_s = time.perf_counter()
+        ds = LpSolverDist(pp.csc(), params)
+        torch.cuda.synchronize()
+        setup_s = allmax(time.perf_counter() - t_s)
+        ds.solve(pp.b, pp.c)  # warm-up
         barrier()
         sh_ms, sh_its = 0.0, 0
-        for _ in range(args.steps):
-            xs, ys, ss, si = ds.solve(p0.b, p0.c)
+        nst = max(1, min(args.steps, 3))
+        for _ in range(nst):
+            xs, ys, ss, si = ds.solve(pp.b, pp.c)
             sh_ms += si["stats"]["solve_event_ms"]
             sh_its += si["admm_iter"]
         barrier()
         ds.close()
-        tsh = torch.tensor([sh_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tsh, op=dist.ReduceOp.MAX)
-        sharded = {"workload": "cfg2 as ONE instance, column blocks of A over %d GPUs" % world,
-                   "value": sh_its / (tsh[0].item() / 1e3), "unit": "iter/s", "scaling": "strong",
-                   "time_to_1e-4_s": tsh[0].item() / args.steps / 1e3, "status": si["status"],
-                   "admm_iter_per_solve": sh_its / args.steps,
-                   "collective": "in-kernel peer-memory sum of the m-vector A_g x_g + scalar blocks (no NCCL in the solve)"}
+        sh_ms = allmax(sh_ms)
+        out = {"workload": f"{label} as ONE instance, column blocks of A over {world} GPUs",
+               "value": sh_its / (sh_ms / 1e3), "unit": "iter/s", "scaling": "strong",
+               "time_to_1e-4_s": sh_ms / nst / 1e3, "setup_s": setup_s, "status": si["status"],
+               "admm_iter_per_solve": sh_its / nst,
+               "collective": "in-kernel peer-memory sum of the m-vector A_g x_g + scalar blocks (no NCCL in the solve)"}
+        if x_ref is not None:
+            out["parity"] = {"against": "single-GPU engine, same instance, same run",
+                             "admm_iter_equal": bool(si["admm_iter"] == its_ref),
+                             "admm_iter": [int(si["admm_iter"]), int(its_ref)],
+                             "pobj_rel": float(abs(si["pobj"] - pobj_ref) / (abs(pobj_ref) + 1e-300)),
+                             "x_rel": float(np.max(np.abs(xs - x_ref)) / (np.max(np.abs(x_ref)) + 1e-300))}
+        return out
 
-    # max over ranks of the device-timed region; whole-job iterations
-    t = torch.tensor([event_ms, float(its), e2e_s, float(e2e_its)], dtype=torch.float64, device=dev)
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        event_ms_max, its_all, e2e_max, e2e_its_all = tmax[0].item(), tsum[1].item(), tmax[2].item(), tsum[3].item()
-    else:
-        event_ms_max, its_all, e2e_max, e2e_its_all = event_ms, float(its), e2e_s, float(e2e_its)
+    if world > 1 and "sharded" in only:
+        guarded("sharded_single_instance", lambda: block_sharded(p, "cfg2", x_single, pobj_single, its_single))
+
+    # ---- cfg4: m=2M n=10M nnz=60M ------------------------------------------------------------------------------
+    def block_cfg4():
+        p4 = problems.cfg4(seed=4, scale=args.scale)
+        A4 = p4.csc()
+        t_s = time.perf_counter()
+        s4 = LpSolver(A4, params)
+        torch.cuda.synchronize()
+        setup1 = time.perf_counter() - t_s
+        x4, y4, ss4, i4 = s4.solve(p4.b, p4.c)
+        ms1, it1 = i4["stats"]["solve_event_ms"], i4["admm_iter"]
+        achieved = i4["stats"]["alg_bytes"] / (ms1 * 1e-3) / 1e9
+        s4.close()
+        out = {"workload": f"cfg4: ABIP-LP synthetic multicommodity-flow LP m={p4.m} n={p4.n} nnz={p4.nnz}, eps={args.eps:g}",
+               "single_gpu": {"value": it1 / (ms1 / 1e3), "unit": "iter/s", "time_to_1e-4_s": ms1 / 1e3, "setup_s": setup1,
+                              "status": i4["status"], "admm_iter": it1, "pres": i4["pres"], "dres": i4["dres"], "gap": i4["gap"],
+                              "achieved_GBps": achieved, "roofline_frac": achieved / peaks()[0]}}
+        if world > 1:
+            sh = block_sharded(p4, "cfg4", x4, i4["pobj"], it1)
+            sh["speedup_vs_single_gpu"] = (ms1 / 1e3) / sh["time_to_1e-4_s"]
+            out["sharded"] = sh
+        return out
+
+    if "cfg4" in only:
+        guarded("cfg4", block_cfg4)
+
+    # ---- cfg5: 512 LPs per GPU ---------------------------------------------------------------------------------
+    def block_cfg5():
+        from abip_b200 import lp_solve_batch
+        per_gpu = max(8, int(round(512 * min(1.0, args.scale))))
+        probs = [problems.random_lp(500, 2000, 5, seed=5000 + rank * per_gpu + i, name=f"cfg5_lp_{rank * per_gpu + i}")
+                 for i in range(per_gpu)]
+        lp_solve_batch(probs[:32], dict(tol=args.eps, verbose=0), concurrency=32)  # warm-up
+        barrier()
+        t_b = time.perf_counter()
+        res = lp_solve_batch(probs, dict(tol=args.eps, verbose=0), concurrency=min(per_gpu, 296))
+        torch.cuda.synchronize()
+        dt = allmax(time.perf_counter() - t_b)
+        solved = allsum(sum(1 for r in res if r[3]["status"] == "Solved"))
+        out = {"workload": f"cfg5: {per_gpu} independent LPs m=500 n=2000 per GPU ({per_gpu * world} in total), eps={args.eps:g}",
+               "value": per_gpu * world / dt, "unit": "LP/s", "scaling": "weak", "wall_s": dt, "solved": int(solved),
+               "total": per_gpu * world, "timing": "host clock around abip_gpu_batch_main (set-up, H2D, solves, D2H), max over ranks"}
+        try:  # parity of a slice against the reference's own results (fixture: first 64 problems)
+            gold = json.load(open(os.path.join(ROOT, "tests", "golden", "cfg5_golden.json")))
+            if rank == 0:
+                nchk = min(len(gold), per_gpu)
+                bad = sum(1 for g, r in zip(gold[:nchk], res[:nchk])
+                          if r[3]["status"] != g["status"] or abs(r[3]["admm_iter"] - g["admm_iter"]) > max(2, 0.05 * g["admm_iter"])
+                          or abs(float(probs[gold.index(g)].c @ r[0]) - g["pobj"]) > 1e-6 * abs(g["pobj"]) + 2e-8)
+                out["parity"] = {"against": "tests/golden/cfg5_golden.json (compiled reference)", "checked": nchk, "mismatches": bad}
+        except Exception as ex:  # noqa: BLE001
+            out["parity"] = {"error": str(ex)}
+        if rank == 0 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cfg5_cpu_baseline(per_gpu)
+        return out
+
+    if "cfg5" in only:
+        guarded("cfg5_batch", block_cfg5)
+
+    # ---- cfg3: ABIP-QCP (N = 1) --------------------------------------------------------------------------------
+    def block_cfg3():
+        from abip_b200.qcp import qcp_solve_raw
+        q = problems.cfg3(seed=3, scale=args.scale)
+        kw = dict(eps_p=args.eps, eps_d=args.eps, eps_g=args.eps, verbose=0)
+        qcp_solve_raw(q.A, q.Q, q.b, q.c, q.K, **kw)  # warm-up
+        tq = time.perf_counter()
+        xq, yq, sq, iq = qcp_solve_raw(q.A, q.Q, q.b, q.c, q.K, **kw)
+        e2e_q = time.perf_counter() - tq
+        class _V:  # counters of the last solve (abip_qcp_gpu_last_counters, read by qcp_solve_raw)
+            def __init__(self, v):
+                self.value = v
+        n_it, n_cg, n_in, kms = _V(iq["n_iter"]), _V(iq["n_cg"]), _V(iq["n_inner"]), _V(iq["kernel_ms"])
+        V, I = 8.0, 4.0
+        nnzA, nnzQ = q.A.nnz, (q.Q.nnz if q.Q is not None else 0)
+        B_A = nnzA * (V + I) + (q.m + 1) * I + q.n * V + q.m * V
+        B_AT = nnzA * (V + I) + (q.n + 1) * I + q.m * V + q.n * V
+        B_Q = nnzQ * (V + I) + (q.n + 1) * I + 2 * q.n * V
+        # per outer (Schur) CG iteration: A' pass + A pass + 12 m-vector passes; per inner (H^-1) CG iteration: Q pass +
+        # 12 n-vector passes; per ADMM iteration: one more (A, A', Q) triple for the convergence check
+        alg = n_cg.value * (B_A + B_AT + 12 * q.m * V) + n_in.value * (B_Q + 12 * q.n * V) + n_it.value * (B_A + B_AT + B_Q + 30 * (q.m + q.n) * V)
+        solve_s = iq["solve_time_ms"] / 1e3
+        ach = alg / max(kms.value * 1e-3, 1e-9) / 1e9
+        Qx = q.Q @ xq if q.Q is not None else 0.0
+        pres = float(np.max(np.abs(q.A @ xq - q.b)) / (1 + max(np.max(np.abs(q.A @ xq)), np.max(np.abs(q.b)))))
+        out = {"workload": f"cfg3: ABIP-QCP SOCP, {len(q.K.get('q', []))} second-order cones, n={q.n}, m={q.m}, nnz(A)={nnzA}, nnz(Q)={nnzQ}, eps={args.eps:g}",
+               "value": iq["admm_iter"] / solve_s, "unit": "iter/s", "time_to_1e-4_s": solve_s, "setup_s": iq["setup_time_ms"] / 1e3,
+               "e2e_s": e2e_q, "status": iq["status"], "admm_iter": iq["admm_iter"], "ipm_iter": iq["ipm_iter"],
+               "outer_cg_iters": n_cg.value, "inner_cg_iters": n_in.value, "pres_recomputed": pres,
+               "roofline": {"bound": "hbm", "kernel": "k_qcp_iter", "achieved": ach, "peak": peaks()[0], "unit": "GB/s",
+                            "frac": ach / peaks()[0], "kernel_ms": kms.value,
+                            "traffic": None, "note": "algorithmic bytes from the engine's CG counters (bench.py block_cfg3)"}}
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cfg3_cpu_baseline(args)
+        return out
+
+    if world == 1 and "cfg3" in only:
+        guarded("cfg3_qcp", block_cfg3)
 
     if rank == 0:
         peak, peak_src = peaks()
         admm_ms, bb_ms = agg["admm_kernel_ms"], agg["bb_kernel_ms"]
-        # dominant kernel: the persistent ADMM-iteration kernel (k_admm_iter); k_bb_round reported beside it
-        ach = agg["alg_bytes_admm"] / (admm_ms * 1e-3) / 1e9 if admm_ms > 0 else None
+        ach_admm = agg["alg_bytes_admm"] / (admm_ms * 1e-3) / 1e9 if admm_ms > 0 else None
         ach_bb = agg["alg_bytes_bb"] / (bb_ms * 1e-3) / 1e9 if bb_ms > 0 else None
         line = {
             "metric": "ADMM iters/sec", "value": its_all / (event_ms_max / 1e3), "unit": "iter/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": event_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "per_gpu": "one independent instance per GPU" if world > 1 else "single instance",
+            "config": {"workload": name,
+                       "per_gpu": "the same instance on every GPU (replicas, no collective)" if world > 1 else "single instance",
                        "l2": "256 MiB buffer written between timed steps (L2 flush); matrices (120 MB) ~ L2 size",
                        "status": last["status"], "admm_iter_per_solve": its / args.steps,
-                       "ipm_iter": last["ipm_iter"], "pres": last["pres"], "dres": last["dres"], "gap": last["gap"]},
+                       "ipm_iter": last["ipm_iter"], "pres": last["pres"], "dres": last["dres"], "gap": last["gap"],
+                       "pobj": last["pobj"]},
             "time_to_1e-4_s": event_ms_max / args.steps / 1e3,
             "host_wall_s_per_step": wall / args.steps,
             "clocks": clocks,
             "e2e": {"value": e2e_its_all / e2e_max, "unit": "iter/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "time_to_1e-4_s": e2e_max / max(1, min(args.steps, 2)),
-                    "note": "abip_gpu_main from host buffers: CSR build + H2D + device equilibration + solve + D2H of x, y, s"},
+                    "d2h_bytes_per_step": d2h, "time_to_1e-4_s": e2e_max / n_e2e,
+                    "note": "abip_gpu_main from host buffers: CSR build + ordering + H2D + device equilibration + solve + D2H of x, y, s"},
             "gpu_launches": int(agg["n_kernel_launches"]),
-            "roofline": {"bound": "hbm", "kernel": "k_admm_iter", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
-                         "launches": int(agg["n_admm_launch"]), "avg_launch_ms": admm_ms / max(1, agg["n_admm_launch"]),
-                         "k_bb_round": {"achieved": ach_bb, "frac": (ach_bb / peak) if ach_bb else None,
-                                        "launches": int(agg["n_bb_launch"]),
-                                        "avg_launch_ms": bb_ms / max(1, agg["n_bb_launch"])},
+            # dominant kernel: k_bb_round (one Barzilai-Borwein lookback round = two solves), ~82 % of the step
+            "roofline": {"bound": "hbm", "kernel": "k_bb_round", "achieved": ach_bb, "peak": peak, "unit": "GB/s",
+                         "frac": (ach_bb / peak) if ach_bb else None, "traffic": None, "peak_source": peak_src,
+                         "launches": int(agg["n_bb_launch"]), "avg_launch_ms": bb_ms / max(1, agg["n_bb_launch"]),
+                         "k_admm_iter": {"achieved": ach_admm, "frac": (ach_admm / peak) if ach_admm else None,
+                                         "launches": int(agg["n_admm_launch"]),
+                                         "avg_launch_ms": admm_ms / max(1, agg["n_admm_launch"])},
                          "share_of_step": {"k_admm_iter": admm_ms / event_ms, "k_bb_round": bb_ms / event_ms}},
             "counters": {"cg_iters": int(agg["n_cg_iters"]), "solves": int(agg["n_solves"]),
                          "spmv_A": int(agg["n_spmv_A"]), "spmv_AT": int(agg["n_spmv_AT"])},
         }
-        if sharded is not None:
-            line["sharded_single_instance"] = sharded
+        line.update(extra)
         tr = ncu_traffic()
         if tr is not None:
             line["roofline"]["traffic"] = tr["dram_bytes_per_launch"]

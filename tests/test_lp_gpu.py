@@ -354,3 +354,50 @@ def test_batch_of_small_lps_matches_oracle(mode):
         assert abs(info["admm_iter"] - o.admm_iter) <= max(2, 0.05 * o.admm_iter)
         assert abs(info["pobj"] - o.pobj) <= 1e-6 * (1 + abs(o.pobj))
         _check_solution(p, x, y, s, info, 1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Benchmark-scale parity: fixtures produced by the compiled reference, OpenMP build
+# (tests/golden/make_golden_large.py): cfg2 at scale 0.1 / 0.25 / 1.0 (the bench workload, 5.0 M nonzeros, 196 ADMM
+# iterations), cfg4 at scale 0.05, and the first 64 problems of cfg5 through the batch executor.
+# ---------------------------------------------------------------------------------------------------------
+GOLD_LARGE = os.path.join(os.path.dirname(__file__), "golden", "lp_golden_large.json")
+GOLD_CFG5 = os.path.join(os.path.dirname(__file__), "golden", "cfg5_golden.json")
+LARGE_CASES = {
+    "cfg2_scale0.1": lambda: problems.cfg2(scale=0.1),
+    "cfg2_scale0.25": lambda: problems.cfg2(scale=0.25),
+    "cfg4_scale0.05": lambda: problems.cfg4(scale=0.05),
+    "cfg2_full": lambda: problems.cfg2(scale=1.0),
+}
+
+
+@pytest.mark.parametrize("name", list(LARGE_CASES))
+def test_benchmark_scale_against_reference_golden(name):
+    g = json.load(open(GOLD_LARGE))[name]
+    p = LARGE_CASES[name]()
+    assert (p.m, p.n, p.nnz) == (g["m"], g["n"], g["nnz"])
+    x, y, s, info = lp_solve(p.csc(), p.b, p.c, dict(tol=1e-4, verbose=0))
+    assert info["status"] == g["status"]
+    assert info["ipm_iter"] == g["ipm_iter"]
+    assert abs(info["admm_iter"] - g["admm_iter"]) <= 0.05 * g["admm_iter"], (info["admm_iter"], g["admm_iter"])
+    assert abs(info["pobj"] - g["pobj"]) <= 1e-6 * abs(g["pobj"]) + 2e-8, (info["pobj"], g["pobj"])
+    assert max(info["pres"], info["dres"], info["gap"]) < 1e-4
+    assert rel(x[:16], np.array(g["x_head"])) < 1e-3 and rel(y[:16], np.array(g["y_head"])) < 1e-3
+    assert abs(np.linalg.norm(x) - g["x_norm"]) < 1e-4 * g["x_norm"]
+    _check_solution(p, x, y, s, info, 1e-4)
+
+
+def test_cfg5_batch_slice_against_reference_golden():
+    """64 problems of BASELINE.json configs[4] through abip_gpu_batch_main (lock-step executor), each against the
+    reference's own result: status, ADMM iterations within 5 %, objective 1e-6."""
+    from abip_b200 import lp_solve_batch
+    gold = json.load(open(GOLD_CFG5))
+    probs = problems.cfg5_batch(len(gold))
+    res = lp_solve_batch(probs, dict(tol=1e-4, verbose=0), concurrency=64, ctas_per_problem=1)
+    assert len(res) == len(gold)
+    for p, g, (x, y, s, info) in zip(probs, gold, res):
+        assert info["status"] == g["status"], (p.name, info["status"], g["status"])
+        assert abs(info["admm_iter"] - g["admm_iter"]) <= max(2, 0.05 * g["admm_iter"]), (p.name, info["admm_iter"], g["admm_iter"])
+        pobj = float(p.c @ x)
+        assert abs(pobj - g["pobj"]) <= 1e-6 * abs(g["pobj"]) + 2e-8, (p.name, pobj, g["pobj"])
+        assert abs(np.linalg.norm(x) - g["x_norm"]) < 1e-3 * g["x_norm"]
