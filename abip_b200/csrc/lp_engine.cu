@@ -1036,6 +1036,103 @@ struct DevInfo {
 static std::mutex g_devinfo_mu;
 static DevInfo g_devinfo[64];
 
+
+// CSR(A') is the caller's CSC; CSR(A) by counting sort (the reference's transpose(), indirect.c:81-139);
+// perm[q] = position in the CSC arrays of entry q of CSR(A).  Every thread takes a range of columns: counts per row
+// first, then fills its entries behind those of the threads before it, so that every row lists its columns in ascending
+// order whatever the thread count.
+// Equilibration sweeps on the device (kernels above) in the CALLER's order: d_val = CSC values (in: A, out: scaled A),
+// dD [m], dE [n] accumulate the factors; Dt [m] and rn [max(m, n)] are scratch.  Bit-identical to abip_normalize_A.
+static int run_equilibration(cudaStream_t st, int m, int n, long nnz, const int* d_atptr, const int* d_atidx, const int* d_aptr,
+                             const int* d_perm, double* d_val, double* dD, double* dE, double* Dt, double* rn,
+                             const ABIPSettings* stgs, double* mean_row, double* mean_col) {
+    const double min_row = 1e-3 * sqrt((double)n), max_row = 1e3 * sqrt((double)n);
+    const double min_col = 1e-3 * sqrt((double)m), max_col = 1e3 * sqrt((double)m);
+    const unsigned gm = (unsigned)((m + 255) / 256), gn = (unsigned)((n + 255) / 256), gz = (unsigned)((nnz + 255) / 256);
+    k_fill<<<gm, 256, 0, st>>>(dD, m, 1.0);
+    k_fill<<<gn, 256, 0, st>>>(dE, n, 1.0);
+    auto sweep = [&](int kind) {
+        k_eq_cols<<<gn, 256, 0, st>>>(kind, d_atptr, d_val, n, dE, min_col, max_col);
+        k_eq_rows<<<gm, 256, 0, st>>>(kind, d_aptr, d_perm, d_val, m, Dt, dD, min_row, max_row);
+        k_eq_apply_rows<<<gz, 256, 0, st>>>(d_atidx, d_val, nnz, Dt);
+    };
+    if (stgs->pc_ruiz_rescale) sweep(0);
+    if (stgs->origin_rescale) sweep(1);
+    if (stgs->pc_ruiz_rescale)
+        for (abip_int it = 0; it < stgs->ruiz_iter; ++it) sweep(2);
+    if (stgs->qp_rescale) sweep(3);
+    // mean row / column norms (summed on the host in index order, like common.c:541-557)
+    std::vector<double> hn(std::max(m, n));
+    k_eq_row_norms<<<gm, 256, 0, st>>>(d_aptr, d_perm, d_val, m, rn);
+    CK(cudaMemcpyAsync(hn.data(), rn, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    double mr = 0.0;
+    for (int i = 0; i < m; ++i) mr += hn[i];
+    k_eq_col_norms<<<gn, 256, 0, st>>>(d_atptr, d_val, n, rn);
+    CK(cudaMemcpyAsync(hn.data(), rn, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    double mc = 0.0;
+    for (int j = 0; j < n; ++j) mc += hn[j];
+    *mean_row = mr;
+    *mean_col = mc;
+    if (stgs->scale != 1) k_scale_all<<<gz, 256, 0, st>>>(d_val, nnz, stgs->scale);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int transpose_csc(abip_int m, abip_int n, const abip_int* Ap, const abip_int* Ai, int host_threads, std::vector<int>* at_ptr_,
+                         std::vector<int>* at_idx_, std::vector<int>* a_ptr_, std::vector<int>* a_idx_, std::vector<int>* perm_) {
+    const long nnz = Ap[n];
+    std::vector<int>&at_ptr = *at_ptr_, &at_idx = *at_idx_, &a_ptr = *a_ptr_, &a_idx = *a_idx_, &perm = *perm_;
+    at_ptr.resize(n + 1);
+    at_idx.resize(nnz);
+    a_ptr.assign(m + 1, 0);
+    a_idx.resize(nnz);
+    perm.resize(nnz);
+    auto par = [&](long cnt, auto fn) { parallel_for(cnt, host_threads, fn); };
+    for (long j = 0; j <= n; ++j) at_ptr[j] = (int)Ap[j];
+    {
+        std::vector<std::vector<int>> cnt(host_threads);
+        std::vector<int> bad(host_threads, 0);
+        par(n, [&](long j0, long j1, int t) {
+            std::vector<int>& c = cnt[t];
+            c.assign(m, 0);
+            for (long k = Ap[j0]; k < Ap[j1]; ++k) {
+                const long r = Ai[k];
+                if (r < 0 || r >= m) { bad[t] = 1; return; }
+                at_idx[k] = (int)r;
+                c[r]++;
+            }
+        });
+        for (int t = 0; t < host_threads; ++t)
+            if (bad[t]) {
+                fprintf(stderr, "[abip_gpu] row index out of range\n");
+                return -1;
+            }
+        for (long i = 0; i < m; ++i) {
+            int tot = 0;
+            for (int t = 0; t < host_threads; ++t) {
+                if (cnt[t].empty()) continue;  // (fewer ranges than threads)
+                const int c = cnt[t][i];
+                cnt[t][i] = tot;
+                tot += c;
+            }
+            a_ptr[i + 1] = a_ptr[i] + tot;
+        }
+        par(n, [&](long j0, long j1, int t) {
+            std::vector<int>& off = cnt[t];
+            for (long j = j0; j < j1; ++j)
+                for (long k = Ap[j]; k < Ap[j + 1]; ++k) {
+                    const int r = at_idx[k];
+                    const int q = a_ptr[r] + off[r]++;
+                    a_idx[q] = (int)j;
+                    perm[q] = (int)k;
+                }
+        });
+    }
+    return 0;
+}
+
 static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap, const abip_int* Ai,
                        const abip_float* Ax, const ABIPSettings* stgs, int device, const ScaleOut* scale_out = nullptr) {
     const long nnz = Ap[n];
@@ -1090,53 +1187,10 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         e->setup_ms[slot] += std::chrono::duration<double, std::milli>(t - lap_t).count();
         lap_t = t;
     };
-    // CSR(A') is the caller's CSC; CSR(A) by counting sort (the reference's transpose(), indirect.c:81-139);
-    // perm[q] = position in the CSC arrays of entry q of CSR(A)
     const int host_threads = (nnz < 200000 || t_batch) ? 1 : std::max(1, std::min(env_int("ABIP_GPU_HOST_THREADS", 8), (int)std::thread::hardware_concurrency()));
     auto par = [&](long cnt, auto fn) { parallel_for(cnt, host_threads, fn); };
-    std::vector<int> at_ptr(n + 1), at_idx(nnz), a_ptr(m + 1, 0), a_idx(nnz), perm(nnz);
-    for (long j = 0; j <= n; ++j) at_ptr[j] = (int)Ap[j];
-    {
-        // every thread takes a range of columns: counts per row first, then fills its entries behind those of the
-        // threads before it, so that every row lists its columns in ascending order whatever the thread count
-        std::vector<std::vector<int>> cnt(host_threads);
-        std::vector<int> bad(host_threads, 0);
-        par(n, [&](long j0, long j1, int t) {
-            std::vector<int>& c = cnt[t];
-            c.assign(m, 0);
-            for (long k = Ap[j0]; k < Ap[j1]; ++k) {
-                const long r = Ai[k];
-                if (r < 0 || r >= m) { bad[t] = 1; return; }
-                at_idx[k] = (int)r;
-                c[r]++;
-            }
-        });
-        for (int t = 0; t < host_threads; ++t)
-            if (bad[t]) {
-                fprintf(stderr, "[abip_gpu] row index out of range\n");
-                return -1;
-            }
-        for (long i = 0; i < m; ++i) {
-            int tot = 0;
-            for (int t = 0; t < host_threads; ++t) {
-                if (cnt[t].empty()) continue;  // (fewer ranges than threads)
-                const int c = cnt[t][i];
-                cnt[t][i] = tot;
-                tot += c;
-            }
-            a_ptr[i + 1] = a_ptr[i] + tot;
-        }
-        par(n, [&](long j0, long j1, int t) {
-            std::vector<int>& off = cnt[t];
-            for (long j = j0; j < j1; ++j)
-                for (long k = Ap[j]; k < Ap[j + 1]; ++k) {
-                    const int r = at_idx[k];
-                    const int q = a_ptr[r] + off[r]++;
-                    a_idx[q] = (int)j;
-                    perm[q] = (int)k;
-                }
-        });
-    }
+    std::vector<int> at_ptr, at_idx, a_ptr, a_idx, perm;
+    if (transpose_csc(m, n, Ap, Ai, host_threads, &at_ptr, &at_idx, &a_ptr, &a_idx, &perm)) return -1;
     // Locality ordering (sjds_host.h): whole-device engines work in a permuted index space in which structurally
     // identical rows / columns are neighbours, so the 32 lanes of a gather touch a few lines instead of 32.
     // e_* : the engine's matrices; e_a_src / e_at_src: position of every entry in the caller's CSC arrays.
@@ -1395,38 +1449,12 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
             upload(&d_val, ax_copy, e))
             return -1;
         if (reorder && (upload(&d_asrc, e_a_src, e) || upload(&d_atsrc, e_at_src, e))) return -1;
-        const double min_row = 1e-3 * sqrt((double)n), max_row = 1e3 * sqrt((double)n);
-        const double min_col = 1e-3 * sqrt((double)m), max_col = 1e3 * sqrt((double)m);
-        double* Dt = e->p;  // scratch [m]
-        const unsigned gm = (unsigned)((m + 255) / 256), gn = (unsigned)((n + 255) / 256), gz = (unsigned)((nnz + 255) / 256);
-        k_fill<<<gm, 256, 0, e->stream>>>(e->dD, m, 1.0);
-        k_fill<<<gn, 256, 0, e->stream>>>(e->dE, n, 1.0);
-        auto sweep = [&](int kind) {
-            k_eq_cols<<<gn, 256, 0, e->stream>>>(kind, d_atptr, d_val, (int)n, e->dE, min_col, max_col);
-            k_eq_rows<<<gm, 256, 0, e->stream>>>(kind, d_aptr, d_perm, d_val, (int)m, Dt, e->dD, min_row, max_row);
-            k_eq_apply_rows<<<gz, 256, 0, e->stream>>>(d_atidx, d_val, nnz, Dt);
-        };
-        if (stgs->pc_ruiz_rescale) sweep(0);
-        if (stgs->origin_rescale) sweep(1);
-        if (stgs->pc_ruiz_rescale)
-            for (abip_int it = 0; it < stgs->ruiz_iter; ++it) sweep(2);
-        if (stgs->qp_rescale) sweep(3);
-        // mean row / column norms (summed on the host in index order, like common.c:541-557)
+        const unsigned gz = (unsigned)((nnz + 255) / 256);
+        double* Dt = e->p;                    // scratch [m]
         double* rn = e->vec[ABIPGPU_VEC_UT];  // scratch [l] >= max(m, n)
-        std::vector<double> hn(std::max(m, n));
-        k_eq_row_norms<<<gm, 256, 0, e->stream>>>(d_aptr, d_perm, d_val, (int)m, rn);
-        CK(cudaMemcpyAsync(hn.data(), rn, sizeof(double) * m, cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
-        double mr = 0.0;
-        for (abip_int i = 0; i < m; ++i) mr += hn[i];
-        k_eq_col_norms<<<gn, 256, 0, e->stream>>>(d_atptr, d_val, (int)n, rn);
-        CK(cudaMemcpyAsync(hn.data(), rn, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
-        double mc = 0.0;
-        for (abip_int j = 0; j < n; ++j) mc += hn[j];
-        *scale_out->mean_row = mr;
-        *scale_out->mean_col = mc;
-        if (stgs->scale != 1) k_scale_all<<<gz, 256, 0, e->stream>>>(d_val, nnz, stgs->scale);
+        if (run_equilibration(e->stream, (int)m, (int)n, nnz, d_atptr, d_atidx, d_aptr, d_perm, d_val, e->dD, e->dE, Dt, rn, stgs,
+                              scale_out->mean_row, scale_out->mean_col))
+            return -1;
         k_gather_perm<<<gz, 256, 0, e->stream>>>(d_val, reorder ? d_asrc : d_perm, e->A_val, nnz);
         if (reorder) k_gather_perm<<<gz, 256, 0, e->stream>>>(d_val, d_atsrc, e->AT_val, nnz);
         else CK(cudaMemcpyAsync(e->AT_val, d_val, sizeof(double) * nnz, cudaMemcpyDeviceToDevice, e->stream));
@@ -1497,6 +1525,49 @@ abipgpu_lp* abipgpu_lp_create_scaling(abip_int m, abip_int n, const abip_int* Ap
         return nullptr;
     }
     return e;
+}
+
+// Equilibration of a whole matrix on the device without building an engine (multi-GPU set-up: every rank scales the FULL
+// matrix on its own GPU instead of on its host cores -- common.c:150-565 took ~25 s per rank at cfg4).  Ax: in A, out the
+// scaled matrix; D [m], E [n] and the two mean norms as abip_normalize_A returns them (bit-identical).
+int abipgpu_equilibrate(abip_int m, abip_int n, const abip_int* Ap, const abip_int* Ai, abip_float* Ax, const ABIPSettings* stgs,
+                        int device, abip_float* D, abip_float* E, abip_float* mean_norm_row_A, abip_float* mean_norm_col_A) {
+    const long nnz = Ap[n];
+    if (m <= 0 || n <= 0 || nnz <= 0 || nnz >= 2147483647L) return -1;
+    CK(cudaSetDevice(device));
+    const int host_threads = std::max(1, std::min(env_int("ABIP_GPU_HOST_THREADS", 8), (int)std::thread::hardware_concurrency()));
+    std::vector<int> at_ptr, at_idx, a_ptr, a_idx, perm;
+    if (transpose_csc(m, n, Ap, Ai, host_threads, &at_ptr, &at_idx, &a_ptr, &a_idx, &perm)) return -1;
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int *d_perm = nullptr, *d_atptr = nullptr, *d_atidx = nullptr, *d_aptr = nullptr;
+    double *d_val = nullptr, *dD = nullptr, *dE = nullptr, *Dt = nullptr, *rn = nullptr;
+    auto up = [&](auto** dst, const void* src, size_t bytes) -> int {
+        CK(cudaMallocAsync((void**)dst, bytes + 64, st));
+        if (src) CK(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return 0;
+    };
+    int rc = 0;
+    if (up(&d_perm, perm.data(), sizeof(int) * nnz) || up(&d_atptr, at_ptr.data(), sizeof(int) * (n + 1)) ||
+        up(&d_atidx, at_idx.data(), sizeof(int) * nnz) || up(&d_aptr, a_ptr.data(), sizeof(int) * (m + 1)) ||
+        up(&d_val, Ax, sizeof(double) * nnz) || up(&dD, nullptr, sizeof(double) * m) || up(&dE, nullptr, sizeof(double) * n) ||
+        up(&Dt, nullptr, sizeof(double) * m) || up(&rn, nullptr, sizeof(double) * std::max(m, n)))
+        rc = -1;
+    if (!rc) rc = run_equilibration(st, (int)m, (int)n, nnz, d_atptr, d_atidx, d_aptr, d_perm, d_val, dD, dE, Dt, rn, stgs,
+                                   mean_norm_row_A, mean_norm_col_A);
+    if (!rc) {
+        if (cudaMemcpyAsync(Ax, d_val, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(D, dD, sizeof(double) * m, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(E, dE, sizeof(double) * n, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess)
+            rc = -1;
+    }
+    void* ptrs[] = {d_perm, d_atptr, d_atidx, d_aptr, d_val, dD, dE, Dt, rn};
+    for (void* q : ptrs)
+        if (q) cudaFreeAsync(q, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
 }
 
 void abipgpu_lp_destroy(abipgpu_lp* e) {

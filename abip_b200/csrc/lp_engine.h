@@ -17,6 +17,8 @@ extern "C" int abipgpu_lp_comm_connect(abipgpu_lp* e, int G, int rank, const voi
 extern "C" void abipgpu_lp_set_global_n(abipgpu_lp* e, long n_global);
 extern "C" void abipgpu_lp_request_grid(int ctas);
 extern "C" void abipgpu_lp_request_order(int on);
+extern "C" int abipgpu_equilibrate(abip_int m, abip_int n, const abip_int* Ap, const abip_int* Ai, abip_float* Ax, const ABIPSettings* stgs,
+                                   int device, abip_float* D, abip_float* E, abip_float* mean_norm_row_A, abip_float* mean_norm_col_A);
 // lock-step batch executor (lp_engine.cu: BatchExec)
 extern "C" void* abipgpu_batch_begin(int device, int capacity);
 extern "C" void abipgpu_batch_attach(void* b);

@@ -3,6 +3,8 @@
 // (group (2)).  Only scalar decisions happen here; every vector operation is a CUDA kernel in lp_engine.cu.
 // Each function cites the reference lines whose behaviour it reproduces (paths under src/abip-lp/).
 #include "lp_engine.h"
+#include "order_host.h"
+#include <thread>
 
 #include <algorithm>
 #include <cmath>
@@ -293,6 +295,7 @@ struct ABIP_GPU_WORK {  // device-resident replacement of struct ABIP_WORK (incl
     double sp = 0;
     abipgpu_lp* eng = nullptr;
     std::vector<double> b, c;  // scaled
+    std::vector<int> rperm, cperm;  // multi-GPU: locality ordering applied to the host copy of A (new -> old; empty: identity)
     double sigma = 0, gamma = 0, mu = 1, beta = 1;
     int final_check = 0, double_check = 0;
     double sc_b = 1, sc_c = 1, nm_b = 0, nm_c = 0;
@@ -562,12 +565,20 @@ int get_solution(ABIP_GPU_WORK* w, ABIPSolution* sol, ABIPInfo* info, Resid* r, 
     if (abipgpu_lp_get_vec(w->eng, avg ? ABIPGPU_VEC_UAVGC : ABIPGPU_VEC_U, uu.data(), l) != 0 ||
         abipgpu_lp_get_vec(w->eng, avg ? ABIPGPU_VEC_VAVGC : ABIPGPU_VEC_V, vv.data(), l) != 0)
         return -1;
-    std::copy(uu.begin(), uu.begin() + m, sol->y);
     // multi-GPU: each rank returns its own column shard of x and s (zeros elsewhere; the caller sums the shards)
     std::fill(sol->x, sol->x + n, 0.0);
     std::fill(sol->s, sol->s + n, 0.0);
-    std::copy(uu.begin() + m, uu.begin() + m + nl, sol->x + w->c0);
-    std::copy(vv.begin() + m, vv.begin() + m + nl, sol->s + w->c0);
+    if (w->cperm.empty()) {
+        std::copy(uu.begin(), uu.begin() + m, sol->y);
+        std::copy(uu.begin() + m, uu.begin() + m + nl, sol->x + w->c0);
+        std::copy(vv.begin() + m, vv.begin() + m + nl, sol->s + w->c0);
+    } else {  // engine order -> caller's order
+        for (abip_int i = 0; i < m; ++i) sol->y[w->rperm[i]] = uu[i];
+        for (abip_int j = 0; j < nl; ++j) {
+            sol->x[w->cperm[w->c0 + j]] = uu[m + j];
+            sol->s[w->cperm[w->c0 + j]] = vv[m + j];
+        }
+    }
     enum { SOLVED, INDET, INFEAS, UNBDD } kind;
     const abip_int sv = info->status_val;
     if (sv == ABIP_UNFINISHED) {
@@ -695,6 +706,52 @@ void abip_gpu_partition(const ABIPGpuWork* w, abip_int* c0, abip_int* nl) {
     *nl = w->nl;
 }
 
+// Multi-GPU: the locality ordering (order_host.h) is applied ONCE to the host copy of the (scaled) matrix, identically on
+// every rank (a pure function of the structure), before the column blocks are cut: the m-space is replicated and
+// exchanged by row index, so all ranks must agree on the row order; the engines then keep the order they are given.
+static void reorder_host_matrix(ABIPGpuWork* w) {
+    const abip_int m = w->m, n = w->n;
+    const long nnz = w->A->p[n];
+    if (nnz >= 2147483647L) return;
+    const int threads = std::max(1, std::min(8, (int)std::thread::hardware_concurrency()));
+    auto par = [&](long cnt, auto fn) { parallel_for(cnt, threads, fn); };
+    std::vector<int> at_ptr(n + 1), at_idx(nnz), a_ptr(m + 1, 0), a_idx(nnz);
+    for (abip_int j = 0; j <= n; ++j) at_ptr[j] = (int)w->A->p[j];
+    for (long k = 0; k < nnz; ++k) { at_idx[k] = (int)w->A->i[k]; a_ptr[w->A->i[k] + 1]++; }
+    for (abip_int i = 0; i < m; ++i) a_ptr[i + 1] += a_ptr[i];
+    {
+        std::vector<int> fill(a_ptr.begin(), a_ptr.end() - 1);
+        for (abip_int j = 0; j < n; ++j)
+            for (long k = w->A->p[j]; k < w->A->p[j + 1]; ++k) a_idx[fill[w->A->i[k]]++] = (int)j;
+    }
+    std::vector<int> rn2o, cn2o;
+    sjds::locality_order((int)m, (int)n, a_ptr, a_idx, at_ptr, at_idx, sjds::kLongRow, &rn2o, &cn2o, par);
+    bool ident = true;
+    for (abip_int i = 0; i < m && ident; ++i) ident = rn2o[i] == i;
+    for (abip_int j = 0; j < n && ident; ++j) ident = cn2o[j] == j;
+    if (ident) return;
+    std::vector<int> ro2n(m);
+    for (abip_int i = 0; i < m; ++i) ro2n[rn2o[i]] = (int)i;
+    abip_int* np_ = (abip_int*)malloc(sizeof(abip_int) * (n + 1));
+    abip_int* ni = (abip_int*)malloc(sizeof(abip_int) * nnz);
+    double* nx = (double*)malloc(sizeof(double) * nnz);
+    np_[0] = 0;
+    for (abip_int j = 0; j < n; ++j) np_[j + 1] = np_[j] + (w->A->p[cn2o[j] + 1] - w->A->p[cn2o[j]]);
+    par(n, [&](long j0, long j1, int) {
+        for (long j = j0; j < j1; ++j) {
+            long q = np_[j];
+            for (long k = w->A->p[cn2o[j]]; k < w->A->p[cn2o[j] + 1]; ++k, ++q) {
+                ni[q] = ro2n[w->A->i[k]];
+                nx[q] = w->A->x[k];
+            }
+        }
+    });
+    free(w->A->p); free(w->A->i); free(w->A->x);
+    w->A->p = np_; w->A->i = ni; w->A->x = nx;
+    w->rperm = std::move(rn2o);
+    w->cperm = std::move(cn2o);
+}
+
 static ABIPGpuWork* gpu_init_impl(const ABIPData* d, ABIPInfo* info, int rank, int G) {  // ABIP(init) + init_work, abip.c:1739-1841, 2341-2389
     if (!d || !info) {
         printf("ERROR: Missing ABIPData or ABIPInfo input\n");
@@ -764,9 +821,26 @@ static ABIPGpuWork* gpu_init_impl(const ABIPData* d, ABIPInfo* info, int rank, i
         return nullptr;
     }
     if (w->stgs.normalize) {
-        abip_normalize_A(w->A, &w->stgs, &w->scal);
+        // multi-GPU: every rank equilibrates the FULL matrix on its own GPU (bit-identical to abip_normalize_A, which took
+        // ~25 s of host time per rank at cfg4)
+        bool done = false;
+        if (G > 1 && !getenv("ABIP_GPU_HOST_SCALING")) {
+            w->scal.D = (double*)malloc(sizeof(double) * w->m);
+            w->scal.E = (double*)malloc(sizeof(double) * w->n);
+            done = abipgpu_equilibrate(w->m, w->n, w->A->p, w->A->i, w->A->x, &w->stgs, dev ? atoi(dev) : 0, w->scal.D, w->scal.E,
+                                       &w->scal.mean_norm_row_A, &w->scal.mean_norm_col_A) == 0;
+            if (!done) {
+                free(w->scal.D); free(w->scal.E);
+                w->scal.D = w->scal.E = nullptr;
+                abip_free_A_matrix(w->A);
+                w->A = nullptr;
+                if (!abip_copy_A_matrix(&w->A, d->A)) { delete w; return nullptr; }
+            }
+        }
+        if (!done) abip_normalize_A(w->A, &w->stgs, &w->scal);
         w->have_scal = true;
     }
+    if (G > 1 && !getenv("ABIP_GPU_NO_REORDER")) reorder_host_matrix(w);
     if (G > 1) {  // contiguous column blocks balanced by nonzeros
         if (w->stgs.half_update) {
             printf("ERROR: half_update is not supported by the multi-GPU engine\n");
@@ -868,10 +942,25 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
         // unless built with NOVALIDATE, i.e. it degenerates to the cold start.
         printf("WARN: warm_start behaves as in the reference build: iterates restart from sqrt(mu/beta)\n");
     }
-    if (abipgpu_lp_cold_start(w->eng, w->mu, w->beta) != 0 ||
-        abipgpu_lp_set_problem(w->eng, w->b.data(), w->c.data() + w->c0, s.normalize ? w->scal.D : nullptr,
-                               s.normalize ? w->scal.E + w->c0 : nullptr) != 0)
-        return failure(m, n, sol, info, ABIP_FAILED, "error in update_work", "Failure");
+    {
+        const double *pb = w->b.data(), *pc = w->c.data() + w->c0;
+        const double *pD = s.normalize ? w->scal.D : nullptr, *pE = s.normalize ? w->scal.E + w->c0 : nullptr;
+        std::vector<double> qb, qc, qD, qE;
+        if (!w->cperm.empty()) {  // multi-GPU with locality ordering: the engine's matrix is P_r A P_c
+            qb.resize(m); qc.resize(w->nl);
+            for (abip_int i = 0; i < m; ++i) qb[i] = w->b[w->rperm[i]];
+            for (abip_int j = 0; j < w->nl; ++j) qc[j] = w->c[w->cperm[w->c0 + j]];
+            pb = qb.data(); pc = qc.data();
+            if (s.normalize) {
+                qD.resize(m); qE.resize(w->nl);
+                for (abip_int i = 0; i < m; ++i) qD[i] = w->scal.D[w->rperm[i]];
+                for (abip_int j = 0; j < w->nl; ++j) qE[j] = w->scal.E[w->cperm[w->c0 + j]];
+                pD = qD.data(); pE = qE.data();
+            }
+        }
+        if (abipgpu_lp_cold_start(w->eng, w->mu, w->beta) != 0 || abipgpu_lp_set_problem(w->eng, pb, pc, pD, pE) != 0)
+            return failure(m, n, sol, info, ABIP_FAILED, "error in update_work", "Failure");
+    }
 
     if (s.verbose) print_header_line(w);
 

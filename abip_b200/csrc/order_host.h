@@ -12,7 +12,24 @@
 #include <cstdint>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include <vector>
+
+// fn(begin, end, thread id) over [0, n) on up to `threads` host threads (set-up of large problems only)
+template <class Fn>
+static inline void parallel_for(long n, int threads, Fn fn) {
+    threads = (int)std::max<long>(1, std::min<long>(threads, n / 4096));
+    if (threads <= 1) {
+        fn(0L, n, 0);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        const long b = n * t / threads, e2 = n * (t + 1) / threads;
+        pool.emplace_back([=] { fn(b, e2, t); });
+    }
+    for (auto& th : pool) th.join();
+}
 
 namespace sjds {  // (name kept from the sliced-JDS experiments of round 2, tools/ubench)
 

@@ -8,6 +8,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "lp_device.cuh"
+#include "order_host.h"
 
 #define CK(call)                                                                                         \
     do {                                                                                                 \
@@ -37,22 +38,6 @@ static inline cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t s) {
 }
 static inline void dev_free(void* p, cudaStream_t s) {
     if (p) cudaFreeAsync(p, s);
-}
-
-// fn(begin, end, thread id) over [0, n) on up to `threads` host threads (set-up of large problems only)
-template <class Fn>
-static inline void parallel_for(long n, int threads, Fn fn) {
-    threads = (int)std::max<long>(1, std::min<long>(threads, n / 4096));
-    if (threads <= 1) {
-        fn(0L, n, 0);
-        return;
-    }
-    std::vector<std::thread> pool;
-    for (int t = 0; t < threads; ++t) {
-        const long b = n * t / threads, e2 = n * (t + 1) / threads;
-        pool.emplace_back([=] { fn(b, e2, t); });
-    }
-    for (auto& th : pool) th.join();
 }
 
 static inline int env_int(const char* name, int dflt) {

@@ -45,16 +45,42 @@ def assemble_shards(local: np.ndarray, group=None) -> np.ndarray:
     return t.cpu().numpy()
 
 
+# Below this many nonzeros per GPU the exchange of the m-vector (two cross-GPU flag round trips + NVLink transfers per
+# operator application) costs more than the local SpMV it saves: measured at cfg2 (5.0 M nonzeros) 1.02x on 2 GPUs but
+# 0.74x / 0.70x on 4 / 8 (SCALE_r01), at cfg4 (60.5 M) 1.7x on 2 (profiles/r02_multi_gpu.md).  A solver asked to use more
+# GPUs than that shards over the first `effective_world` ranks only; the others hold no engine and contribute zeros.
+MIN_NNZ_PER_GPU = 2_400_000
+
+
+def effective_world(nnz: int, world: int, min_nnz_per_gpu: int | None = None) -> int:
+    lim = MIN_NNZ_PER_GPU if min_nnz_per_gpu is None else min_nnz_per_gpu
+    return max(1, min(world, nnz // max(1, lim)))
+
+
 class LpSolverDist:
     """Collective counterpart of LpSolver: every rank constructs it with the FULL problem and calls solve()."""
 
-    def __init__(self, A, params: dict | None = None, group=None, **raw_settings):
+    def __init__(self, A, params: dict | None = None, group=None, min_nnz_per_gpu: int | None = None, **raw_settings):
         import torch.distributed as dist
         self.L = _capi.lib()
-        self.group = group
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.outer_group = group
+        self.outer_rank, self.outer_world = dist.get_rank(group), dist.get_world_size(group)
         self.p, self.st = _lp_settings(params, **raw_settings)
         self.H = CscHolder(A)
+        self.world = effective_world(self.H.nnz, self.outer_world, min_nnz_per_gpu)
+        self.w = None
+        # every rank of the outer group must take part in new_group()
+        if self.world < self.outer_world:
+            ranks = list(range(self.world)) if group is None else None
+            if ranks is None:
+                raise ValueError("a custom group with fewer effective ranks is not supported")
+            group = dist.new_group(ranks=ranks)
+        self.group = group
+        self.active = self.outer_rank < self.world
+        self.rank = self.outer_rank
+        if not self.active:
+            self.setup_time_ms = 0.0
+            return
         self.info = _capi.ABIPInfo()
         self._b = np.zeros(self.H.m)
         self._c = np.zeros(self.H.n)
@@ -75,7 +101,19 @@ class LpSolverDist:
         self._libc = C.CDLL(None)
         self._libc.free.argtypes = [C.c_void_p]
 
+    def _solve_idle(self):
+        """rank outside the effective group: zero shards + the result record of rank 0"""
+        import torch.distributed as dist
+        x = assemble_shards(np.zeros(self.H.n), self.outer_group)
+        s = assemble_shards(np.zeros(self.H.n), self.outer_group)
+        box = [None]
+        dist.broadcast_object_list(box, src=0, group=self.outer_group)
+        res, y = box[0]
+        return x, y, s, res
+
     def solve(self, b, c):
+        if not self.active:
+            return self._solve_idle()
         self._b[:] = b
         self._c[:] = c
         sol = _capi.ABIPSolution()
@@ -89,12 +127,15 @@ class LpSolverDist:
             out[name] = np.ctypeslib.as_array(ptr, shape=(ln,)).copy() if ptr else np.full(ln, np.nan)
             if ptr:
                 self._libc.free(C.cast(ptr, C.c_void_p))
-        x = assemble_shards(out["x"], self.group)
-        s = assemble_shards(out["s"], self.group)
+        x = assemble_shards(out["x"], self.outer_group)
+        s = assemble_shards(out["s"], self.outer_group)
         res = dict(status=info.status.decode(), status_val=int(info.status_val), ipm_iter=int(info.ipm_iter),
                    admm_iter=int(info.admm_iter), pres=info.res_pri, dres=info.res_dual, gap=info.rel_gap,
-                   pobj=info.pobj, dobj=info.dobj, solve_time_ms=info.solve_time,
+                   pobj=info.pobj, dobj=info.dobj, solve_time_ms=info.solve_time, gpus_used=self.world,
                    stats={f: getattr(stats, f) for f, _ in stats._fields_})
+        if self.world < self.outer_world:
+            import torch.distributed as dist
+            dist.broadcast_object_list([(res, out["y"])], src=0, group=self.outer_group)
         return x, out["y"], s, res
 
     def close(self):

@@ -406,7 +406,7 @@ def run_ours(args):
         out = {"workload": f"{label} as ONE instance, column blocks of A over {world} GPUs",
                "value": sh_its / (sh_ms / 1e3), "unit": "iter/s", "scaling": "strong",
                "time_to_1e-4_s": sh_ms / nst / 1e3, "setup_s": setup_s, "status": si["status"],
-               "admm_iter_per_solve": sh_its / nst,
+               "admm_iter_per_solve": sh_its / nst, "gpus_used": si.get("gpus_used", world),
                "collective": "in-kernel peer-memory sum of the m-vector A_g x_g + scalar blocks (no NCCL in the solve)"}
         if x_ref is not None:
             out["parity"] = {"against": "single-GPU engine, same instance, same run",

@@ -14,7 +14,7 @@ p = {'small': lambda: problems.random_lp(200, 700, 4, seed=3), 'mcf': lambda: pr
      'cfg1': problems.cfg1, 'cfg2s': lambda: problems.cfg2(scale=0.05), 'cfg2': problems.cfg2,
      'cfg4s': lambda: problems.cfg4(scale=float(os.environ.get('CFG4_SCALE', '0.25'))), 'cfg4': problems.cfg4}[case]()
 print('rank', rank, 'init...', flush=True)
-sol = LpSolverDist(p.csc(), dict(tol=1e-4, verbose=int(os.environ.get('VERB', 0))))
+sol = LpSolverDist(p.csc(), dict(tol=1e-4, verbose=int(os.environ.get('VERB', 0))), min_nnz_per_gpu=0)  # force sharding of the small test problems
 print('rank', rank, 'connected', flush=True)
 dist.barrier(); torch.cuda.synchronize()
 t0 = time.time()
