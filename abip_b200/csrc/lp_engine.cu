@@ -2091,6 +2091,7 @@ int abipgpu_lp_solve_timer(abipgpu_lp* e, int stop) {  // CUDA events on the eng
     return 0;
 }
 int abipgpu_lp_dims(const abipgpu_lp* e, int* m, int* n) { *m = e->m; *n = e->n; return 0; }
+void abipgpu_lp_drop_pending(abipgpu_lp* e) { e->n_pend = 0; }
 int abipgpu_lp_sync(abipgpu_lp* e) {
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));

@@ -11,6 +11,7 @@ int abipgpu_lp_solve_host(abipgpu_lp* e, double* b, const double* s, long iter, 
 ABIPGpuStats* abipgpu_lp_stats(abipgpu_lp* e);
 int abipgpu_lp_dims(const abipgpu_lp* e, int* m, int* n);
 int abipgpu_lp_sync(abipgpu_lp* e);
+void abipgpu_lp_drop_pending(abipgpu_lp* e);  // batch engines: forget deferred vector operations (failed solve)
 int abipgpu_lp_solve_timer(abipgpu_lp* e, int stop);
 extern "C" int abipgpu_lp_comm_export(abipgpu_lp* e, void* handle64);
 extern "C" int abipgpu_lp_comm_connect(abipgpu_lp* e, int G, int rank, const void* handles);

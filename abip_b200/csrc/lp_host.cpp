@@ -34,10 +34,18 @@ double now_ms() {  // src/util.c:73-102 (CLOCK_MONOTONIC, milliseconds)
 }
 
 // ---- SIGINT polling, same contract as src/ctrlc.c:62-93 -------------------------------------------------
+// The handler is process-global but solves may run concurrently (abip_gpu_batch_main: one host thread per problem in
+// flight): the listener is reference-counted under a mutex -- only the FIRST solve saves the host's handler and clears
+// the flag, only the LAST one restores it, so an interrupt delivered during a batch reaches every solve and the host
+// process (e.g. Python's KeyboardInterrupt handler) gets its own handler back afterwards.
 volatile sig_atomic_t g_interrupted = 0;
 struct sigaction g_old_action;
+std::mutex g_sig_mu;
+int g_sig_users = 0;
 void on_sigint(int) { g_interrupted = 1; }
 void start_interrupt_listener() {
+    std::lock_guard<std::mutex> lk(g_sig_mu);
+    if (g_sig_users++ > 0) return;
     struct sigaction act;
     g_interrupted = 0;
     act.sa_flags = 0;
@@ -46,6 +54,8 @@ void start_interrupt_listener() {
     sigaction(SIGINT, &act, &g_old_action);
 }
 void end_interrupt_listener() {
+    std::lock_guard<std::mutex> lk(g_sig_mu);
+    if (g_sig_users <= 0 || --g_sig_users > 0) return;
     struct sigaction cur;
     sigaction(SIGINT, &g_old_action, &cur);
 }
@@ -65,6 +75,7 @@ struct ABIP_LIN_SYS_WORK {
     abipgpu_lp* eng;
     abip_int tot_cg_its;        // linsys/indirect.h:26-28
     abip_float total_solve_time;
+    int failed;                 // latched error of accum_by_A / accum_by_Atrans (their signature has no error channel)
 };
 
 extern "C" {
@@ -249,6 +260,7 @@ abip_int abip_solve_lin_sys(const ABIPMatrix* A, const ABIPSettings* stgs, ABIPL
     (void)stgs;
     const double t0 = now_ms();
     int its = 0;
+    if (p->failed) return -1;  // an earlier accum_by_A / accum_by_Atrans failed (no error channel there): fail here
     if (abipgpu_lp_solve_host(p->eng, b, s, (long)iter, &its) != 0) return -1;
     if (iter >= 0) p->tot_cg_its += its;
     p->total_solve_time += now_ms() - t0;
@@ -257,9 +269,11 @@ abip_int abip_solve_lin_sys(const ABIPMatrix* A, const ABIPSettings* stgs, ABIPL
 
 void abip_accum_by_Atrans(const ABIPMatrix* A, ABIPLinSysWork* p, const abip_float* x, abip_float* y) {
     (void)A;
-    if (abipgpu_lp_spmv_host(p->eng, 1, x, y, 1) != 0) {  // the reference signature has no error channel
+    // the reference signature has no error channel: latch the error, the next solve_lin_sys returns -1 (=> ABIP_FAILED in
+    // the caller, src/abip.c:2137-2140) instead of taking the host process (MATLAB) down
+    if (abipgpu_lp_spmv_host(p->eng, 1, x, y, 1) != 0) {
         fprintf(stderr, "[abip_gpu] accum_by_Atrans failed\n");
-        abort();
+        p->failed = 1;
     }
 }
 
@@ -267,7 +281,7 @@ void abip_accum_by_A(const ABIPMatrix* A, ABIPLinSysWork* p, const abip_float* x
     (void)A;
     if (abipgpu_lp_spmv_host(p->eng, 0, x, y, 1) != 0) {
         fprintf(stderr, "[abip_gpu] accum_by_A failed\n");
-        abort();
+        p->failed = 1;
     }
 }
 
@@ -369,8 +383,7 @@ abip_int failure(abip_int m, abip_int n, ABIPSolution* sol, ABIPInfo* info, abip
         }
     }
     printf("Failure:%s\n", msg);
-    end_interrupt_listener();
-    return status;
+    return status;  // (abip_gpu_solve releases the SIGINT listener in its epilogue guard)
 }
 
 // Q-norm criterion from one 13-scalar group (src/abip.c:1972-1992)
@@ -912,6 +925,18 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
     ABIPGpuStats* st = abipgpu_lp_stats(w->eng);
     memset(st, 0, sizeof(*st));
     abipgpu_lp_solve_timer(w->eng, 0);
+    // ONE epilogue for every way out of the solve (normal returns and the failure() paths): the solve timer is stopped,
+    // the statistics are copied, deferred batch operations are dropped and the SIGINT listener is released
+    struct SolveEpilogue {
+        ABIP_GPU_WORK* w;
+        ABIPGpuStats* st;
+        ~SolveEpilogue() {
+            abipgpu_lp_solve_timer(w->eng, 1);
+            w->last_stats = *st;
+            abipgpu_lp_drop_pending(w->eng);
+            end_interrupt_listener();
+        }
+    } solve_epilogue{w, st};
     w->tot_cg_its = 0;
     w->total_adapt_ms = 0;
 
@@ -1008,9 +1033,6 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
                         return failure(m, n, sol, info, ABIP_FAILED, "error in get_solution", "Failure");
                     info->solve_time = now_ms() - t0;
                     if (s.verbose) print_footer(w, info);
-                    end_interrupt_listener();
-                    abipgpu_lp_solve_timer(w->eng, 1);
-                    w->last_stats = *st;
                     return info->status_val;
                 }
             }
@@ -1028,9 +1050,6 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
                 return failure(m, n, sol, info, ABIP_FAILED, "error in get_solution", "Failure");
             info->solve_time = now_ms() - t0;
             if (s.verbose) print_footer(w, info);
-            end_interrupt_listener();
-            abipgpu_lp_solve_timer(w->eng, 1);
-            w->last_stats = *st;
             return info->status_val;
         }
         if (update_mu(w, &r) != 0) return failure(m, n, sol, info, ABIP_FAILED, "error in mu update", "Failure");
@@ -1052,9 +1071,6 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
     if (get_solution(w, sol, info, &r, s.max_ipm_iters - 1, k) != 0)
         return failure(m, n, sol, info, ABIP_FAILED, "error in get_solution", "Failure");
     info->solve_time = now_ms() - t0;
-    end_interrupt_listener();
-    abipgpu_lp_solve_timer(w->eng, 1);
-    w->last_stats = *st;
     return info->status_val;
 }
 

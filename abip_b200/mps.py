@@ -6,10 +6,11 @@ min c'x  s.t. A x = b, x >= 0.  `read_mps` restates what mpsread returns (E rows
 negated into Aineq, ranged rows -> two inequalities, N row -> objective, BOUNDS section), `to_standard_form` restates
 preprocess.m line by line:
 
-    lb: finite kept, NaN -> -1e6, -inf -> -1e8                       (preprocess.m:35-37)
+    lb: finite kept, NaN -> -1e6, -inf -> -1.01e8 (MATLAB: 0 * -Inf = NaN -> -1e6, then -1e8 added)   (preprocess.m:35-37)
     x' = x - lb >= 0; one slack per inequality; one row  x'_j + t_j = ub_j - lb_j  per finite ub   (:40-57)
     A = [Aeq 0 0; Aineq I 0; D 0 I],  b = [beq - Aeq lb; bineq - Aineq lb; ub - lb],  c = [f; 0]
-    objcon = f'lb (+ the objective constant of the file)                  (:75-80)
+    objcon = f'lb with the SHIFTED lb (+ the objective constant of the file).  Deliberate deviation: preprocess.m:75
+             uses prob.lb, which is -Inf (NaN for f_j = 0) as soon as the problem has a free variable      (:75-80)
 
 Host-side Python (the reference's own preprocessing is a script); the GPU engine only ever sees the standard form.
 """
@@ -83,8 +84,12 @@ def read_mps(path) -> GeneralLP:
                     name = tok[1] if len(tok) > 1 else ""
                 elif section == "ENDATA":
                     break
-                elif section in ("OBJSENSE", "OBJSENSE MAX"):
-                    pass
+                elif section.startswith("OBJSENSE"):
+                    # "OBJSENSE MAX" / "OBJSENSE MAXIMIZE" on the header line, or extensions such as OBJSENSE_MAX
+                    rest = (section[len("OBJSENSE"):] + " " + " ".join(tok[1:])).upper()
+                    if "MAX" in rest:
+                        raise ValueError("maximisation problems are not supported (mpsread rejects them as well)")
+                    section = "OBJSENSE"
                 continue
             tok = raw.split()
             if section == "OBJSENSE":
@@ -205,7 +210,10 @@ def to_standard_form(g: GeneralLP) -> StandardLP:
     """scripts/bench-lp/preprocess.m:20-80."""
     n = g.f.size
     m1, m2 = g.Aeq.shape[0], g.Aineq.shape[0]
-    lb = np.where(g.lb > -np.inf, g.lb, 0.0)
+    # preprocess.m:35-37 in MATLAB arithmetic: (lb > -inf) .* lb is 0 * -Inf = NaN for a free variable, NaN becomes -1e6,
+    # then -1e8 is added: a free variable is shifted by -1.01e8 (and a NaN bound in the input by -1e6)
+    with np.errstate(invalid="ignore"):
+        lb = (g.lb > -np.inf) * g.lb
     lb = np.where(np.isnan(lb), -1e6, lb)                        # :36
     lb = lb + (g.lb == -np.inf) * (-1e8)                         # :37
     idxub = g.ub < np.inf

@@ -401,3 +401,44 @@ def test_cfg5_batch_slice_against_reference_golden():
         pobj = float(p.c @ x)
         assert abs(pobj - g["pobj"]) <= 1e-6 * abs(g["pobj"]) + 2e-8, (p.name, pobj, g["pobj"])
         assert abs(np.linalg.norm(x) - g["x_norm"]) < 1e-3 * g["x_norm"]
+
+
+def test_sigint_handler_is_restored_after_a_batch():
+    """the SIGINT listener is process-global but a batch runs one solve per host thread; it is
+    reference-counted, so the host's own handler (Python's KeyboardInterrupt) is back in place afterwards."""
+    import signal
+    from abip_b200 import lp_solve_batch
+    before = signal.getsignal(signal.SIGINT)
+    probs = [problems.random_lp(40, 120, 3, seed=70 + i) for i in range(12)]
+    res = lp_solve_batch(probs, dict(tol=1e-3, verbose=0), concurrency=12, ctas_per_problem=1)
+    assert all(r[3]["status_val"] == 1 for r in res)
+    assert signal.getsignal(signal.SIGINT) is before
+    x, y, s, info = lp_solve(probs[0].csc(), probs[0].b, probs[0].c, dict(tol=1e-3, verbose=0))
+    assert signal.getsignal(signal.SIGINT) is before
+
+
+@pytest.mark.parametrize("name", ["rand_200x700", "cfg1"])
+def test_trajectory_without_resync_matches_oracle(name, tmp_path):
+    """The whole solve, iteration by iteration, with NO re-synchronisation of the iterates from the oracle: the trace of
+    the host loop (ABIP_GPU_TRACE: outer / inner / global iteration, mu, beta, CG iterations, Q-norm criterion) against the
+    oracle's own trace.  Drift is allowed to show: the iteration structure must be identical, mu exact, beta and the
+    criterion to the accuracy the inexact solves allow."""
+    p = problems.cfg1() if name == "cfg1" else PROBLEMS[name]()
+    tf = str(tmp_path / "trace.txt")
+    os.environ["ABIP_GPU_TRACE"] = tf
+    try:
+        x, y, s, info = lp_solve(p.csc(), p.b, p.c, dict(tol=1e-4, verbose=0))
+    finally:
+        del os.environ["ABIP_GPU_TRACE"]
+    o = O.solve(p.csc(), p.b, p.c, O.Settings(eps=1e-4), trace=True)
+    gpu = [ln.split() for ln in open(tf) if ln.startswith("it ")]
+    assert info["admm_iter"] == o.admm_iter
+    assert len(gpu) == len(o.trace)
+    cg_diff = 0
+    for a, b in zip(gpu, o.trace):
+        assert (int(a[1]), int(a[2]), int(a[3])) == (b[0], b[1], b[2])
+        assert abs(float(a[4]) - b[3]) <= 1e-9 * abs(b[3])                       # mu
+        assert abs(float(a[5]) - b[4]) <= 1e-4 * abs(b[4])                       # beta (BB search on inexact solves)
+        assert abs(float(a[7]) - b[6]) <= 1e-3 * abs(b[6]) + 1e-12               # Q-norm criterion
+        cg_diff += int(a[6]) != b[5]
+    assert cg_diff <= 0.05 * len(gpu) + 1

@@ -95,13 +95,14 @@ def test_standard_form_matches_general_form_under_highs(tmp_path, seed):
 
 
 def test_unbounded_below_defaults_of_preprocess_m(tmp_path):
-    """preprocess.m:35-37: -inf lower bounds become -1e8 (the shift), finite ones are kept."""
+    """preprocess.m:35-37 in MATLAB arithmetic: (lb > -inf) .* lb = 0 * -Inf = NaN -> -1e6, then -1e8 is added: a free
+    variable is shifted by -1.01e8; finite lower bounds are kept."""
     f = str(tmp_path / "u.mps")
     open(f, "w").write("NAME U\nROWS\n N C\n E R0\nCOLUMNS\n X0 C 1.0 R0 1.0\n X1 C 1.0 R0 1.0\nRHS\n RHS R0 3.0\n"
                        "BOUNDS\n MI B X0\n LO B X1 2.0\nENDATA\n")
     s = mps.to_standard_form(mps.read_mps(f))
-    assert s.lb_shift.tolist() == [-1e8, 2.0]
-    assert s.b.tolist() == [3.0 + 1e8 - 2.0] and s.objcon == -1e8 + 2.0
+    assert s.lb_shift.tolist() == [-1.01e8, 2.0]
+    assert s.b.tolist() == [3.0 + 1.01e8 - 2.0] and s.objcon == -1.01e8 + 2.0
     assert s.A.shape == (1, 2)
 
 
@@ -161,3 +162,12 @@ def test_cli_end_to_end_on_gpu(tmp_path):
     x = np.loadtxt(out + ".sol")
     assert x.size == g.f.size
     assert np.all(g.Aineq @ x <= g.bineq + 1e-2 * (1 + np.abs(g.bineq)))
+
+
+@pytest.mark.parametrize("hdr", ["OBJSENSE MAX", "OBJSENSE MAXIMIZE", "OBJSENSE\n    MAX", "OBJSENSE_MAX"])
+def test_objsense_max_is_rejected_in_every_spelling(tmp_path, hdr):
+    """a maximisation problem must not be silently minimised (mpsread rejects it as well)"""
+    f = str(tmp_path / "o.mps")
+    open(f, "w").write("NAME O\n" + hdr + "\nROWS\n N C\n E R0\nCOLUMNS\n X0 C 1.0 R0 1.0\nRHS\n RHS R0 3.0\nENDATA\n")
+    with pytest.raises(ValueError):
+        mps.read_mps(f)

@@ -1,0 +1,25 @@
+"""compute-sanitizer (memcheck / racecheck) over the persistent kernels: the TMA staging windows over-read behind a chunk
+and the bulk copies write through the async proxy into buffers the warps read through the generic proxy (DESIGN.md
+section 3, "memory safety of the staging scheme"); the lock-step batch runs one CTA per problem.  Small problems: the
+tools slow the kernels down 10-100x."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SAN = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+
+
+@pytest.mark.skipif(not os.path.exists(SAN), reason="compute-sanitizer not installed")
+@pytest.mark.parametrize("tool,mode", [("memcheck", "single"), ("memcheck", "batch"), ("racecheck", "single")])
+def test_compute_sanitizer_clean(tool, mode):
+    cmd = [SAN, "--tool", tool, "--error-exitcode", "77", sys.executable, os.path.join(ROOT, "tools", "sanitize_target.py"), mode]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    tail = out.stdout[-3000:] + out.stderr[-2000:]
+    assert out.returncode == 0, tail
+    assert "OK " in out.stdout, tail
+    assert "ERROR SUMMARY: 0 errors" in out.stdout + out.stderr, tail
