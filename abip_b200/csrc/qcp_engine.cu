@@ -23,8 +23,9 @@ struct QcpCtx {
     int m, n;
     Csr A, AT, Q;
     int has_q, q_diag;
-    const double *b, *c, *D, *E, *Hd, *Ms, *r;
+    const double *b, *c, *D, *E, *Hd, *Ms, *Mn, *r;  // Mn: n-space Jacobi preconditioner of the reference (init_qcp_precon)
     double rho_y, rho_x, rho_tau, alpha, a_coef, rtol;
+    int use_nspace;                                 // projection through the reference's n-space qcp_pcg (ABIP_GPU_QCP_NSPACE=1)
     const int *cone_start, *cone_dim, *cone_kind;  // SOC (kind 0) / RSOC (kind 1) blocks, x-index space
     int n_cones, cone_vars;                         // cone_vars = total variables in SOC/RSOC blocks
     int f_len, z_len, l_len;                        // then free, zero, orthant ranges (in this order)
@@ -103,6 +104,134 @@ __device__ __forceinline__ int dev_hinv_general(const QcpCtx& c, Reducer& R, cg:
         grid_sync(grid);
     }
     return its;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The reference's own indirect path, restated on the device (selected with linsys_solver = 3 in abip_qcp_gpu, and
+// through abipgpu_qcp_solve_nspace): n-space operator mat_vec (source/linsys.c:725-750)
+//     G x = rho_x x + Q x + A' ((A x) / rho_y),
+// Jacobi preconditioner init_qcp_precon (qcp_config.c:754-780: Mn_j = 1 / (sum_i A_ij^2 / rho_y + Q_jj + rho_x), kernel
+// k_qcp_mn) and qcp_pcg (linsys.c:755-851: stop on |r|_inf < tol, skip when the initial |r|_inf < max(tol, 1e-12)).
+// Its condition number is ~ 1 / rho_y = 1e6, which is why the Schur path above is the default.
+// bx [n]: right-hand side on entry, solution on exit; warm [n] or nullptr.  Work vectors: tn1 (x), ir (r), ip (p),
+// iHp (G p), tn2 (rho_x p + Q p), cg_p (A p / rho_y, [m]).  Ends with a grid barrier.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dev_nspace_matvec(const QcpCtx& c, Reducer& R, cg::grid_group& grid, const double* x, double* y,
+                                                  const double* dot_with, double* dot_out) {
+    const int n = c.n;
+    spmv_rows(c.A, x, R.ws, nullptr, [&](int row, double a) { c.cg_p[row] = a / c.rho_y; });
+    if (c.has_q) {
+        spmv_rows(c.Q, x, R.ws, nullptr, [&](int row, double a) { c.tn2[row] = fma(c.rho_x, x[row], a); });
+    } else {
+        GRID_STRIDE(j, n) c.tn2[j] = c.rho_x * x[j];
+    }
+    grid_sync(grid);
+    double d[1] = {0.0};
+    spmv_rows(c.AT, c.cg_p, R.ws, nullptr, [&](int row, double a) {
+        const double g = c.tn2[row] + a;
+        y[row] = g;
+        if (dot_with) d[0] = fma(dot_with[row], g, d[0]);
+    });
+    if (dot_with) {
+        R.block_store<1>(d);
+        grid_sync(grid);
+        R.finish<1>(d);
+        *dot_out = d[0];
+    } else {
+        grid_sync(grid);
+    }
+}
+
+__device__ __forceinline__ void dev_qcp_pcg_nspace(const QcpCtx& c, Reducer& R, cg::grid_group& grid, double* bx, const double* warm,
+                                                   double tol, long max_iter, int& its_out, double& res_out) {
+    const int n = c.n;
+    double* x = c.tn1;
+    double* r = c.ir;
+    double* p = c.ip;
+    double* Gp = c.iHp;
+    // r = b - G x0, x = x0   (:771-786)
+    if (warm) {
+        dev_nspace_matvec(c, R, grid, warm, Gp, nullptr, nullptr);
+        GRID_STRIDE(j, n) { r[j] = bx[j] - Gp[j]; x[j] = warm[j]; }
+    } else {
+        GRID_STRIDE(j, n) { r[j] = bx[j]; x[j] = 0.0; }
+    }
+    grid_sync(grid);
+    double s[2] = {0.0, 0.0};  // [|r|_inf (max), z.r]
+    GRID_STRIDE(j, n) {
+        const double rj = r[j], zj = rj * __ldg(c.Mn + j);
+        p[j] = zj;
+        s[0] = fmax(s[0], fabs(rj));
+        s[1] = fma(zj, rj, s[1]);
+    }
+    {
+        double mx[1] = {s[0]}, sm[1] = {s[1]};
+        R.block_store_max<1>(mx, 0);
+        R.block_store<1>(sm, 1);
+        grid_sync(grid);
+        double o[2];
+        R.finish<2, 1u>(o);
+        s[0] = o[0];
+        s[1] = o[1];
+    }
+    int its = 0;
+    double rinf = s[0], ztr = s[1];
+    if (!(rinf < fmax(tol, 1e-12))) {
+        for (long i = 0; i < max_iter; ++i) {
+            double pGp;
+            dev_nspace_matvec(c, R, grid, p, Gp, p, &pGp);
+            const double alpha = ztr / pGp;
+            double t[2] = {0.0, 0.0};
+            GRID_STRIDE(j, n) {
+                x[j] = fma(alpha, p[j], x[j]);
+                const double rj = fma(-alpha, Gp[j], r[j]);
+                r[j] = rj;
+                t[0] = fmax(t[0], fabs(rj));
+                t[1] = fma(rj * __ldg(c.Mn + j), rj, t[1]);
+            }
+            double mx[1] = {t[0]}, sm[1] = {t[1]};
+            R.block_store_max<1>(mx, 0);
+            R.block_store<1>(sm, 1);
+            grid_sync(grid);
+            double o[2];
+            R.finish<2, 1u>(o);
+            its = (int)i + 1;
+            rinf = o[0];
+            if (rinf < tol) break;
+            const double beta = o[1] / ztr;
+            ztr = o[1];
+            GRID_STRIDE(j, n) p[j] = fma(p[j], beta, r[j] * __ldg(c.Mn + j));
+            grid_sync(grid);
+        }
+    }
+    GRID_STRIDE(j, n) bx[j] = x[j];
+    grid_sync(grid);
+    its_out = its;
+    res_out = rinf;
+}
+
+// solve_qcp_linsys with the n-space PCG (qcp_config.c:826-881): b_x += A'(b_y / rho_y); PCG on x; b_y = (b_y - A x) / rho_y.
+// Tolerance: rtol * |b_x|_inf of the reduced right-hand side (the reference passes error_ratio there by mistake, :852-855).
+__device__ __forceinline__ void dev_solve_nspace(const QcpCtx& c, Reducer& R, cg::grid_group& grid, double* vec, const double* warm_x,
+                                                 double rtol, long max_iter, int& its, double& res) {
+    const int m = c.m;
+    double* by = vec;
+    double* bx = vec + m;
+    GRID_STRIDE(i, m) c.cg_r[i] = by[i] / c.rho_y;
+    grid_sync(grid);
+    double mx[1] = {0.0};
+    spmv_rows(c.AT, c.cg_r, R.ws, nullptr, [&](int row, double a) {
+        const double v = bx[row] + a;
+        bx[row] = v;
+        mx[0] = fmax(mx[0], fabs(v));
+    });
+    R.block_store_max<1>(mx);
+    grid_sync(grid);
+    R.finish<1, 1u>(mx);
+    const double tol = rtol * fmax(mx[0], 1e-300);
+    dev_qcp_pcg_nspace(c, R, grid, bx, warm_x, tol, max_iter, its, res);
+    spmv_rows(c.A, bx, R.ws, nullptr, [&](int row, double a) { by[row] = (by[row] - a) / c.rho_y; });
+    grid_sync(grid);
 }
 
 struct QcpSolveOut {
@@ -271,6 +400,7 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_qcp_iter(Qcp
         c.mu[i] = mui;
         p[i] = mui;
         if (i < m) c.warm[i] = fma(utau, __ldg(c.r + i), ui);
+        else if (c.use_nspace) c.hb[i - m] = fma(utau, __ldg(c.r + i), ui);  // x warm start u_x + tau r_x (abip.c:207-209)
         s1[0] = fma(__ldg(c.r + i), mui, s1[0]);
     }
     R.block_store<1>(s1);
@@ -278,7 +408,13 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_qcp_iter(Qcp
     R.finish<1>(s1);
     const double r_mu = s1[0];
     QcpSolveOut so;
-    dev_qcp_solve(c, R, grid, p, c.warm, c.rtol, so);
+    if (c.use_nspace) {
+        so.inner = 0;
+        so.tol = c.rtol;
+        dev_solve_nspace(c, R, grid, p, c.hb, c.rtol, (long)c.n, so.its, so.res);
+    } else {
+        dev_qcp_solve(c, R, grid, p, c.warm, c.rtol, so);
+    }
     // tau~ from a tau^2 + b tau + c = 0 (abip.c:228-246)
     double s2[2] = {0.0, 0.0};
     GRID_STRIDE(i, mn) s2[0] = fma(__ldg(c.r + i), (i < m ? c.rho_y : c.rho_x) * p[i], s2[0]);
@@ -488,6 +624,31 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_qcp_iter(Qcp
     }
 }
 
+__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
+    k_qcp_solve_nspace(QcpCtx c, double* vec, const double* warm_x, double rtol, long max_iter) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Reducer R = make_reducer(smem_raw, c.partials);
+    int its;
+    double res;
+    dev_solve_nspace(c, R, grid, vec, warm_x, rtol, max_iter, its, res);
+    R.ws.drain();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        c.sc[ABIPGPU_QSC_CG_ITS] = (double)its;
+        c.sc[ABIPGPU_QSC_INNER_ITS] = 0.0;
+        c.sc[ABIPGPU_QSC_CG_RES] = res;
+    }
+}
+
+// init_qcp_precon (qcp_config.c:754-780): Mn_j = 1 / (sum_i A_ij^2 / rho_y + Q_jj + rho_x); AT = CSR(A') (rows = columns of A)
+__global__ void k_qcp_mn(Csr AT, const double* Hd, double rho_y, double* Mn) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= AT.nrows) return;
+    double s = 0.0;
+    for (int k = AT.ptr[j]; k < AT.ptr[j + 1]; ++k) s = fma(AT.val[k], AT.val[k], s);
+    Mn[j] = 1.0 / (s / rho_y + Hd[j]);
+}
+
 // pre_calculate (abip.c:886-910): r = K^-1 [-b; c] (tight tolerance), a = rho_tau + r'(rho o r)
 __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_qcp_precalc(QcpCtx c, double* rvec) {
     cg::grid_group grid = cg::this_grid();
@@ -594,10 +755,11 @@ static int qcp_create_impl(abipgpu_qcp* e, int m, int n, const int* Ap, const in
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
     {
-        int occ[3];
-        const void* ks[3] = {(const void*)k_qcp_iter, (const void*)k_qcp_precalc, (const void*)k_qcp_solve_vec};
+        int occ[4];
+        const void* ks[4] = {(const void*)k_qcp_iter, (const void*)k_qcp_precalc, (const void*)k_qcp_solve_vec,
+                             (const void*)k_qcp_solve_nspace};
         int g = 1 << 30;
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 4; ++i) {
             CK(cudaFuncSetAttribute(ks[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[i], ks[i], kBlock, kSmemBytes));
             if (occ[i] < 1) {
@@ -666,7 +828,7 @@ static int qcp_create_impl(abipgpu_qcp* e, int m, int n, const int* Ap, const in
     double* cg_p = take(Mm); double* cg_r = take(Mm); double* cg_Gp = take(Mm); take(Mm);
     double* dc = take(Nn); double* dE = take(Nn); double* Hd = take(Nn); double* hb = take(Nn);
     double* tn1 = take(Nn); double* tn2 = take(Nn); double* ir = take(Nn); double* ip = take(Nn);
-    double* iHp = take(Nn); take(Nn);
+    double* iHp = take(Nn); double* Mn = take(Nn);
     double* partials = take((size_t)2 * kMaxRed * e->grid + 64);
     double* dsc = take(ABIPGPU_QSC_COUNT);
     CK(cudaMallocHost((void**)&e->hsc, sizeof(double) * ABIPGPU_QSC_COUNT));
@@ -679,8 +841,9 @@ static int qcp_create_impl(abipgpu_qcp* e, int m, int n, const int* Ap, const in
     x.m = m; x.n = n;
     x.A = e->A.view(); x.AT = e->AT.view(); x.Q = e->Q.view();
     x.has_q = e->has_q; x.q_diag = e->q_diag;
-    x.b = db; x.c = dc; x.D = dD; x.E = dE; x.Hd = Hd; x.Ms = Ms; x.r = e->r;
+    x.b = db; x.c = dc; x.D = dD; x.E = dE; x.Hd = Hd; x.Ms = Ms; x.Mn = Mn; x.r = e->r;
     x.rho_y = rho_y; x.rho_x = rho_x; x.rho_tau = rho_tau; x.alpha = alpha; x.a_coef = 0.0; x.rtol = rtol;
+    x.use_nspace = env_int("ABIP_GPU_QCP_NSPACE", 0) != 0 ? 1 : 0;
     x.cone_start = e->d_cone_start; x.cone_dim = e->d_cone_dim; x.cone_kind = e->d_cone_kind;
     x.n_cones = (int)cs.size(); x.cone_vars = pos; x.f_len = f; x.z_len = z; x.l_len = l;
     x.mu = mu; x.p = p; x.warm = warm; x.hb = hb;
@@ -689,6 +852,7 @@ static int qcp_create_impl(abipgpu_qcp* e, int m, int n, const int* Ap, const in
 
     k_qcp_hd<<<(n + 255) / 256, 256, 0, e->stream>>>(x.Q, e->has_q, rho_x, Hd, n);
     k_qcp_ms<<<(m + 255) / 256, 256, 0, e->stream>>>(x.A, Hd, rho_y, Ms);
+    k_qcp_mn<<<(n + 255) / 256, 256, 0, e->stream>>>(x.AT, Hd, rho_y, Mn);
     CK(cudaGetLastError());
     // update_work (abip.c:912-992): initial point
     std::vector<double> u0(e->l, 0.0);
@@ -759,6 +923,18 @@ int abipgpu_qcp_solve_vec(abipgpu_qcp* e, double* host_vec, const double* host_w
     CK(cudaMemcpyAsync(e->ctx.mu, host_vec, sizeof(double) * mn, cudaMemcpyHostToDevice, e->stream));
     if (host_warm) CK(cudaMemcpyAsync(e->ctx.warm, host_warm, sizeof(double) * e->m, cudaMemcpyHostToDevice, e->stream));
     if (qlaunch(e, (const void*)k_qcp_solve_vec, e->ctx, e->ctx.mu, (const double*)(host_warm ? e->ctx.warm : nullptr), rtol))
+        return -1;
+    CK(cudaMemcpyAsync(host_vec, e->ctx.mu, sizeof(double) * mn, cudaMemcpyDeviceToHost, e->stream));
+    return qread_sc(e, sc);
+}
+
+// the reference's n-space path (mat_vec + init_qcp_precon + qcp_pcg + solve_qcp_linsys): vec [m+n] in/out, warm_x [n] or NULL
+int abipgpu_qcp_solve_nspace(abipgpu_qcp* e, double* host_vec, const double* host_warm_x, double rtol, long max_iter, double* sc) {
+    CK(cudaSetDevice(e->device));
+    const int mn = e->m + e->n;
+    CK(cudaMemcpyAsync(e->ctx.mu, host_vec, sizeof(double) * mn, cudaMemcpyHostToDevice, e->stream));
+    if (host_warm_x) CK(cudaMemcpyAsync(e->ctx.hb, host_warm_x, sizeof(double) * e->n, cudaMemcpyHostToDevice, e->stream));
+    if (qlaunch(e, (const void*)k_qcp_solve_nspace, e->ctx, e->ctx.mu, (const double*)(host_warm_x ? e->ctx.hb : nullptr), rtol, max_iter))
         return -1;
     CK(cudaMemcpyAsync(host_vec, e->ctx.mu, sizeof(double) * mn, cudaMemcpyDeviceToHost, e->stream));
     return qread_sc(e, sc);

@@ -211,6 +211,18 @@ class QcpEngine:
             raise RuntimeError("abipgpu_qcp_solve_vec failed")
         return vec, sc
 
+    def solve_nspace(self, vec, warm_x=None, rtol=1e-10, max_iter=None):
+        """solve_qcp_linsys through the reference's n-space qcp_pcg (abipgpu_qcp_solve_nspace)"""
+        vec = np.ascontiguousarray(vec, dtype=np.float64).copy()
+        w = None if warm_x is None else np.ascontiguousarray(warm_x, dtype=np.float64)
+        sc = np.zeros(32)
+        fn = self.L.abipgpu_qcp_solve_nspace
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_long, C.POINTER(C.c_double)]
+        fn.restype = C.c_int
+        if fn(self.e, _dp(vec), _dp(w) if w is not None else None, float(rtol), int(max_iter or 4 * self.n + 50), _dp(sc)) != 0:
+            raise RuntimeError("abipgpu_qcp_solve_nspace failed")
+        return vec, sc
+
     def get(self, name):
         out = np.zeros(self.l if name != "r" else self.m + self.n)
         if self.L.abipgpu_qcp_get_vec(self.e, {"u": 0, "v": 1, "ut": 2, "r": 3}[name], _dp(out), out.size) != 0:

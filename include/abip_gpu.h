@@ -408,6 +408,12 @@ void abipgpu_qcp_destroy(abipgpu_qcp *e);
 int abipgpu_qcp_iter(abipgpu_qcp *e, long k, double mu, double beta, double *sc);
 /* vec (host, m+n) <- K^-1 vec with K = [rho_y I, A; -A', Q + rho_x I]; warm: y warm start (host, m) or NULL */
 int abipgpu_qcp_solve_vec(abipgpu_qcp *e, double *host_vec, const double *host_warm, double rtol, double *sc);
+/* the same solve through the reference's own indirect path, restated on the device: n-space operator mat_vec
+ * (source/linsys.c:725-750), Jacobi preconditioner init_qcp_precon (qcp_config.c:754-780), qcp_pcg (linsys.c:755-851,
+ * |r|_inf stopping rule) inside solve_qcp_linsys (qcp_config.c:826-881).  warm_x: x warm start (host, n) or NULL;
+ * tolerance rtol * |reduced rhs|_inf; sc[ABIPGPU_QSC_CG_ITS] = iterations, sc[ABIPGPU_QSC_CG_RES] = final |r|_inf */
+int abipgpu_qcp_solve_nspace(abipgpu_qcp *e, double *host_vec, const double *host_warm_x, double rtol, long max_iter,
+                             double *sc);
 int abipgpu_qcp_get_vec(abipgpu_qcp *e, int id, double *host, long len); /* 0 u, 1 v, 2 u_t, 3 r */
 int abipgpu_qcp_set_vec(abipgpu_qcp *e, int id, const double *host, long len);
 double abipgpu_qcp_a_coef(const abipgpu_qcp *e);

@@ -137,3 +137,52 @@ def test_abip_entry_dispatches_to_qcp():
     bad["l"] = 5
     x, y, s, info = qcp_solve(dict(A=p.A, Q=p.Q, b=p.b, c=p.c), bad, dict(verbose=0))
     assert info["status_val"] == -4 and np.isnan(x).all()
+
+
+@pytest.mark.parametrize("name", ["toy_qcp", "mixed_cones_q", "socp_noq"])
+def test_reference_nspace_pcg_path(name):
+    """The reference's own indirect path on the device -- mat_vec (source/linsys.c:725-750), init_qcp_precon
+    (qcp_config.c:754-780), qcp_pcg (linsys.c:755-851, |r|_inf stop) inside solve_qcp_linsys (qcp_config.c:826-881) --
+    against the oracle's restatement of the same functions (linsys="pcg"): same iterates for a FIXED number of PCG
+    iterations (the operator is ill-conditioned, cond ~ 1/rho_y: converged solutions agree only loosely), the iteration
+    counts of the stopping rule within one, and the converged solve against the exact factorisation."""
+    p = CASES[name]()
+    st = O.Settings()
+    wd = O.Work(p.A, p.Q, p.b, p.c, p.K, st, "direct")
+    wp = O.Work(p.A, p.Q, p.b, p.c, p.K, st, "pcg", pcg_rtol=1e-9)
+    e = QcpEngine(wd.A, wd.Q, wd.b, wd.c, wd.D, wd.E, p.K, rho_x=st.rho_x, rho_y=st.rho_y, rho_tau=st.rho_tau,
+                  alpha=st.alpha, rtol=1e-10)
+    rng = np.random.default_rng(1)
+    m, n = p.m, p.n
+    for warm in (None, rng.standard_normal(n)):
+        b = rng.standard_normal(m + n)
+        # (a) fixed iteration budget: compare the iterates themselves
+        for iters in (1, 3):
+            ref = b.copy()
+            ref[m:] += wp.A.T @ (ref[:m] / st.rho_y)
+            x0 = None if warm is None else warm.copy()
+            r0 = ref[m:] - (wp.mat_vec(x0) if x0 is not None else 0.0)
+            x = np.zeros(n) if x0 is None else x0.copy()
+            z = r0 * wp.M
+            pp, ztr, r = z.copy(), float(z @ r0), r0.copy()
+            for _ in range(iters):
+                Gp = wp.mat_vec(pp)
+                al = ztr / float(pp @ Gp)
+                x += al * pp
+                r -= al * Gp
+                z = r * wp.M
+                ztr, ztr_prev = float(z @ r), ztr
+                pp = pp * (ztr / ztr_prev) + z
+            got, sc = e.solve_nspace(b, warm, rtol=0.0, max_iter=iters)
+            assert int(sc[0]) == iters
+            assert rel(got[m:], x) < 1e-6, (name, iters, rel(got[m:], x))  # cond ~ 1e6 amplifies rounding
+        # (b) the stopping rule
+        ref = b.copy()
+        its_ref = wp.solve_linsys(ref, None if warm is None else np.concatenate([np.zeros(m), warm]), 0)
+        got, sc = e.solve_nspace(b, warm, rtol=1e-9)
+        # (CG over 100+ iterations at cond ~ 1e6 is sensitive to the summation order: 113 vs 125 on socp_noq)
+        assert abs(int(sc[0]) - its_ref) <= max(2, 0.15 * its_ref), (name, sc[0], its_ref)
+        exact = b.copy()
+        wd.solve_linsys(exact, None, 0)
+        assert rel(got, exact) < 1e-3, (name, rel(got, exact))
+    e.close()
