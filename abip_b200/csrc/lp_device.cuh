@@ -74,6 +74,11 @@ struct Csr {
     const int4* long_rows;   // {row, first piece slot, #pieces, 0}
     double* long_part;       // [#pieces] piece sums (scratch)
     int plan_slot;           // 1 + slot of the per-warp plan cache in shared memory (0: not cached)
+    // shared-memory-resident copy (batches of small LPs, k_batch: one CTA per problem keeps BOTH matrices of its problem in
+    // shared memory for the whole launch: 16-bit column indices); set by the kernel, nullptr otherwise
+    const double* sm_val;
+    const unsigned short* sm_idx;
+    const int* sm_ptr;
 };
 
 // Per-warp staging buffer in shared memory: [val window | idx window | row-ptr window].  The value and index windows
@@ -116,6 +121,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                  "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_inval(unsigned bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
 
 struct WarpSmem {
     unsigned char* base;  // generic pointer to this warp's buffer
@@ -276,6 +282,7 @@ struct Reducer {
 // barrier's fence).  Replaces _accum_by_Atrans (reference linsys/common.c:598-639) for both A and A'.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void spmv_prefetch(const Csr& A, WarpSmem& ws) {
+    if (A.sm_ptr) return;
     int c0, c1;
     int4 d0;
     ws.get_plan(A, c0, c1, d0);
@@ -306,8 +313,32 @@ __device__ unsigned long long g_spmv_prof[16];  // [0..7] matrices with 1 lane/r
 #define SPROF_FLUSH() do { } while (0)
 #endif
 
+// Shared-memory-resident matrix (one CTA owns the whole problem): one thread per row, values / 16-bit indices / row
+// pointers out of shared memory, the gathers of a batch of kL1U nonzeros in flight together, the row summed in its own
+// order (separate multiply and add, like the lane-per-row path below).
+template <class RowFn>
+__device__ __forceinline__ void spmv_rows_resident(const Csr& A, const double* x, RowFn fn) {
+    for (int row = threadIdx.x; row < A.nrows; row += kBlock) {
+        const int a = A.sm_ptr[row], b = A.sm_ptr[row + 1];
+        double acc = 0.0;
+        for (int k0 = a; k0 < b; k0 += kL1U) {
+            double xv[kL1U];
+#pragma unroll
+            for (int u = 0; u < kL1U; ++u) xv[u] = (k0 + u < b) ? x[A.sm_idx[k0 + u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < kL1U; ++u)
+                if (k0 + u < b) acc = __dadd_rn(acc, __dmul_rn(A.sm_val[k0 + u], xv[u]));
+        }
+        fn(row, acc);
+    }
+}
+
 template <class RowFn>
 __device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, WarpSmem& ws, const Csr* next, RowFn fn) {
+    if (A.sm_ptr) {  // uniform over the CTA
+        spmv_rows_resident(A, x, fn);
+        return;
+    }
     const int lane = threadIdx.x & 31;
     const int lg = A.lanes_log2;
     const int L = 1 << lg;
@@ -527,6 +558,16 @@ __device__ __forceinline__ Reducer make_reducer(unsigned char* smem_raw, double*
     R.ws.cur = nullptr;
     R.ws.cur_c = 0;
     return R;
+}
+
+// End of one persistent "body": no copy may be outstanding when the CTA exits, and the warp's mbarrier is invalidated so
+// that a kernel which runs several bodies in a row (k_batch: device-resident loops) may initialise it again
+// (mbarrier.init on a live mbarrier object is undefined).
+__device__ __forceinline__ void release_reducer(Reducer& R) {
+    R.ws.drain();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_inval(R.ws.bar_s);
+    __syncwarp();
 }
 
 // Optional per-phase timing (build with -DABIP_PHASE_TIMING): block 0 / thread 0 accumulates globaltimer deltas per

@@ -1,6 +1,7 @@
 // lp_engine.cu -- persistent cooperative kernels of the ABIP-LP engine and the device-resident step ABI
 // (group (3) of include/abip_gpu.h).  sm_100a only; no cuSPARSE/cuBLAS; no CPU fallback.
 #include "lp_engine.h"
+#include "lp_logic.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -161,7 +162,7 @@ __device__ __forceinline__ void body_admm_iter(const LpCtx& c, const IterArgs& a
     const int has_avg = ((a.j + 1) % 10 == 0) ? 1 : 0;
     dev_qnorm_sums<DIST>(c, R, grid, cs, a.u, a.v, a.half_update, 0, has_avg != 0);
     if (has_avg) dev_qnorm_sums<DIST>(c, R, grid, cs, a.u_avgc, a.v_avgc, a.half_update, 11, false);
-    R.ws.drain();
+    release_reducer(R);  // (drain + mbarrier invalidation: k_batch runs several bodies in one launch)
     grid_sync(grid);
     double t[22];
     if (has_avg) R.finish<22>(t);
@@ -289,7 +290,7 @@ __device__ __forceinline__ void body_bb_round(const LpCtx& c, const BBArgs& a, u
     int its1, its2;
     dev_bb_half<DIST>(c, R, grid, cs, a.u_prev, a.v_prev, a.ut, a.u, a.v, a.k, lam, nullptr, false, its1);
     dev_bb_half<DIST>(c, R, grid, cs, a.u, a.v, a.ut_next, a.u_next, a.v_next, a.k, lam, a.v_prev, true, its2);
-    R.ws.drain();  // no asynchronous copy may be outstanding when the CTA exits
+    release_reducer(R);  // no asynchronous copy may be outstanding when the CTA exits
     if (DIST && VB() == 0 && threadIdx.x == 0) {
         *c.comm.seq = cs.seq;
         c.sc[ABIPGPU_SC_COMM_ERR] = cs.failed ? 1.0 : 0.0;
@@ -438,7 +439,11 @@ __global__ void __launch_bounds__(kBlock) k_mu_stats(const double* u, const doub
 // engine) as block 0 of a one-block virtual grid, then copies the engine's scalar block to the host-mapped output.
 // Replaces one launch + one copy + one synchronisation per problem and step by one launch + one synchronisation per
 // batch and step (the per-context driver lock serialised the per-problem calls at ~13 us each).
-enum { BATCH_ADMM = 0, BATCH_BB = 1, BATCH_MU = 2 };
+enum { BATCH_ADMM = 0, BATCH_BB = 1, BATCH_MU = 2, BATCH_INNER = 3, BATCH_BBSEARCH = 4 };
+struct BBSearchArgs {
+    int lookback;
+    double eps_cor, eps_pen;
+};
 // Deferred vector operations of a batch engine (cold start, outer-iteration prologue, re-initialisation, clamp, BB
 // hand-over, restart copy): the host functions only record them, the next batched step of the problem executes them
 // in order before its own work -- no launch, no copy, no synchronisation of their own (they were ~8 driver calls per
@@ -456,6 +461,9 @@ struct BatchItem {
     IterArgs it;
     BBArgs bb;
     MuArgs mu;
+    LpInnerArgs inner;
+    BBSearchArgs search;
+    int resident_bytes;  // shared memory needed to keep A and A' resident (0: not eligible)
     PreOp pre[kMaxPre];
     double* vec[21];
 };
@@ -524,7 +532,33 @@ __device__ __forceinline__ void apply_pre_ops(const BatchItem& it) {
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_batch(const BatchItem* items, double* sc_out) {
+// Shared-memory-resident matrices of a batch problem: [A: val f64 | A': val f64 | A: ptr i32 | A': ptr i32 | A: idx u16 |
+// A': idx u16] behind the reducer / barrier / plan-cache area (the TMA stages are not used in this mode).
+__host__ __device__ inline size_t resident_bytes_for(long m, long n, long nnz) {
+    return kStageOff + 16 * (size_t)nnz + 4 * (size_t)(m + n + 2) + 4 * (size_t)nnz + 64;
+}
+__device__ __forceinline__ void load_resident(Csr& A, unsigned char*& p) {
+    const int nnz = __ldg(A.ptr + A.nrows);
+    double* v = reinterpret_cast<double*>(p);
+    for (int i = threadIdx.x; i < nnz; i += kBlock) v[i] = __ldg(A.val + i);
+    A.sm_val = v;
+    p += 8 * (size_t)nnz;
+}
+__device__ __forceinline__ void load_resident_ptr(Csr& A, unsigned char*& p) {
+    int* q = reinterpret_cast<int*>(p);
+    for (int i = threadIdx.x; i <= A.nrows; i += kBlock) q[i] = __ldg(A.ptr + i);
+    A.sm_ptr = q;
+    p += 4 * (size_t)(A.nrows + 1);
+}
+__device__ __forceinline__ void load_resident_idx(Csr& A, unsigned char*& p) {
+    const int nnz = __ldg(A.ptr + A.nrows);
+    unsigned short* q = reinterpret_cast<unsigned short*>(p);
+    for (int i = threadIdx.x; i < nnz; i += kBlock) q[i] = (unsigned short)__ldg(A.idx + i);
+    A.sm_idx = q;
+    p += 2 * (size_t)((nnz + 7) & ~7);
+}
+
+__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_batch(const BatchItem* items, double* sc_out, int resident) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(16) BatchItem s_item;
     {
@@ -533,11 +567,103 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_batch(const 
         for (int i = threadIdx.x; i < (int)(sizeof(BatchItem) / sizeof(int)); i += kBlock) dst[i] = src[i];
     }
     __syncthreads();
+    if (resident) {
+        // this launch has the shared memory for it: the CTA copies both matrices of its problem once and every SpMV pass of
+        // every iteration of the step reads them from there (re-streaming 240 KB per CG iteration for 296 problems at once
+        // is what bound the batch: 7 TB/s of HBM traffic)
+        Csr A = s_item.c.A, AT = s_item.c.AT;
+        unsigned char* p = smem_raw + kStageOff;
+        load_resident(A, p);
+        load_resident(AT, p);
+        load_resident_ptr(A, p);
+        load_resident_ptr(AT, p);
+        p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
+        load_resident_idx(A, p);
+        load_resident_idx(AT, p);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_item.c.A = A;
+            s_item.c.AT = AT;
+        }
+        __syncthreads();
+    }
     const BatchItem& it = s_item;
     apply_pre_ops(it);
     if (it.kind == BATCH_ADMM) body_admm_iter<false>(it.c, it.it, smem_raw, true);
     else if (it.kind == BATCH_BB) body_bb_round<false>(it.c, it.bb, smem_raw, true);
-    else body_mu_stats(it.mu.u, it.mu.v, it.c.m, it.c.m + it.c.n + 1, it.c.partials, it.c.sc, it.c.comm, true);
+    else if (it.kind == BATCH_INNER) {
+        // the inner ADMM loop of one outer iteration without leaving the device: every thread of the CTA reads the
+        // scalar block of the iteration and takes the decisions of the host loop (lp_logic.h) redundantly
+        const LpInnerArgs& L = it.inner;
+        IterArgs a = it.it;
+        long j = L.j0, k = L.k0, done = 0;
+        double cg = 0.0;
+        int avg = L.avg_in, code = LP_INNER_CONTINUE;
+        for (;;) {
+            if (k >= L.restart_thresh) { code = LP_INNER_HOST; break; }
+            a.j = j;
+            a.k = k;
+            a.restart_active = 0;
+            a.restart_fire = 0;
+            body_admm_iter<false>(it.c, a, smem_raw, true);
+            __syncthreads();
+            const double* sc = it.c.sc;
+            k += 1;
+            done += 1;
+            cg += sc[ABIPGPU_SC_CG_ITS];
+            const double q = lp_qnorm_decide(sc, (double)L.max_admm_iters, &avg);
+            if (q < L.gamma * L.mu) {
+                if (L.half_update) {  // src/abip.c:2175-2186
+                    double* v = a.v;
+                    for (int i = threadIdx.x; i < it.c.m + it.c.n + 1; i += kBlock)
+                        if (v[i] < 0) v[i] = 1e-6;
+                }
+                code = LP_INNER_CONVERGED;
+                break;
+            }
+            if (L.final_check) {
+                LpResid r;
+                lp_calc_residuals(L.rin, sc, avg, &r);
+                const int status = lp_has_converged(L.eps, L.pfeasopt, &r, L.ipm_iter, k);
+                if (status != 0 || k + 1 >= L.max_admm_iters || L.ipm_iter + 1 >= L.max_ipm_iters) { code = LP_INNER_FINISHED; break; }
+            }
+            ++j;
+            if (j >= L.j_end) { code = LP_INNER_STOPPER; break; }
+            if (done >= L.cap) break;
+            __syncthreads();  // every thread has read the scalar block before the next iteration rewrites it
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            it.c.sc[ABIPGPU_SC_LOOP_EXIT] = (double)code;
+            it.c.sc[ABIPGPU_SC_LOOP_ITERS] = (double)done;
+            it.c.sc[ABIPGPU_SC_LOOP_CG] = cg;
+            it.c.sc[ABIPGPU_SC_LOOP_AVG] = (double)avg;
+        }
+    } else if (it.kind == BATCH_BBSEARCH) {
+        // the whole Barzilai-Borwein search (src/adaptive.c:34-256): lookback rounds + the safeguarded step on the device
+        BBArgs b = it.bb;
+        double beta_prev = 1.0, beta = 0.0, cg = 0.0;
+        int carry = 0, rounds = 0;
+        for (int i = 0; i < it.search.lookback; ++i) {
+            b.carry = carry;
+            b.beta_prev = beta_prev;
+            body_bb_round<false>(it.c, b, smem_raw, true);
+            __syncthreads();
+            const double* sc = it.c.sc;
+            cg += sc[ABIPGPU_SC_CG_ITS] + sc[ABIPGPU_SC_CG_ITS2];
+            ++rounds;
+            const int action = lp_bb_step(sc, it.search.eps_cor, it.search.eps_pen, &beta_prev, &beta);
+            if (action == 0) break;
+            carry = action;
+            __syncthreads();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            it.c.sc[ABIPGPU_SC_LOOP_BETA] = beta;
+            it.c.sc[ABIPGPU_SC_LOOP_CG] = cg;
+            it.c.sc[ABIPGPU_SC_LOOP_ROUNDS] = (double)rounds;
+        }
+    } else body_mu_stats(it.mu.u, it.mu.v, it.c.m, it.c.m + it.c.n + 1, it.c.partials, it.c.sc, it.c.comm, true);
     __syncthreads();
     if (threadIdx.x < ABIPGPU_SC_COUNT) sc_out[(size_t)blockIdx.x * ABIPGPU_SC_COUNT + threadIdx.x] = it.c.sc[threadIdx.x];
 }
@@ -741,6 +867,7 @@ struct ABIPGPU_LP {
     bool permuted = false;                   // locality ordering active: engine index space != caller's
     int *d_rn2o = nullptr, *d_cn2o = nullptr, *d_pl = nullptr;  // new -> old maps: rows [m], columns [n], whole l-space
     double order_ms = 0;
+    int resident_bytes = 0;               // batch engines: shared memory that keeps A and A' resident in k_batch (0: too large)
     double setup_ms[8] = {0};             // host set-up laps: transpose, ordering, permuted CSR, plans, upload, scaling, rest
     double* hsc = nullptr;                   // pinned host scalar block
     bool have_scaling = false;
@@ -852,74 +979,90 @@ struct BatchReq {
     BatchReq() { sem_init(&sem, 0, 0); }
     ~BatchReq() { sem_destroy(&sem); }
 };
+constexpr int kResidentMax = 232448 - 4096;  // 227 KB per CTA on sm_100 minus the static shared memory of k_batch
 struct BatchExec {
     int device = 0;
-    cudaStream_t stream = nullptr;
-    BatchItem* items = nullptr;  // host-mapped pinned memory, read by the kernel
-    double* sc_out = nullptr;    // host-mapped pinned memory, written by the kernel
     int cap = 0;
-    int wait_us = 5000;
+    int wait_us = 200;
+    bool use_resident = true;  // shared-memory-resident matrices when every problem of a launch fits (k_batch)
+    // Launcher slots: each slot is a host thread with its own stream and its own host-mapped item / result buffers.  A
+    // slot takes whatever requests are pending (after a short accumulation window), launches ONE k_batch for them,
+    // synchronises its stream and wakes the owners -- while other slots launch the requests that arrive meanwhile.
+    // With the device-resident loops a step lasts milliseconds and the steps of different problems differ widely (an
+    // inner loop of 48 iterations, a BB search of 3 to 20 rounds): strict lock-step (one launch at a time, everybody
+    // waits for the slowest item) left most CTAs idle (254 LP/s at cfg5 against 331 with one launch per iteration).
+    struct Slot {
+        cudaStream_t stream = nullptr;
+        BatchItem* items = nullptr;  // host-mapped pinned memory, read by the kernel
+        double* sc_out = nullptr;    // host-mapped pinned memory, written by the kernel
+        std::thread th;
+    };
+    std::vector<Slot> slots;
     std::mutex mu;
     std::condition_variable cv_req;
     std::vector<BatchReq*> pending;
     int n_solving = 0;
     bool stop = false;
-    std::thread launcher;
-    long n_launches = 0, n_items = 0;
+    std::atomic<long> n_launches{0}, n_items{0};
     double t_wait_ms = 0, t_kernel_ms = 0;
 
-    // launch as soon as this many requests wait: a fraction of the threads inside a solve (100 %: strict lock-step,
-    // measured best -- 343 LP/s at cfg5 with 296 problems in flight; 50 %: two alternating groups, 315 LP/s)
-    int frac_pct = 100;
-    int threshold() const { return std::max(1, n_solving * frac_pct / 100); }
     int start(int dev, int capacity) {
         device = dev;
         cap = capacity;
-        wait_us = std::max(20, env_int("ABIP_GPU_BATCH_WAIT_US", 5000));
-        frac_pct = std::min(100, std::max(1, env_int("ABIP_GPU_BATCH_FRAC", 100)));
+        wait_us = std::max(0, env_int("ABIP_GPU_BATCH_WAIT_US", 200));
+        use_resident = env_int("ABIP_GPU_BATCH_RESIDENT", 1) != 0;
+        const int nslots = std::max(1, std::min(env_int("ABIP_GPU_BATCH_SLOTS", 6), 32));
         CK(cudaSetDevice(dev));
-        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        CK(cudaHostAlloc((void**)&items, sizeof(BatchItem) * cap, cudaHostAllocMapped));
-        CK(cudaHostAlloc((void**)&sc_out, sizeof(double) * ABIPGPU_SC_COUNT * cap, cudaHostAllocMapped));
-        CK(cudaFuncSetAttribute((const void*)k_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        launcher = std::thread([this] { run(); });
+        CK(cudaFuncSetAttribute((const void*)k_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentMax));
+        slots.resize(nslots);
+        for (Slot& sl : slots) {
+            CK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+            CK(cudaHostAlloc((void**)&sl.items, sizeof(BatchItem) * cap, cudaHostAllocMapped));
+            CK(cudaHostAlloc((void**)&sl.sc_out, sizeof(double) * ABIPGPU_SC_COUNT * cap, cudaHostAllocMapped));
+        }
+        for (int i = 0; i < nslots; ++i) slots[i].th = std::thread([this, i] { run(i); });
         return 0;
     }
-    void run() {
+    void run(int si) {
         cudaSetDevice(device);
+        Slot& sl = slots[si];
         std::vector<BatchReq*> batch;
         std::unique_lock<std::mutex> lk(mu);
-        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-        double t_mark = now();
         for (;;) {
-            // launch when every thread that is inside a solve is waiting; a short timeout keeps the batch moving
-            // while some threads are busy with host work between two steps
-            cv_req.wait_for(lk, std::chrono::microseconds(wait_us),
-                            [&] { return stop || (!pending.empty() && (int)pending.size() >= threshold()); });
+            cv_req.wait(lk, [&] { return stop || !pending.empty(); });
             if (stop && pending.empty()) break;
-            if (pending.empty()) continue;
+            if (wait_us > 0 && (int)pending.size() < std::min(cap, std::max(1, n_solving))) {
+                // accumulation window: more requests usually arrive within a fraction of a millisecond
+                lk.unlock();
+                std::this_thread::sleep_for(std::chrono::microseconds(wait_us));
+                lk.lock();
+                if (pending.empty()) continue;  // another slot took them
+            }
             batch.clear();
             const size_t take = std::min(pending.size(), (size_t)cap);
             batch.assign(pending.begin(), pending.begin() + take);
             pending.erase(pending.begin(), pending.begin() + take);
             lk.unlock();
-            const double t_go = now();
-            t_wait_ms += t_go - t_mark;
             const int n = (int)batch.size();
-            for (int i = 0; i < n; ++i) items[i] = batch[i]->item;
-            k_batch<<<n, kBlock, kSmemBytes, stream>>>(items, sc_out);
+            size_t smem = kSmemBytes;
+            int resident = use_resident ? 1 : 0;
+            for (int i = 0; i < n; ++i) {
+                sl.items[i] = batch[i]->item;
+                const int need = batch[i]->item.resident_bytes;
+                if (need <= 0) resident = 0;
+                else smem = std::max(smem, (size_t)need);
+            }
+            if (!resident) smem = kSmemBytes;
+            k_batch<<<n, kBlock, smem, sl.stream>>>(sl.items, sl.sc_out, resident);
             cudaError_t err = cudaGetLastError();
-            if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
+            if (err == cudaSuccess) err = cudaStreamSynchronize(sl.stream);
             if (err != cudaSuccess) fprintf(stderr, "[abip_gpu] batched step failed: %s\n", cudaGetErrorString(err));
             for (int i = 0; i < n; ++i) {
-                memcpy(batch[i]->e->hsc, sc_out + (size_t)i * ABIPGPU_SC_COUNT, sizeof(double) * ABIPGPU_SC_COUNT);
+                memcpy(batch[i]->e->hsc, sl.sc_out + (size_t)i * ABIPGPU_SC_COUNT, sizeof(double) * ABIPGPU_SC_COUNT);
                 batch[i]->rc = (err == cudaSuccess) ? 0 : -1;
             }
             n_launches++;
             n_items += n;
-            t_mark = now();
-            t_kernel_ms += t_mark - t_go;
-            // (a 4-ary wake-up tree, woken threads waking their children, was measured slower: 185-270 vs 343 LP/s)
             for (int i = 0; i < n; ++i) sem_post(&batch[i]->sem);  // the request may be gone right after this
             lk.lock();
         }
@@ -928,8 +1071,8 @@ struct BatchExec {
         {
             std::lock_guard<std::mutex> lk(mu);
             pending.push_back(r);
-            if ((int)pending.size() >= threshold()) cv_req.notify_one();
         }
+        cv_req.notify_one();
         while (sem_wait(&r->sem) != 0) {
         }
         return r->rc;
@@ -937,22 +1080,24 @@ struct BatchExec {
     void solving(int delta) {
         std::lock_guard<std::mutex> lk(mu);
         n_solving += delta;
-        if (!pending.empty() && (int)pending.size() >= threshold()) cv_req.notify_one();
     }
     void finish() {
         {
             std::lock_guard<std::mutex> lk(mu);
             stop = true;
         }
-        cv_req.notify_one();
-        if (launcher.joinable()) launcher.join();
+        cv_req.notify_all();
+        for (Slot& sl : slots)
+            if (sl.th.joinable()) sl.th.join();
         cudaSetDevice(device);
-        if (stream) {
-            cudaStreamSynchronize(stream);
-            cudaStreamDestroy(stream);
+        for (Slot& sl : slots) {
+            if (sl.stream) {
+                cudaStreamSynchronize(sl.stream);
+                cudaStreamDestroy(sl.stream);
+            }
+            if (sl.items) cudaFreeHost(sl.items);
+            if (sl.sc_out) cudaFreeHost(sl.sc_out);
         }
-        if (items) cudaFreeHost(items);
-        if (sc_out) cudaFreeHost(sc_out);
     }
 };
 static thread_local BatchExec* t_batch = nullptr;  // engines created by this thread join this executor
@@ -981,6 +1126,7 @@ extern "C" void abipgpu_batch_attach(void* b) {
         t_worker_stream = nullptr;
     }
 }
+extern "C" int abipgpu_batch_attached() { return t_batch != nullptr; }
 extern "C" void abipgpu_batch_end(void* b, long* launches, long* items) {
     BatchExec* x = (BatchExec*)b;
     if (!x) return;
@@ -988,8 +1134,8 @@ extern "C" void abipgpu_batch_end(void* b, long* launches, long* items) {
     if (getenv("ABIP_GPU_BATCH_VERBOSE"))
         printf("[abip_gpu] batch executor: %.1f ms waiting for requests, %.1f ms in launches (fill + kernel + sync)\n",
                x->t_wait_ms, x->t_kernel_ms);
-    if (launches) *launches = x->n_launches;
-    if (items) *items = x->n_items;
+    if (launches) *launches = x->n_launches.load();
+    if (items) *items = x->n_items.load();
     delete x;
 }
 static int flush_pending(abipgpu_lp* e);
@@ -1004,6 +1150,7 @@ static int batch_step(abipgpu_lp* e, BatchReq* r, abip_float* sc) {
     for (int q = 0; q < e->n_pend; ++q) r->item.pre[q] = e->pend[q];
     e->n_pend = 0;
     for (int id = 0; id <= 20; ++id) r->item.vec[id] = e->vec[id];
+    r->item.resident_bytes = e->resident_bytes;
     if (e->dirty) {  // copies / memsets / small kernels queued by this thread must have finished
         CK(cudaStreamSynchronize(e->stream));
         e->dirty = false;
@@ -1170,6 +1317,10 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     e->num_sms = prop.multiProcessorCount;
     if (t_batch && t_worker_stream) {  // lock-step batch: one CTA per problem, the worker thread's stream, no events
         e->batch = t_batch;
+        {
+            const size_t need = resident_bytes_for(m, n, nnz);
+            e->resident_bytes = (m < 65536 && n < 65536 && need <= (size_t)kResidentMax) ? (int)need : 0;
+        }
         e->stream = t_worker_stream;
         e->own_stream = false;
         e->dirty = true;
@@ -1409,9 +1560,9 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     c.m = (int)m;
     c.n = (int)n;
     c.A = Csr{e->A_ptr, e->A_idx, e->A_val, (int)m, e->A_wc, e->A_chunk, planA.lanes_log2,
-              e->A_cl, e->A_lr, e->A_lp, 1};
+              e->A_cl, e->A_lr, e->A_lp, 1, nullptr, nullptr, nullptr};
     c.AT = Csr{e->AT_ptr, e->AT_idx, e->AT_val, (int)n, e->AT_wc, e->AT_chunk, planAT.lanes_log2,
-               e->AT_cl, e->AT_lr, e->AT_lp, 2};
+               e->AT_cl, e->AT_lr, e->AT_lp, 2, nullptr, nullptr, nullptr};
     c.M = e->dM;
     c.D = nullptr;
     c.E = nullptr;
@@ -1816,6 +1967,51 @@ int abipgpu_lp_bb_round(abipgpu_lp* e, int carry, abip_int k, abip_float mu, abi
     const double extra = (2 * 6.0 + 2 * 6.0 + (carry ? 4.0 : 0.0)) * e->l * 8.0;
     e->stats.alg_bytes += extra;
     e->stats.alg_bytes_bb += bytes + extra;
+    return 0;
+}
+
+// ---- device-resident loops (batch engines only): one batched step = the inner ADMM loop of an outer iteration (up to
+// L->cap iterations) or a whole Barzilai-Borwein search
+int abipgpu_lp_is_batch(const abipgpu_lp* e) { return e->batch != nullptr; }
+
+static void fill_iter_args(abipgpu_lp* e, IterArgs* a) {
+    a->u = e->vec[ABIPGPU_VEC_U]; a->v = e->vec[ABIPGPU_VEC_V]; a->ut = e->vec[ABIPGPU_VEC_UT];
+    a->u_prev = e->vec[ABIPGPU_VEC_UPREV]; a->u_sum = e->vec[ABIPGPU_VEC_USUM]; a->v_sum = e->vec[ABIPGPU_VEC_VSUM];
+    a->u_avgc = e->vec[ABIPGPU_VEC_UAVGC]; a->v_avgc = e->vec[ABIPGPU_VEC_VAVGC];
+    a->u_avg = e->vec[ABIPGPU_VEC_UAVG]; a->v_avg = e->vec[ABIPGPU_VEC_VAVG];
+    a->half_update = (int)e->stgs.half_update;
+    a->restart_active = 0; a->restart_fire = 0; a->restart_fre = (double)e->stgs.restart_fre;
+}
+
+int abipgpu_lp_inner_loop(abipgpu_lp* e, const LpInnerArgs* L, abip_float* sc) {
+    if (!e->batch) return -1;
+    BatchReq r;
+    r.e = e;
+    r.item.c = e->ctx;
+    r.item.kind = BATCH_INNER;
+    fill_iter_args(e, &r.item.it);
+    r.item.it.j = L->j0; r.item.it.k = L->k0; r.item.it.mu = L->mu; r.item.it.beta = L->beta;
+    r.item.inner = *L;
+    if (batch_step(e, &r, sc)) return -1;
+    e->stats.n_admm_launch++;
+    return 0;
+}
+
+int abipgpu_lp_bb_search(abipgpu_lp* e, abip_int k, abip_float mu, int lookback, abip_float eps_cor, abip_float eps_pen,
+                         abip_float* sc) {
+    if (!e->batch) return -1;
+    BatchReq r;
+    r.e = e;
+    r.item.c = e->ctx;
+    r.item.kind = BATCH_BBSEARCH;
+    BBArgs& a = r.item.bb;
+    a.u_prev = e->vec[ABIPGPU_VEC_BB_UPREV]; a.v_prev = e->vec[ABIPGPU_VEC_BB_VPREV]; a.ut = e->vec[ABIPGPU_VEC_BB_UT];
+    a.u = e->vec[ABIPGPU_VEC_BB_U]; a.v = e->vec[ABIPGPU_VEC_BB_V]; a.ut_next = e->vec[ABIPGPU_VEC_BB_UTNEXT];
+    a.u_next = e->vec[ABIPGPU_VEC_BB_UNEXT]; a.v_next = e->vec[ABIPGPU_VEC_BB_VNEXT];
+    a.carry = 0; a.k = k; a.mu = mu; a.beta_prev = 1.0;
+    r.item.search = BBSearchArgs{lookback, eps_cor, eps_pen};
+    if (batch_step(e, &r, sc)) return -1;
+    e->stats.n_bb_launch++;
     return 0;
 }
 

@@ -11,7 +11,11 @@ int abipgpu_lp_solve_host(abipgpu_lp* e, double* b, const double* s, long iter, 
 ABIPGpuStats* abipgpu_lp_stats(abipgpu_lp* e);
 int abipgpu_lp_dims(const abipgpu_lp* e, int* m, int* n);
 int abipgpu_lp_sync(abipgpu_lp* e);
-void abipgpu_lp_drop_pending(abipgpu_lp* e);  // batch engines: forget deferred vector operations (failed solve)
+void abipgpu_lp_drop_pending(abipgpu_lp* e);
+struct LpInnerArgs;
+extern "C" int abipgpu_lp_is_batch(const abipgpu_lp* e);
+extern "C" int abipgpu_lp_inner_loop(abipgpu_lp* e, const LpInnerArgs* L, abip_float* sc);
+extern "C" int abipgpu_lp_bb_search(abipgpu_lp* e, abip_int k, abip_float mu, int lookback, abip_float eps_cor, abip_float eps_pen, abip_float* sc);  // batch engines: forget deferred vector operations (failed solve)
 int abipgpu_lp_solve_timer(abipgpu_lp* e, int stop);
 extern "C" int abipgpu_lp_comm_export(abipgpu_lp* e, void* handle64);
 extern "C" int abipgpu_lp_comm_connect(abipgpu_lp* e, int G, int rank, const void* handles);
@@ -23,5 +27,6 @@ extern "C" int abipgpu_equilibrate(abip_int m, abip_int n, const abip_int* Ap, c
 // lock-step batch executor (lp_engine.cu: BatchExec)
 extern "C" void* abipgpu_batch_begin(int device, int capacity);
 extern "C" void abipgpu_batch_attach(void* b);
+extern "C" int abipgpu_batch_attached();
 extern "C" void abipgpu_batch_end(void* b, long* launches, long* items);
 void abipgpu_lp_batch_solving(abipgpu_lp* e, int delta);

@@ -4,6 +4,7 @@
 // Each function cites the reference lines whose behaviour it reproduces (paths under src/abip-lp/).
 #include "lp_engine.h"
 #include "order_host.h"
+#include "lp_logic.h"
 #include <thread>
 
 #include <algorithm>
@@ -309,6 +310,7 @@ struct ABIP_GPU_WORK {  // device-resident replacement of struct ABIP_WORK (incl
     double sp = 0;
     abipgpu_lp* eng = nullptr;
     std::vector<double> b, c;  // scaled
+    bool device_loops = false;      // batch engines: inner ADMM loop and BB search run on the device (lp_engine.cu: k_batch)
     std::vector<int> rperm, cperm;  // multi-GPU: locality ordering applied to the host copy of A (new -> old; empty: identity)
     double sigma = 0, gamma = 0, mu = 1, beta = 1;
     int final_check = 0, double_check = 0;
@@ -386,46 +388,24 @@ abip_int failure(abip_int m, abip_int n, ABIPSolution* sol, ABIPInfo* info, abip
     return status;  // (abip_gpu_solve releases the SIGINT listener in its epilogue guard)
 }
 
-// Q-norm criterion from one 13-scalar group (src/abip.c:1972-1992)
-double qnorm_value(const double* g) {
-    const double S_PR = g[0], BTY = g[3], UU_Y = g[4], S_DR = g[5], CTX = g[8], UU_X = g[9], VV = g[10];
-    const double tau = g[11], kap = g[12];
-    const double gap = BTY - CTX - kap;
-    const double Q = S_PR + S_DR + gap * gap;
-    const double nrm = 1 + std::sqrt((UU_Y + UU_X + tau * tau) + (VV + kap * kap));
-    return std::sqrt(Q) / nrm;
+static LpResidIn resid_in(const ABIP_GPU_WORK* w) {
+    return LpResidIn{w->nm_b, w->nm_c, w->sc_b, w->sc_c, w->stgs.scale, (int)w->stgs.normalize};
 }
 
-// calc_residuals (src/abip.c:458-535) evaluated from the sums the ADMM kernel already reduced
+// calc_residuals (src/abip.c:458-535) evaluated from the sums the ADMM kernel already reduced (lp_logic.h)
 void calc_residuals(ABIP_GPU_WORK* w, Resid* r, abip_int ipm_iter, abip_int admm_iter) {
     if (admm_iter && r->last_admm_iter == admm_iter) return;
     r->last_ipm_iter = ipm_iter;
     r->last_admm_iter = admm_iter;
-    const double* g = w->sc + (w->stgs.avg_criterion ? ABIPGPU_SC_AVG_BASE : ABIPGPU_SC_S_PR);
-    const double W_AX = g[1], W_PR = g[2], BTY = g[3], W_ATYS = g[6], W_DR = g[7], CTX = g[8];
-    const bool nz = w->stgs.normalize != 0;
-    const double nrm = nz ? (w->stgs.scale * w->sc_c * w->sc_b) : 1.0;
-    const double sb = nz ? (w->sc_b * w->stgs.scale) : 1.0, scn = nz ? (w->sc_c * w->stgs.scale) : 1.0;
-    r->tau = std::fabs(g[11]);
-    r->kap = std::fabs(g[12]) / nrm;
-    const double nmpr_tau = std::sqrt(W_PR) / sb, nm_A_x_tau = std::sqrt(W_AX) / sb;
-    const double nmdr_tau = std::sqrt(W_DR) / scn, nm_At_ys_tau = std::sqrt(W_ATYS) / scn;
-    r->bt_y_by_tau = BTY / nrm;
-    r->ct_x_by_tau = CTX / nrm;
-    r->res_infeas = r->bt_y_by_tau > 0 ? w->nm_b * nm_At_ys_tau / r->bt_y_by_tau : NAN;
-    r->res_unbdd = r->ct_x_by_tau < 0 ? w->nm_c * nm_A_x_tau / -r->ct_x_by_tau : NAN;
-    const double bt_y = safediv_pos(r->bt_y_by_tau, r->tau), ct_x = safediv_pos(r->ct_x_by_tau, r->tau);
-    r->res_pri = safediv_pos(nmpr_tau / (1 + w->nm_b), r->tau);
-    r->res_dual = safediv_pos(nmdr_tau / (1 + w->nm_c), r->tau);
-    r->rel_gap = std::fabs(ct_x - bt_y) / (1 + std::fabs(ct_x) + std::fabs(bt_y));
+    LpResid q;
+    lp_calc_residuals(resid_in(w), w->sc, (int)w->stgs.avg_criterion, &q);
+    r->res_pri = q.res_pri; r->res_dual = q.res_dual; r->rel_gap = q.rel_gap; r->res_infeas = q.res_infeas;
+    r->res_unbdd = q.res_unbdd; r->ct_x_by_tau = q.ct_x_by_tau; r->bt_y_by_tau = q.bt_y_by_tau; r->tau = q.tau; r->kap = q.kap;
 }
 
 abip_int has_converged(const ABIP_GPU_WORK* w, const Resid* r, abip_int ipm_iter, abip_int admm_iter) {  // :1613-1641
-    const double eps = w->stgs.eps;
-    if (r->res_pri < eps && (r->res_dual < eps || w->stgs.pfeasopt) && r->rel_gap < eps) return ABIP_SOLVED;
-    if (r->res_unbdd < eps && ipm_iter > 0 && admm_iter > 0) return ABIP_UNBOUNDED;
-    if (r->res_infeas < eps && ipm_iter > 0 && admm_iter > 0) return ABIP_INFEASIBLE;
-    return 0;
+    LpResid q{r->res_pri, r->res_dual, r->rel_gap, r->res_infeas, r->res_unbdd, r->ct_x_by_tau, r->bt_y_by_tau, r->tau, r->kap};
+    return lp_has_converged(w->stgs.eps, (int)w->stgs.pfeasopt, &q, (long)ipm_iter, (long)admm_iter);
 }
 
 // table-driven mu rule (src/abip.c:753-921)
@@ -508,37 +488,28 @@ int adaptive_search(ABIP_GPU_WORK* w, abip_int iter) {
     if (s.adaptive_lookback <= 0) return -1;
     const double t0 = now_ms();
     if (abipgpu_lp_bb_begin(w->eng) != 0) return -1;
+    if (w->device_loops && !w->trace) {  // batch engines: the whole search is one batched step (lp_engine.cu: BATCH_BBSEARCH)
+        double scb[ABIPGPU_SC_COUNT];
+        if (abipgpu_lp_bb_search(w->eng, iter, w->mu, (int)s.adaptive_lookback, s.eps_cor, s.eps_pen, scb) != 0) return -1;
+        w->tot_cg_its += (abip_int)scb[ABIPGPU_SC_LOOP_CG];
+        w->beta = scb[ABIPGPU_SC_LOOP_BETA];
+        w->total_adapt_ms += now_ms() - t0;
+        return 0;
+    }
     double beta_prev = 1.0, beta = 0.0;
     int carry = 0;
     double sc[ABIPGPU_SC_COUNT];
     for (abip_int i = 0; i < s.adaptive_lookback; ++i) {
         if (abipgpu_lp_bb_round(w->eng, carry, iter, w->mu, beta_prev, sc) != 0) return -1;
         w->tot_cg_its += (abip_int)(sc[ABIPGPU_SC_CG_ITS] + sc[ABIPGPU_SC_CG_ITS2]);
-        const double utut = sc[ABIPGPU_SC_BB_UTUT], utv = sc[ABIPGPU_SC_BB_UTV], uu = sc[ABIPGPU_SC_BB_UU],
-                     vv = sc[ABIPGPU_SC_BB_VV], uv = sc[ABIPGPU_SC_BB_UV];
-        const double norm_ut = std::sqrt(utut), norm_u = std::sqrt(uu), norm_v = std::sqrt(vv);
-        const double alpha_SD = vv / utv, alpha_MG = utv / utut, gamma_SD = vv / uv, gamma_MG = uv / uu;
-        const double alpha_ss = (2 * alpha_MG > alpha_SD) ? alpha_MG : alpha_SD - 0.5 * alpha_MG;
-        const double gamma_ss = (2 * gamma_MG > gamma_SD) ? gamma_MG : gamma_SD - 0.5 * gamma_MG;
-        const double alpha_cor = utv / (norm_v * norm_ut), gamma_cor = uv / (norm_v * norm_u);
-        if (alpha_cor > s.eps_cor && gamma_cor > s.eps_cor) beta = std::sqrt(alpha_ss * gamma_ss);
-        else if (alpha_cor > s.eps_cor && gamma_cor <= s.eps_cor) beta = alpha_ss;
-        else if (alpha_cor <= s.eps_cor && gamma_cor > s.eps_cor) beta = gamma_ss;
-        else beta = beta_prev;
-        const double diff = std::fabs(beta - beta_prev);
+        const double bp_before = beta_prev;
+        const int action = lp_bb_step(sc, s.eps_cor, s.eps_pen, &beta_prev, &beta);
         if (w->trace)
             fprintf(w->trace, "bbround %ld carry %d beta_prev %.17g beta %.17g dots %.10e %.10e %.10e %.10e %.10e cg %d %d\n",
-                    (long)i, carry, beta_prev, beta, utut, utv, uu, vv, uv, (int)sc[ABIPGPU_SC_CG_ITS],
-                    (int)sc[ABIPGPU_SC_CG_ITS2]);
-        if (diff > 0 && diff <= s.eps_pen) {
-            beta = (beta + beta_prev) / 2;
-            break;
-        } else if (diff > s.eps_pen) {
-            beta_prev = beta;
-            carry = 1;  // u_prev = u; v_prev = [v_y; (mu/beta)/u_x]   (:230-242), applied by the next launch
-        } else {
-            carry = 2;  // u_prev = u; v_prev = v                      (:243-247)
-        }
+                    (long)i, carry, bp_before, beta, sc[ABIPGPU_SC_BB_UTUT], sc[ABIPGPU_SC_BB_UTV], sc[ABIPGPU_SC_BB_UU],
+                    sc[ABIPGPU_SC_BB_VV], sc[ABIPGPU_SC_BB_UV], (int)sc[ABIPGPU_SC_CG_ITS], (int)sc[ABIPGPU_SC_CG_ITS2]);
+        if (action == 0) break;
+        carry = action;  // 1: u_prev = u; v_prev = [v_y; (mu/beta)/u_x] (:230-242); 2: u_prev = u; v_prev = v (:243-247)
     }
     w->beta = beta;
     w->total_adapt_ms += now_ms() - t0;
@@ -800,7 +771,10 @@ static ABIPGpuWork* gpu_init_impl(const ABIPData* d, ABIPInfo* info, int rank, i
     w->dist_rank = rank;
     w->c0 = 0;
     w->nl = w->n;
-    const bool host_scaling = G > 1 || getenv("ABIP_GPU_HOST_SCALING") != nullptr;
+    // batches of small LPs equilibrate on the host: the device version costs ~100 driver calls per problem (40 tiny
+    // launches), which serialise on the context lock and were 2/3 of the wall time of a batch; on the host it is a
+    // fraction of a millisecond per problem and runs in parallel over the worker threads (results are bit-identical)
+    const bool host_scaling = G > 1 || abipgpu_batch_attached() || getenv("ABIP_GPU_HOST_SCALING") != nullptr;
     if (!host_scaling) {
         // single GPU: the caller's matrix goes to the device as it is and is equilibrated there (bit-identical to
         // abip_normalize_A); the host keeps only D and E
@@ -939,6 +913,7 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
     } solve_epilogue{w, st};
     w->tot_cg_its = 0;
     w->total_adapt_ms = 0;
+    w->device_loops = abipgpu_lp_is_batch(w->eng) != 0 && getenv("ABIP_GPU_BATCH_HOST_LOOPS") == nullptr;
 
     // ---- update_work (abip.c:1843-1927) ----
     w->nm_b = norm2(d->b, m);
@@ -1003,19 +978,57 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
         if (abipgpu_lp_outer_prologue(w->eng, (int)s.avg_criterion) != 0)
             return failure(m, n, sol, info, ABIP_FAILED, "error in outer prologue", "Failure");
 
-        for (abip_int j = 0; j < inner_stopper; ++j) {  // inner loop: one kernel launch per iteration
+        // a solve is over inside the inner loop when final_check finds convergence or an iteration limit (abip.c:2190-2211)
+        auto finish_in_loop = [&](abip_int kk) -> abip_int {
+            if (s.verbose && kk > 0) print_summary(w, i, kk, &r, t0);
+            if (get_solution(w, sol, info, &r, i, kk) != 0)
+                return failure(m, n, sol, info, ABIP_FAILED, "error in get_solution", "Failure");
+            info->solve_time = now_ms() - t0;
+            if (s.verbose) print_footer(w, info);
+            return info->status_val;
+        };
+        for (abip_int j = 0; j < inner_stopper;) {  // inner loop
+            if (w->device_loops && !trace) {
+                // batch engines: up to `cap` iterations per batched step, decisions taken on the device (lp_logic.h)
+                LpInnerArgs L;
+                L.j0 = j; L.k0 = k; L.j_end = inner_stopper; L.cap = 48;
+                L.max_admm_iters = s.max_admm_iters; L.max_ipm_iters = s.max_ipm_iters; L.ipm_iter = i;
+                L.restart_thresh = s.restart_thresh;
+                L.mu = w->mu; L.beta = w->beta; L.gamma = w->gamma; L.eps = s.eps;
+                L.final_check = w->final_check; L.pfeasopt = (int)s.pfeasopt; L.half_update = (int)s.half_update;
+                L.avg_in = (int)s.avg_criterion;
+                L.rin = resid_in(w);
+                if (abipgpu_lp_inner_loop(w->eng, &L, w->sc) != 0)
+                    return failure(m, n, sol, info, ABIP_FAILED, "error in project_lin_sys", "Failure");
+                const abip_int done = (abip_int)w->sc[ABIPGPU_SC_LOOP_ITERS];
+                const int code = (int)w->sc[ABIPGPU_SC_LOOP_EXIT];
+                k += done;
+                w->tot_cg_its += (abip_int)w->sc[ABIPGPU_SC_LOOP_CG];
+                s.avg_criterion = (abip_int)w->sc[ABIPGPU_SC_LOOP_AVG];
+                if (g_interrupted) return failure(m, n, sol, info, ABIP_SIGINT, "Interrupted", "Interrupted");
+                if (code == LP_INNER_HOST) {  // restart bookkeeping ahead: single steps from here on
+                    w->device_loops = false;
+                    j += done;
+                    continue;
+                }
+                if (code == LP_INNER_CONVERGED) break;
+                if (code == LP_INNER_FINISHED) {
+                    calc_residuals(w, &r, i, k);
+                    info->status_val = has_converged(w, &r, i, k);
+                    return finish_in_loop(k);
+                }
+                j += done;
+                continue;  // LP_INNER_STOPPER ends the loop through its condition, LP_INNER_CONTINUE goes on
+            }
             if (abipgpu_lp_admm_iter(w->eng, j, k, w->mu, w->beta, w->sc) != 0)
                 return failure(m, n, sol, info, ABIP_FAILED, "error in project_lin_sys", "Failure");
             w->tot_cg_its += (abip_int)w->sc[ABIPGPU_SC_CG_ITS];
             if (g_interrupted) return failure(m, n, sol, info, ABIP_SIGINT, "Interrupted", "Interrupted");
             k += 1;
             // iterate_Q_norm_resd decision (abip.c:2040-2050)
-            const double q_cur = qnorm_value(w->sc + ABIPGPU_SC_S_PR);
-            const double q_avg = w->sc[ABIPGPU_SC_HAS_AVG] != 0 ? qnorm_value(w->sc + ABIPGPU_SC_AVG_BASE)
-                                                                 : std::sqrt((double)s.max_admm_iters) / 1.0;
-            double q;
-            if (q_avg < q_cur) { s.avg_criterion = 1; q = q_avg; }
-            else { s.avg_criterion = 0; q = q_cur; }
+            int avg_c = 0;
+            const double q = lp_qnorm_decide(w->sc, (double)s.max_admm_iters, &avg_c);
+            s.avg_criterion = avg_c;
             if (trace)
                 fprintf(trace, "it %ld %ld %ld %.17g %.17g %d %.17g %d\n", (long)i, (long)j, (long)k, w->mu, w->beta,
                         (int)w->sc[ABIPGPU_SC_CG_ITS], q, (int)s.avg_criterion);
@@ -1027,15 +1040,9 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
             if (w->final_check) {
                 calc_residuals(w, &r, i, k);
                 info->status_val = has_converged(w, &r, i, k);
-                if (info->status_val != 0 || k + 1 >= s.max_admm_iters || i + 1 >= s.max_ipm_iters) {
-                    if (s.verbose && k > 0) print_summary(w, i, k, &r, t0);
-                    if (get_solution(w, sol, info, &r, i, k) != 0)
-                        return failure(m, n, sol, info, ABIP_FAILED, "error in get_solution", "Failure");
-                    info->solve_time = now_ms() - t0;
-                    if (s.verbose) print_footer(w, info);
-                    return info->status_val;
-                }
+                if (info->status_val != 0 || k + 1 >= s.max_admm_iters || i + 1 >= s.max_ipm_iters) return finish_in_loop(k);
             }
+            ++j;
         }
         if ((now_ms() - t0) / 1e3 > max_time) {  // wall clock; the reference uses clock() CPU time (trap 9)
             printf("Timelimit reached. \n");

@@ -276,7 +276,7 @@ struct DevCsr {
     int nrows = 0;
     long nnz = 0;
     Csr view() const {
-        return Csr{ptr, idx, val, nrows, wc, chunk, plan.lanes_log2, cta_long, long_rows, long_part, 0};
+        return Csr{ptr, idx, val, nrows, wc, chunk, plan.lanes_log2, cta_long, long_rows, long_part, 0, nullptr, nullptr, nullptr};
     }
     void release(cudaStream_t s = nullptr) {
         dev_free(ptr, s); dev_free(idx, s); dev_free(wc, s); dev_free(chunk, s); dev_free(val, s);

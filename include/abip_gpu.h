@@ -243,6 +243,9 @@ enum {
     /* mu statistics: abip.c:957-960 */
     ABIPGPU_SC_MIN_XS = 48, ABIPGPU_SC_SUM_XS = 49,
     ABIPGPU_SC_VEC_NORM2 = 50,
+    /* device-resident loops of the batch kernel (abipgpu_lp_inner_loop / abipgpu_lp_bb_search) */
+    ABIPGPU_SC_LOOP_EXIT = 51, ABIPGPU_SC_LOOP_ITERS = 52, ABIPGPU_SC_LOOP_CG = 53, ABIPGPU_SC_LOOP_AVG = 54,
+    ABIPGPU_SC_LOOP_BETA = 56, ABIPGPU_SC_LOOP_ROUNDS = 57,
     ABIPGPU_SC_COMM_ERR = 63, /* multi-GPU: a peer did not answer within the spin limit */
     ABIPGPU_SC_COUNT = 64
 };
