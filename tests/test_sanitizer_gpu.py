@@ -14,13 +14,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SAN = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
 
 
-@pytest.mark.skipif(not os.path.exists(SAN), reason="compute-sanitizer not installed")
 # racecheck on the single-problem engine does not finish: it serialises the warps, and the persistent cooperative kernel
 # spins in grid barriers (measured: > 15 min for a 0.1 s solve).  It is therefore run on the one-CTA batch kernel only,
 # where the grid barrier degenerates to a CTA barrier, and only on request (ABIP_RACECHECK=1).
 CASES = [("memcheck", "single"), ("memcheck", "batch")] + ([("racecheck", "batch")] if os.environ.get("ABIP_RACECHECK") else [])
 
 
+@pytest.mark.skipif(not os.path.exists(SAN), reason="compute-sanitizer not installed")
 @pytest.mark.parametrize("tool,mode", CASES)
 def test_compute_sanitizer_clean(tool, mode):
     cmd = [SAN, "--tool", tool, "--error-exitcode", "77", sys.executable, os.path.join(ROOT, "tools", "sanitize_target.py"), mode]
