@@ -45,16 +45,21 @@ def assemble_shards(local: np.ndarray, group=None) -> np.ndarray:
     return t.cpu().numpy()
 
 
-# Below this many nonzeros per GPU the exchange of the m-vector (two cross-GPU flag round trips + NVLink transfers per
-# operator application) costs more than the local SpMV it saves: measured at cfg2 (5.0 M nonzeros) 1.02x on 2 GPUs but
-# 0.74x / 0.70x on 4 / 8 (SCALE_r01), at cfg4 (60.5 M) 1.7x on 2 (profiles/r02_multi_gpu.md).  A solver asked to use more
-# GPUs than that shards over the first `effective_world` ranks only; the others hold no engine and contribute zeros.
-MIN_NNZ_PER_GPU = 2_400_000
+# Where sharding is refused (measured, profiles/r02_multi_gpu.md):
+#   * below MIN_NNZ_PER_GPU nonzeros per GPU the exchange of the m-vector (two cross-GPU flag round trips + NVLink
+#     transfers per operator application) costs as much as the local SpMV it saves: cfg2 (5.0 M nonzeros) runs at
+#     0.98x - 1.02x on 2 GPUs and 0.74x / 0.70x on 4 / 8 (SCALE_r01), so it stays on one GPU;
+#   * beyond MAX_SHARD_GPUS the in-kernel reduce-scatter + all-gather stops paying: cfg4 (60.5 M nonzeros) 1.70x on 2 GPUs,
+#     2.37x on 4, but 1.24x on 8.
+# A solver asked to use more GPUs than that shards over the first `effective_world` ranks only; the others hold no engine
+# and contribute zeros to the assembly of x and s.
+MIN_NNZ_PER_GPU = 4_000_000
+MAX_SHARD_GPUS = 4
 
 
 def effective_world(nnz: int, world: int, min_nnz_per_gpu: int | None = None) -> int:
     lim = MIN_NNZ_PER_GPU if min_nnz_per_gpu is None else min_nnz_per_gpu
-    return max(1, min(world, nnz // max(1, lim)))
+    return max(1, min(world, MAX_SHARD_GPUS if min_nnz_per_gpu is None else world, nnz // max(1, lim)))
 
 
 class LpSolverDist:
@@ -89,14 +94,15 @@ class LpSolverDist:
         self.w = self.L.abip_gpu_init_dist(C.byref(self.d), C.byref(self.info), self.rank, self.world)
         if not self.w:
             raise RuntimeError("abip_gpu_init_dist failed")
-        buf = (C.c_ubyte * 64)()
-        if self.L.abip_gpu_comm_export(self.w, C.cast(buf, C.c_void_p)) != 0:
-            raise RuntimeError("abip_gpu_comm_export failed")
-        allh = exchange_handles(bytes(buf), group)
-        hb = (C.c_ubyte * len(allh)).from_buffer_copy(allh)
-        if self.L.abip_gpu_comm_connect(self.w, C.cast(hb, C.c_void_p)) != 0:
-            raise RuntimeError("abip_gpu_comm_connect failed")
-        dist.barrier(group)  # every rank has mapped every buffer before the first kernel spins on a flag
+        if self.world > 1:
+            buf = (C.c_ubyte * 64)()
+            if self.L.abip_gpu_comm_export(self.w, C.cast(buf, C.c_void_p)) != 0:
+                raise RuntimeError("abip_gpu_comm_export failed")
+            allh = exchange_handles(bytes(buf), group)
+            hb = (C.c_ubyte * len(allh)).from_buffer_copy(allh)
+            if self.L.abip_gpu_comm_connect(self.w, C.cast(hb, C.c_void_p)) != 0:
+                raise RuntimeError("abip_gpu_comm_connect failed")
+            dist.barrier(group)  # every rank has mapped every buffer before the first kernel spins on a flag
         self.setup_time_ms = self.info.setup_time
         self._libc = C.CDLL(None)
         self._libc.free.argtypes = [C.c_void_p]
