@@ -403,7 +403,9 @@ def run_ours(args):
         barrier()
         ds.close()
         sh_ms = allmax(sh_ms)
-        out = {"workload": f"{label} as ONE instance, column blocks of A over {world} GPUs",
+        used = si.get("gpus_used", world)
+        out = {"workload": f"{label} as ONE instance: {world} GPUs offered, {used} used (column blocks of A; abip_b200/dist.py refuses to "
+                           f"shard below {4_000_000:,} nonzeros per GPU or over more than 4 GPUs, see profiles/r02_multi_gpu.md)",
                "value": sh_its / (sh_ms / 1e3), "unit": "iter/s", "scaling": "strong",
                "time_to_1e-4_s": sh_ms / nst / 1e3, "setup_s": setup_s, "status": si["status"],
                "admm_iter_per_solve": sh_its / nst, "gpus_used": si.get("gpus_used", world),
