@@ -126,6 +126,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+L2_NOTE = ("GPU arm: 256 MiB buffer written between timed steps (L2 flush), matrices (120 MB) ~ L2 size; "
+           "reference (CPU) arm: not applicable")
+
+
+def bench_config(name):
+    """identical in both arms (the driver compares the `config` objects)"""
+    return {"workload": name, "l2": L2_NOTE}
+
+
 def workload(args):
     from abip_b200 import problems
     p = problems.cfg2(seed=2, scale=args.scale)
@@ -217,7 +226,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "ADMM iters/sec", "value": value, "unit": "iter/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(per_step)),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name},
+            "config": bench_config(name),
             "cpu_baseline": {"value": value, "unit": "iter/s", "cores": cores, "kind": "reference", "sample": sample,
                              "full_solve_fixture": _full_solve_fixture()},
             "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -529,12 +538,11 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": event_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name,
-                       "per_gpu": "the same instance on every GPU (replicas, no collective)" if world > 1 else "single instance",
-                       "l2": "256 MiB buffer written between timed steps (L2 flush); matrices (120 MB) ~ L2 size",
-                       "status": last["status"], "admm_iter_per_solve": its / args.steps,
-                       "ipm_iter": last["ipm_iter"], "pres": last["pres"], "dres": last["dres"], "gap": last["gap"],
-                       "pobj": last["pobj"]},
+            "config": bench_config(name),
+            "run": {"per_gpu": "the same instance on every GPU (replicas, no collective)" if world > 1 else "single instance",
+                    "status": last["status"], "admm_iter_per_solve": its / args.steps,
+                    "ipm_iter": last["ipm_iter"], "pres": last["pres"], "dres": last["dres"], "gap": last["gap"],
+                    "pobj": last["pobj"]},
             "time_to_1e-4_s": event_ms_max / args.steps / 1e3,
             "host_wall_s_per_step": wall / args.steps,
             "clocks": clocks,
