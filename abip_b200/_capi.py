@@ -73,10 +73,10 @@ DECLARED_SYMBOLS = [
     "abipgpu_lp_create", "abipgpu_lp_create_scaling", "abipgpu_lp_destroy", "abipgpu_lp_set_problem", "abipgpu_lp_cold_start",
     "abipgpu_lp_outer_prologue", "abipgpu_lp_admm_iter", "abipgpu_lp_mu_stats", "abipgpu_lp_reinit",
     "abipgpu_lp_clamp_v", "abipgpu_lp_bb_begin", "abipgpu_lp_bb_round", "abipgpu_lp_solve_vec", "abipgpu_lp_get_vec",
-    "abipgpu_lp_set_vec", "abipgpu_lp_g_th", "abipgpu_lp_spmv", "abipgpu_lp_describe", "abipgpu_plan_debug",
+    "abipgpu_lp_set_vec", "abipgpu_lp_g_th", "abipgpu_lp_spmv", "abipgpu_lp_describe", "abipgpu_plan_debug", "abipgpu_plan_debug_cost",
     # ABIP-QCP (bound in abip_b200/qcp.py)
     "abip_qcp_gpu_set_default_settings", "abip_qcp_gpu", "abip_qcp_gpu_last_counters", "abip_qcp_scale_data",
-    "abipgpu_qcp_create", "abipgpu_qcp_destroy", "abipgpu_qcp_iter", "abipgpu_qcp_solve_vec", "abipgpu_qcp_get_vec",
+    "abipgpu_qcp_create", "abipgpu_qcp_destroy", "abipgpu_qcp_iter", "abipgpu_qcp_solve_vec", "abipgpu_qcp_solve_nspace", "abipgpu_qcp_get_vec",
     "abipgpu_qcp_set_vec", "abipgpu_qcp_a_coef", "abipgpu_qcp_counters",
 ]
 

@@ -365,8 +365,8 @@ class LpEngine:
         return y
 
     def describe(self):
-        buf = C.create_string_buffer(512)
-        self.L.abipgpu_lp_describe(self.e, buf, 512)
+        buf = C.create_string_buffer(1280)
+        self.L.abipgpu_lp_describe(self.e, buf, 1280)
         return buf.value.decode()
 
     def close(self):

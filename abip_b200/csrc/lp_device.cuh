@@ -116,9 +116,23 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+#ifndef ABIP_TMA_L2_HINT
+#define ABIP_TMA_L2_HINT 0  // 1: evict_first, 2: evict_last policy on the matrix stream (experiment, profiles/r02_spmv.md)
+#endif
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+#if ABIP_TMA_L2_HINT
+    unsigned long long pol;
+#if ABIP_TMA_L2_HINT == 1
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#else
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#endif
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar) : "memory");
+#endif
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_inval(unsigned bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }

@@ -92,6 +92,13 @@ __device__ __forceinline__ void body_admm_iter(const LpCtx& c, const IterArgs& a
     CommState cs{DIST ? *c.comm.seq : 0ull, false};
     const int m = c.m, lm1 = c.m + c.n, l = lm1 + 1;
 
+#ifdef ABIP_PHASE_TIMING
+    if (threadIdx.x == 0 && c.phase_ns) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        c.phase_ns[32 + 2 * VG() * kWarps + VB()] = (double)smid;
+    }
+#endif
     PHASE_START(tk);
     dev_build_rhs<DIST>(c, R, grid, cs, a.u, a.v, a.ut, a.u_prev);
     PHASE_MARK(c, tk, 0);
@@ -351,6 +358,67 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
     Reducer R = make_reducer(smem_raw, nullptr);
     spmv_rows(A, x, R.ws, nullptr, [&](int row, double a) { y[row] = accumulate ? y[row] + a : a; });
     R.ws.drain();
+}
+
+// Measured balance (tune_balance() below): `reps` iterations of the two SpMV passes of the PCG loop (A' then A with the
+// seven-sum epilogue, then the vector update, same barriers) on the engine's own matrices; every CTA reports the SM cycles
+// between the start of a pass and the moment its last warp has finished its rows.  The first iteration is a warm-up.
+// The PCG workspace it runs on is all zeros (alpha = 0 keeps it so); only the timing matters.
+__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_tune(LpCtx c, double* t_out /* [3][G] */, int reps) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Reducer R = make_reducer(smem_raw, c.partials);
+    const int m = c.m;
+    long long acc_at = 0, acc_a = 0;
+    double sink = 0.0;
+    spmv_prefetch(c.AT, R.ws);
+    grid_sync(grid);
+    for (int rep = 0; rep < reps; ++rep) {
+        const long long t0 = clock64();
+        spmv_rows(c.AT, c.p, R.ws, &c.A, [&](int row, double a) { c.tmp[row] = a; });
+        __syncthreads();
+        const long long t1 = clock64();
+        grid_sync(grid);
+        double d[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        const long long t2 = clock64();
+        spmv_rows(c.A, c.tmp, R.ws, &c.AT, [&](int row, double a) {
+            const double pi = c.p[row], ri = c.r[row], Mi = __ldg(c.M + row);
+            const double gp = fma(c.rho_y, pi, a);
+            c.Gp[row] = gp;
+            const double zi = Mi * ri, mg = Mi * gp;
+            d[0] = fma(pi, gp, d[0]);
+            d[1] = fma(zi, gp, d[1]);
+            d[2] = fma(mg, gp, d[2]);
+            d[3] = fma(ri, gp, d[3]);
+            d[4] = fma(gp, gp, d[4]);
+            d[5] = fma(zi, ri, d[5]);
+            d[6] = fma(ri, ri, d[6]);
+        });
+        __syncthreads();
+        const long long t3 = clock64();
+        R.block_store<7>(d);
+        grid_sync(grid);
+        R.finish<7>(d);
+        sink += d[0] + d[1] + d[2] + d[3] + d[4] + d[5] + d[6];
+        const double alpha = 0.0 * sink;
+        GRID_STRIDE(i, m) {
+            const double pi = c.p[i];
+            const double ri = fma(-alpha, c.Gp[i], c.r[i]);
+            c.r[i] = ri;
+            c.p[i] = fma(1.0, pi, alpha * (__ldg(c.M + i) * ri));
+        }
+        grid_sync(grid);
+        if (rep > 0) {
+            acc_at += t1 - t0;
+            acc_a += t3 - t2;
+        }
+    }
+    release_reducer(R);
+    if (threadIdx.x == 0) {
+        t_out[VB()] = (double)acc_at;
+        t_out[VG() + VB()] = (double)acc_a;
+        t_out[2 * VG() + VB()] = sink;
+    }
 }
 
 // min / sum of u_i v_i over the (x, tau) tail: update_barrier_dynamic, src/abip.c:957-960
@@ -848,6 +916,10 @@ struct ABIPGPU_LP {
     // matrix
     int *A_ptr = nullptr, *A_idx = nullptr, *AT_ptr = nullptr, *AT_idx = nullptr, *A_wc = nullptr, *AT_wc = nullptr;
     unsigned char* arena = nullptr;              // all matrix / plan arrays live in this one allocation
+    unsigned char* plan_arena = nullptr;         // plan arrays after the measured balance (tune_balance)
+    double tune_ms = 0;                          // host time of the measured balance
+    double tune_first_us[2] = {0, 0}, tune_best_us[2] = {0, 0};  // slowest CTA per pass (A', A): structural plan / chosen plan
+    int tune_rounds = 0, tune_best_round = 0;
     int *A_cl = nullptr, *AT_cl = nullptr;       // long-row tables
     int4 *A_lr = nullptr, *AT_lr = nullptr;
     double *A_lp = nullptr, *AT_lp = nullptr;
@@ -875,7 +947,7 @@ struct ABIPGPU_LP {
     ABIPSettings stgs;
     ABIPGpuStats stats;
     double B_A = 0, B_AT = 0;  // algorithmic bytes of one SpMV pass
-    char desc[768];
+    char desc[1024];
     bool restart_synced = false;
     struct BatchExec* batch = nullptr;  // lock-step batch executor this engine belongs to
     bool own_stream = true;             // batch engines borrow the stream of their worker thread
@@ -1280,6 +1352,162 @@ static int transpose_csc(abip_int m, abip_int n, const abip_int* Ap, const abip_
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Measured balance of the persistent grid.  A phase of the PCG loop lasts as long as its slowest CTA; the structural cost
+// model of build_spmv_plan (nonzeros + rows + distinct gathered lines) leaves the CTA times of a pass spread by +-25 % at
+// cfg2 (profiles/r02_phase_times.txt: per-CTA mean busy time 20-32 us for A', 24-37 us for A) -- gather cost depends on what
+// the neighbouring CTAs of the SM and of the L2 slice do, which no static model sees.  So the engine measures: k_tune runs
+// the two passes on the real matrices, the model cost of the rows of every CTA is rescaled by (its time / mean time)^damp,
+// the row ranges are cut again on the rescaled costs, and the best plan seen (smallest sum of the slowest-CTA times of
+// the two passes) is kept.  Only the plan tables change (a few hundred KB); row sums do not depend on the plan, the order
+// of the reduced scalars does (the same way it depends on the grid size), so a solve is reproducible for a given plan.
+// ABIP_GPU_TUNE=0 keeps the structural plan; ABIP_GPU_TUNE_ROUNDS / _REPS / _DAMP / _MIN_NNZ are tuning knobs.
+// ---------------------------------------------------------------------------------------------------------
+static int upload_plans(abipgpu_lp* e, const SpmvPlan& pa, const SpmvPlan& pat) {
+    size_t bytes = 0;
+    auto put = [&](size_t b, size_t elem) {
+        const size_t off = (bytes + 255) & ~(size_t)255;
+        bytes = off + b + (size_t)kPad * elem;
+        return off;
+    };
+    struct Offs { size_t wc, ch, cl, lr, lp; } o[2];
+    const SpmvPlan* P[2] = {&pa, &pat};
+    for (int k = 0; k < 2; ++k) {
+        o[k].wc = put(P[k]->warp_chunk.size() * sizeof(int), sizeof(int));
+        o[k].ch = put(P[k]->chunk.size() * sizeof(int4), sizeof(int4));
+        o[k].cl = o[k].lr = o[k].lp = 0;
+        if (P[k]->n_long) {
+            o[k].cl = put(P[k]->cta_long.size() * sizeof(int), sizeof(int));
+            o[k].lr = put(P[k]->long_rows.size() * sizeof(int4), sizeof(int4));
+            o[k].lp = put((size_t)P[k]->n_pieces * sizeof(double), sizeof(double));
+        }
+    }
+    std::vector<unsigned char> stage(bytes, 0);
+    for (int k = 0; k < 2; ++k) {
+        memcpy(stage.data() + o[k].wc, P[k]->warp_chunk.data(), P[k]->warp_chunk.size() * sizeof(int));
+        memcpy(stage.data() + o[k].ch, P[k]->chunk.data(), P[k]->chunk.size() * sizeof(int4));
+        if (P[k]->n_long) {
+            memcpy(stage.data() + o[k].cl, P[k]->cta_long.data(), P[k]->cta_long.size() * sizeof(int));
+            memcpy(stage.data() + o[k].lr, P[k]->long_rows.data(), P[k]->long_rows.size() * sizeof(int4));
+        }
+    }
+    unsigned char* buf = nullptr;
+    CK(dev_alloc((void**)&buf, bytes, e->stream));
+    CK(cudaMemcpyAsync(buf, stage.data(), bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));  // also: every launch that used the previous tables has finished
+    e->stats.h2d_bytes += (double)bytes;
+    if (e->plan_arena) dev_free(e->plan_arena, e->stream);
+    e->plan_arena = buf;
+    e->A_wc = (int*)(buf + o[0].wc); e->A_chunk = (int4*)(buf + o[0].ch);
+    e->AT_wc = (int*)(buf + o[1].wc); e->AT_chunk = (int4*)(buf + o[1].ch);
+    e->A_cl = pa.n_long ? (int*)(buf + o[0].cl) : nullptr;
+    e->A_lr = pa.n_long ? (int4*)(buf + o[0].lr) : nullptr;
+    e->A_lp = pa.n_long ? (double*)(buf + o[0].lp) : nullptr;
+    e->AT_cl = pat.n_long ? (int*)(buf + o[1].cl) : nullptr;
+    e->AT_lr = pat.n_long ? (int4*)(buf + o[1].lr) : nullptr;
+    e->AT_lp = pat.n_long ? (double*)(buf + o[1].lp) : nullptr;
+    Csr& A = e->ctx.A;
+    A.warp_chunk = e->A_wc; A.chunk = e->A_chunk; A.lanes_log2 = pa.lanes_log2;
+    A.cta_long = e->A_cl; A.long_rows = e->A_lr; A.long_part = e->A_lp;
+    Csr& AT = e->ctx.AT;
+    AT.warp_chunk = e->AT_wc; AT.chunk = e->AT_chunk; AT.lanes_log2 = pat.lanes_log2;
+    AT.cta_long = e->AT_cl; AT.long_rows = e->AT_lr; AT.long_part = e->AT_lp;
+    return 0;
+}
+
+static int tune_balance(abipgpu_lp* e, const std::vector<int>& a_ptr, const std::vector<int>& at_ptr, SpmvPlan* planA,
+                        SpmvPlan* planAT, int W, bool threads) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    const int G = e->grid;
+    const int rounds = std::max(0, std::min(env_int("ABIP_GPU_TUNE_ROUNDS", 3), 8));
+    const int reps = std::max(2, std::min(env_int("ABIP_GPU_TUNE_REPS", 4), 64));
+    const char* denv = getenv("ABIP_GPU_TUNE_DAMP");
+    const double damp = (denv && *denv) ? atof(denv) : 0.8;
+    const std::vector<int>* ptr[2] = {&a_ptr, &at_ptr};
+    const int nrows[2] = {e->m, e->n};
+    const char* lanes_env[2] = {"ABIP_GPU_LANES_A", "ABIP_GPU_LANES_AT"};
+    SpmvPlan cur[2], best[2];
+    std::vector<double> cost[2];
+    cost[0].swap(planA->row_cost);
+    cost[1].swap(planAT->row_cost);
+    if ((int)cost[0].size() != e->m || (int)cost[1].size() != e->n) return 0;  // no model costs (one-CTA engines)
+    cur[0] = *planA;
+    cur[1] = *planAT;
+    CK(cudaFuncSetAttribute((const void*)k_tune, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    double* d_t = nullptr;
+    CK(dev_alloc((void**)&d_t, sizeof(double) * 3 * G, e->stream));
+    std::vector<double> t(3 * (size_t)G);
+    double best_score = 1e300;
+    int best_round = -1, uploaded_round = 0;
+    int cl = 0;
+    cudaDeviceGetAttribute(&cl, cudaDevAttrClockRate, e->device);  // kHz
+    const double us_per_cycle = cl > 0 ? 1e3 / (double)cl : 1.0 / 1965.0;
+    for (int round = 0; round <= rounds; ++round) {
+        if (launch_coop(e, (const void*)k_tune, G, e->smem, e->ctx, d_t, reps)) return -1;
+        CK(cudaMemcpyAsync(t.data(), d_t, sizeof(double) * 3 * G, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        double mx[2] = {0, 0}, mean[2] = {0, 0};
+        for (int k = 0; k < 2; ++k) {
+            const double* tk = t.data() + (k == 0 ? G : 0);  // t = [A' | A | sink]; k = 0 is A
+            for (int b = 0; b < G; ++b) {
+                mx[k] = std::max(mx[k], tk[b]);
+                mean[k] += tk[b] / G;
+            }
+        }
+        const double score = mx[0] + mx[1];
+        const double to_us = us_per_cycle / (reps - 1);
+        if (round == 0) {
+            e->tune_first_us[0] = mx[1] * to_us;
+            e->tune_first_us[1] = mx[0] * to_us;
+        }
+        if (env_int("ABIP_GPU_TUNE_VERBOSE", 0))
+            fprintf(stderr, "[abip_gpu] balance round %d: slowest CTA A' %.1f us (mean %.1f), A %.1f us (mean %.1f)\n", round,
+                    mx[1] * to_us, mean[1] * to_us, mx[0] * to_us, mean[0] * to_us);
+        if (score < best_score) {
+            best_score = score;
+            best_round = round;
+            best[0] = cur[0];
+            best[1] = cur[1];
+            e->tune_best_us[0] = mx[1] * to_us;
+            e->tune_best_us[1] = mx[0] * to_us;
+        }
+        if (round == rounds) break;
+        auto replan = [&](int k) {
+            const double* tk = t.data() + (k == 0 ? G : 0);
+            if (!(mean[k] > 0)) return;
+            std::vector<double>& c = cost[k];
+            const std::vector<int>& cr = cur[k].cta_row;
+            for (int b = 0; b < G; ++b) {
+                double f = pow(std::max(tk[b], 1.0) / mean[k], damp);
+                f = std::min(2.0, std::max(0.5, f));
+                for (int r = cr[b]; r < cr[b + 1]; ++r) c[r] *= f;
+            }
+            SpmvPlan np;
+            build_spmv_plan(*ptr[k], nrows[k], W, lanes_env[k], &np, nullptr, &c);
+            cur[k] = std::move(np);
+        };
+        if (threads) {
+            std::thread tp([&] { replan(0); });
+            replan(1);
+            tp.join();
+        } else {
+            replan(0);
+            replan(1);
+        }
+        if (upload_plans(e, cur[0], cur[1])) return -1;
+        uploaded_round = round + 1;
+    }
+    if (best_round != uploaded_round && upload_plans(e, best[0], best[1])) return -1;
+    dev_free(d_t, e->stream);
+    // the PCG workspace stays zero (alpha = 0 in k_tune), Gp and tmp are scratch
+    *planA = std::move(best[0]);
+    *planAT = std::move(best[1]);
+    e->tune_rounds = rounds;
+    e->tune_best_round = best_round;
+    e->tune_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return 0;
+}
+
 static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap, const abip_int* Ai,
                        const abip_float* Ax, const ABIPSettings* stgs, int device, const ScaleOut* scale_out = nullptr) {
     const long nnz = Ap[n];
@@ -1447,14 +1675,17 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         }
     }
     const int W = e->grid * kWarps;
+    // measured balance (tune_balance): whole-device engines of at least ABIP_GPU_TUNE_MIN_NNZ nonzeros, contiguous row ranges
+    const bool tune = env_int("ABIP_GPU_TUNE", 1) != 0 && !e->batch && t_grid_request == 0 && e->grid > 1 &&
+                      nnz >= (long)env_int("ABIP_GPU_TUNE_MIN_NNZ", 1000000) && env_int("ABIP_GPU_PLAN_DEAL", 0) == 0;
     SpmvPlan planA, planAT;
     if (host_threads > 1) {
-        std::thread tp([&] { build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data()); });
-        build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data());
+        std::thread tp([&] { build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data(), nullptr, tune); });
+        build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data(), nullptr, tune);
         tp.join();
     } else {
-        build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data());
-        build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data());
+        build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data(), nullptr, tune);
+        build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data(), nullptr, tune);
     }
     lap(3);
     // One device arena for all matrix and plan arrays: packed on the host (zero padding of kPad elements behind every
@@ -1515,7 +1746,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     const size_t L = ((size_t)e->l + 31) & ~(size_t)31;
     const size_t Mm = ((size_t)m + 31) & ~(size_t)31, Nn = ((size_t)n + 31) & ~(size_t)31;
     const size_t n_l_vecs = 21 + 2 + (reorder ? 2 : 0);  // ids 0..20 + xin + yout (+ xin2 + yout2)
-    const size_t total = n_l_vecs * L + 7 * Mm + 3 * Nn + (size_t)2 * kMaxRed * gmax + 64 + ABIPGPU_SC_COUNT + 32 + 2 * (size_t)gmax * kWarps;
+    const size_t total = n_l_vecs * L + 7 * Mm + 3 * Nn + (size_t)2 * kMaxRed * gmax + 64 + ABIPGPU_SC_COUNT + 32 + 2 * (size_t)gmax * kWarps + gmax;
     CK(dev_alloc((void**)&e->slab, total * sizeof(double), e->stream));
     CK(cudaMemsetAsync(e->slab, 0, total * sizeof(double), e->stream));
     e->slab_doubles = total;
@@ -1552,7 +1783,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     e->tmp = take(Nn);
     e->partials = take((size_t)2 * kMaxRed * gmax + 64);
     e->dsc = take(ABIPGPU_SC_COUNT);
-    e->dphase = take(32 + 2 * (size_t)gmax * kWarps);
+    e->dphase = take(32 + 2 * (size_t)gmax * kWarps + gmax);  // (+ the SM id of every CTA, debug builds)
     e->hsc = pinned_acquire();
     if (!e->hsc) return -1;
 
@@ -1624,6 +1855,8 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     lap(6);
+    if (tune && tune_balance(e, e_a_ptr, e_at_ptr, &planA, &planAT, W, host_threads > 1)) return -1;
+    lap(7);
 
     const double V = 8, I = 4;
     e->B_A = (double)nnz * (V + I) + (m + 1.0) * I + n * V + m * V;
@@ -1631,10 +1864,10 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     snprintf(e->desc, sizeof(e->desc),
              "device %d (%s, %d SMs) persistent grid %d x %d threads, %zu B smem/block | CSR(A): %d rows, mean %.1f max %d "
              "nnz/row, %zu chunks (%d long rows), %d lane(s)/row | CSR(A'): %d rows, mean %.1f max %d, %zu chunks (%d long), "
-             "%d lane(s)/row | nnz=%ld | locality ordering %s | set-up ms: transpose %.0f, ordering %.0f, permuted CSR %.0f, grid+plans %.0f, arena+upload %.0f, scaling %.0f, precond %.0f",
+             "%d lane(s)/row | nnz=%ld | locality ordering %s | set-up ms: transpose %.0f, ordering %.0f, permuted CSR %.0f, grid+plans %.0f, arena+upload %.0f, scaling %.0f, precond %.0f, measured balance %.0f (%d rounds, kept round %d: slowest CTA A' %.1f -> %.1f us, A %.1f -> %.1f us)",
              device, prop.name, e->num_sms, e->grid, kBlock, (size_t)e->smem, (int)m, planA.mean, planA.max_len,
              planA.chunk.size(), planA.n_long, 1 << planA.lanes_log2, (int)n, planAT.mean, planAT.max_len,
-             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, reorder ? "on" : "off", e->setup_ms[0], e->setup_ms[1], e->setup_ms[2], e->setup_ms[3], e->setup_ms[4], e->setup_ms[5], e->setup_ms[6]);
+             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, reorder ? "on" : "off", e->setup_ms[0], e->setup_ms[1], e->setup_ms[2], e->setup_ms[3], e->setup_ms[4], e->setup_ms[5], e->setup_ms[6], e->setup_ms[7], e->tune_rounds, e->tune_best_round, e->tune_first_us[0], e->tune_best_us[0], e->tune_first_us[1], e->tune_best_us[1]);
     return 0;
 }
 
@@ -1726,7 +1959,7 @@ void abipgpu_lp_destroy(abipgpu_lp* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     {
-        void* ptrs[] = {e->arena, e->slab, e->d_pl, e->d_rn2o, e->d_cn2o};
+        void* ptrs[] = {e->arena, e->plan_arena, e->slab, e->d_pl, e->d_rn2o, e->d_cn2o};
         for (void* q : ptrs) {
             if (e->stream && q) dev_free(q, e->stream);  // stream-ordered: no device-wide synchronisation
         }
@@ -2097,13 +2330,21 @@ int abipgpu_lp_spmv(abipgpu_lp* e, int trans, const abip_float* x, abip_float* y
 
 abip_int abipgpu_plan_debug(abip_int nrows, const int* rowptr, abip_int ctas, abip_int deal, int* chunks4,
                             abip_int max_chunks, int* warp_chunk, int* info6) {
+    return abipgpu_plan_debug_cost(nrows, rowptr, ctas, deal, nullptr, chunks4, max_chunks, warp_chunk, info6);
+}
+
+// same with explicit per-row costs for the cut of the CTA row ranges (the path of the measured balance, tune_balance)
+abip_int abipgpu_plan_debug_cost(abip_int nrows, const int* rowptr, abip_int ctas, abip_int deal, const double* row_cost,
+                                 int* chunks4, abip_int max_chunks, int* warp_chunk, int* info6) {
     if (nrows <= 0 || !rowptr || ctas <= 0) return 0;
     std::vector<int> ptr(rowptr, rowptr + nrows + 1);
+    std::vector<double> cost;
+    if (row_cost) cost.assign(row_cost, row_cost + nrows);
     SpmvPlan P;
     const char* prev = getenv("ABIP_GPU_PLAN_DEAL");
     const std::string saved = prev ? prev : "";
     setenv("ABIP_GPU_PLAN_DEAL", deal ? "1" : "0", 1);
-    build_spmv_plan(ptr, (int)nrows, (int)ctas * kWarps, "ABIP_GPU_LANES_DEBUG", &P);
+    build_spmv_plan(ptr, (int)nrows, (int)ctas * kWarps, "ABIP_GPU_LANES_DEBUG", &P, nullptr, row_cost ? &cost : nullptr);
     if (prev) setenv("ABIP_GPU_PLAN_DEAL", saved.c_str(), 1);
     else unsetenv("ABIP_GPU_PLAN_DEAL");
     if (info6) {
@@ -2256,7 +2497,7 @@ extern "C" int abipgpu_lp_phase_times(abipgpu_lp* e, double* out32, int reset) {
 extern "C" int abipgpu_lp_warp_times(abipgpu_lp* e, double* out, int* W) {  // [2][W] per-warp SpMV busy ns (debug builds)
     CK(cudaSetDevice(e->device));
     *W = e->grid * kWarps;
-    CK(cudaMemcpyAsync(out, e->dphase + 32, sizeof(double) * 2 * (*W), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(out, e->dphase + 32, sizeof(double) * (2 * (*W) + e->grid), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }

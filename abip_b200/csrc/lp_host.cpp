@@ -794,7 +794,7 @@ static ABIPGpuWork* gpu_init_impl(const ABIPData* d, ABIPInfo* info, int rank, i
         }
         abipgpu_lp_set_global_n(w->eng, w->n);
         if (d->stgs->verbose) {
-            char buf[768];
+            char buf[1280];
             abipgpu_lp_describe(w->eng, buf, sizeof(buf));
             printf("Engine: %s\n", buf);
         }
@@ -869,7 +869,7 @@ static ABIPGpuWork* gpu_init_impl(const ABIPData* d, ABIPInfo* info, int rank, i
         }
     }
     if (d->stgs->verbose) {
-        char buf[768];
+        char buf[1280];
         abipgpu_lp_describe(w->eng, buf, sizeof(buf));
         printf("Engine: %s\n", buf);
     }

@@ -2,6 +2,7 @@
 // control of ABIP(solve) (source/abip.c:1076-1249), has_converged (:750-777), adjust_barrier (:994-1071),
 // get_solution (:559-586) and the entry abip_qcp_gpu == abip() (:1335-1371).  Vector work is in qcp_engine.cu.
 #include "qcp_engine.h"
+#include "order_host.h"
 
 #include <algorithm>
 #include <cmath>
@@ -97,11 +98,20 @@ void abip_qcp_scale_data(ABIPQcpMatrix* A, ABIPQcpMatrix* Q, double* b, double* 
         }
         return kind == ORIGIN ? std::sqrt(acc) : acc;  // ORIGIN: 2-norm; RUIZ: inf-norm; PC: 1-norm
     };
+    // Large problems: the column loops run on up to ABIP_GPU_HOST_THREADS (default 8) host threads; every element sees the
+    // same operations in the same order as in the serial loops (columns are independent, a maximum does not depend on
+    // the order), the row SUMS of the origin / pc sweeps stay serial -- results are bit-identical for any thread count.
+    const char* thr_env = getenv("ABIP_GPU_HOST_THREADS");
+    const int threads = (nnzA + nnzQ < 400000) ? 1
+                        : std::max(1, std::min(thr_env && *thr_env ? atoi(thr_env) : 8, (int)std::thread::hardware_concurrency()));
+    std::vector<double> Dt;  // per-thread row maxima
     auto sweep = [&](Kind kind) {
-        for (int j = 0; j < n; ++j) {
-            double e1 = col_stat(A, j, kind), e2 = Q ? col_stat(Q, j, kind) : 0.0;
-            E[j] = std::sqrt(std::max(e1, e2));  // sqrt of the (larger) column statistic, for all three kinds
-        }
+        parallel_for(n, threads, [&](long j0, long j1, int) {
+            for (long j = j0; j < j1; ++j) {
+                double e1 = col_stat(A, (int)j, kind), e2 = Q ? col_stat(Q, (int)j, kind) : 0.0;
+                E[j] = std::sqrt(std::max(e1, e2));  // sqrt of the (larger) column statistic, for all three kinds
+            }
+        });
         int pos = 0;  // cone averaging (:207-225)
         auto avg_blocks = [&](const int* dims, int cnt) {
             for (int i = 0; i < cnt; ++i) {
@@ -118,28 +128,52 @@ void abip_qcp_scale_data(ABIPQcpMatrix* A, ABIPQcpMatrix* Q, double* b, double* 
         if (K->q) avg_blocks(K->q, K->qsize);
         if (K->rq) avg_blocks(K->rq, K->rqsize);
         std::fill(D.begin(), D.end(), 0.0);
-        for (int k = 0; k < nnzA; ++k) {
-            const double a = std::fabs(A->x[k]);
-            double& d = D[A->i[k]];
-            if (kind == RUIZ) { if (d < a) d = a; }
-            else if (kind == ORIGIN) d += a * a;
-            else d += a;
+        if (kind == RUIZ && threads > 1) {
+            Dt.assign((size_t)threads * m, 0.0);
+            parallel_for(n, threads, [&](long j0, long j1, int t) {
+                double* d = Dt.data() + (size_t)t * m;
+                for (int k = A->p[j0]; k < A->p[j1]; ++k) {
+                    const double a = std::fabs(A->x[k]);
+                    if (d[A->i[k]] < a) d[A->i[k]] = a;
+                }
+            });
+            for (int t = 0; t < threads; ++t) {
+                const double* d = Dt.data() + (size_t)t * m;
+                for (int i = 0; i < m; ++i)
+                    if (D[i] < d[i]) D[i] = d[i];
+            }
+        } else {
+            for (int k = 0; k < nnzA; ++k) {
+                const double a = std::fabs(A->x[k]);
+                double& d = D[A->i[k]];
+                if (kind == RUIZ) { if (d < a) d = a; }
+                else if (kind == ORIGIN) d += a * a;
+                else d += a;
+            }
         }
         for (int i = 0; i < m; ++i) {
             double d = kind == ORIGIN ? std::sqrt(std::sqrt(D[i])) : std::sqrt(D[i]);
             if (d < min_row) d = 1; else if (d > max_row) d = max_row;
             D[i] = d;
         }
-        for (int j = 0; j < n; ++j) {
+        for (int j = 0; j < n; ++j)
             if (E[j] < min_col) E[j] = 1; else if (E[j] > max_col) E[j] = max_col;
-            for (int k = A->p[j]; k < A->p[j + 1]; ++k) A->x[k] /= E[j];
-        }
-        if (Q) {
-            for (int j = 0; j < n; ++j)
-                for (int k = Q->p[j]; k < Q->p[j + 1]; ++k) Q->x[k] /= E[j];
-            for (int k = 0; k < nnzQ; ++k) Q->x[k] /= E[Q->i[k]];
-        }
-        for (int k = 0; k < nnzA; ++k) A->x[k] /= D[A->i[k]];
+        parallel_for(n, threads, [&](long j0, long j1, int) {
+            for (long j = j0; j < j1; ++j) {
+                const double ej = E[j];
+                for (int k = A->p[j]; k < A->p[j + 1]; ++k) {
+                    double x = A->x[k] / ej;  // first the column factor, then the row factor, as two divisions
+                    x /= D[A->i[k]];
+                    A->x[k] = x;
+                }
+                if (Q)
+                    for (int k = Q->p[j]; k < Q->p[j + 1]; ++k) {
+                        double x = Q->x[k] / ej;
+                        x /= E[Q->i[k]];
+                        Q->x[k] = x;
+                    }
+            }
+        });
         for (int j = 0; j < n; ++j) E_hat[j] *= E[j];
         for (int i = 0; i < m; ++i) D_hat[i] *= D[i];
     };

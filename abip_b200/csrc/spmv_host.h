@@ -61,6 +61,8 @@ struct SpmvPlan {
     std::vector<int4> chunk;      // grouped by warp
     std::vector<int> cta_long;    // [G+1] range of long_rows per CTA
     std::vector<int4> long_rows;  // {row, first piece slot, #pieces, 0}
+    std::vector<int> cta_row;     // [G+1] contiguous row range of each CTA (deal == 0)
+    std::vector<double> row_cost; // model cost of every row (kept for the measured balance, tune_balance() in lp_engine.cu)
     int n_pieces = 0;
     int lanes_log2 = 0;
     double mean = 0;
@@ -103,16 +105,22 @@ static inline void row_line_costs(const std::vector<int>& ptr, const int* idx, i
     }
 }
 
+// cost_override: per-row costs that replace the model (measured balance: the model costs rescaled CTA by CTA with the
+// measured pass times); keep_cost: leave the model costs in P->row_cost.
 static inline void build_spmv_plan(const std::vector<int>& ptr, int nrows, int W, const char* env_lanes, SpmvPlan* P,
-                                   const int* idx = nullptr) {
+                                   const int* idx = nullptr, const std::vector<double>* cost_override = nullptr,
+                                   bool keep_cost = false) {
     const long nnz = ptr[nrows];
     const int G = std::max(1, W / kWarps);
     // prefix of the row costs (contiguous ranges, deal == 0)
     std::vector<double> cum(nrows + 1, 0.0);
-    if (idx && G > 1) {
+    if (cost_override) {
+        for (int r = 0; r < nrows; ++r) cum[r + 1] = cum[r] + (*cost_override)[r];
+    } else if (idx && G > 1) {
         std::vector<double> rc;
         row_line_costs(ptr, idx, nrows, &rc);
         for (int r = 0; r < nrows; ++r) cum[r + 1] = cum[r] + rc[r];
+        if (keep_cost) P->row_cost.swap(rc);
     } else {
         for (int r = 0; r < nrows; ++r) cum[r + 1] = (double)ptr[r + 1] + 2.0 * (r + 1);
     }
@@ -120,6 +128,7 @@ static inline void build_spmv_plan(const std::vector<int>& ptr, int nrows, int W
     P->warp_chunk.assign(W + 1, 0);
     P->chunk.clear();
     P->cta_long.assign(G + 1, 0);
+    P->cta_row.assign(G + 1, 0);
     P->long_rows.clear();
     P->n_pieces = 0;
     P->n_long = 0;
@@ -206,6 +215,7 @@ static inline void build_spmv_plan(const std::vector<int>& ptr, int nrows, int W
             } else {
                 const double target = total_cost * (double)(b + 1) / (double)G;
                 while (r < nrows && (cum[r + 1] <= target || b == G - 1)) ++r;
+                P->cta_row[b + 1] = r;
                 const long nnz_cta = (long)ptr[r] - ptr[ra];
                 const long rc = std::max(1L, (nnz_cta + (long)kWarps * kChunk - 1) / ((long)kWarps * kChunk));
                 want = (int)std::min<long>(kChunk, std::max<long>(32, (nnz_cta + rc * kWarps - 1) / (rc * kWarps)));

@@ -293,6 +293,12 @@ void abipgpu_lp_describe(const abipgpu_lp *e, char *buf, abip_int buflen);
  * info = {warps per CTA, chunk nonzero limit, chunk row limit, long rows, pieces, lanes per row (log2)}. */
 abip_int abipgpu_plan_debug(abip_int nrows, const int *rowptr, abip_int ctas, abip_int deal, int *chunks4,
                             abip_int max_chunks, int *warp_chunk, int *info6);
+/* Same, with explicit per-row costs for the cut of the CTA row ranges (row_cost[nrows], NULL: the structural model).
+ * This is the path of the measured balance: whole-device engines time the two SpMV passes of the PCG loop per CTA at
+ * set-up, rescale the model costs with the measured times and cut the ranges again (lp_engine.cu: tune_balance;
+ * ABIP_GPU_TUNE=0 disables it). */
+abip_int abipgpu_plan_debug_cost(abip_int nrows, const int *rowptr, abip_int ctas, abip_int deal, const double *row_cost,
+                                 int *chunks4, abip_int max_chunks, int *warp_chunk, int *info6);
 
 /* ------------------------------------------------------------------------------------------------
  * (4) ABIP-QCP: min 1/2 x'Qx + c'x  s.t. Ax = b, x in K (SOC, rotated SOC, free, zero, orthant blocks in this

@@ -166,3 +166,59 @@ def test_spmv_plan_invariants(case, deal):
         first_rows = [ch[wc[b * warps]:wc[(b + 1) * warps], 0] for b in range(ctas) if wc[(b + 1) * warps] > wc[b * warps]]
         for a, b in zip(first_rows, first_rows[1:]):
             assert a.max() < b.min()
+
+
+def test_spmv_plan_with_measured_costs():
+    """abipgpu_plan_debug_cost: the CTA row ranges follow the per-row costs handed in (the path of the measured balance,
+    lp_engine.cu tune_balance): with the first half of the rows four times as expensive, the CTAs split the COST evenly,
+    every row is still covered exactly once, and NULL costs reproduce the structural plan."""
+    import ctypes as C
+    import numpy as np
+    from abip_b200 import _capi
+    L = _capi.lib()
+    rng = np.random.default_rng(5)
+    lens = rng.integers(1, 12, 8000)
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    nrows, nnz, ctas = len(lens), int(ptr[-1]), 8
+    cap = 4 * (nnz // 8 + nrows + 64)
+    L.abipgpu_plan_debug_cost.restype = C.c_long
+    L.abipgpu_plan_debug_cost.argtypes = [C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p,
+                                          C.c_void_p]
+    L.abipgpu_plan_debug.restype = C.c_long
+    L.abipgpu_plan_debug.argtypes = [C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
+
+    def plan(cost):
+        chunks = np.zeros(4 * cap, dtype=np.int32)
+        info = np.zeros(6, dtype=np.int32)
+        wc = np.zeros(ctas * 64 + 1, dtype=np.int32)
+        n = L.abipgpu_plan_debug_cost(nrows, ptr.ctypes.data, ctas, 0, cost.ctypes.data if cost is not None else None,
+                                      chunks.ctypes.data, cap, wc.ctypes.data, info.ctypes.data)
+        assert n > 0
+        warps = int(info[0])
+        return chunks[:4 * n].reshape(n, 4).copy(), wc[:ctas * warps + 1].copy(), warps
+
+    cost = (lens + 2.0) * np.where(np.arange(nrows) < nrows // 2, 4.0, 1.0)
+    ch, wc, warps = plan(cost)
+    seen = np.zeros(nrows, dtype=np.int64)
+    for row0, nnz0, nr, cnt in ch.tolist():
+        assert nr > 0 and ptr[row0] == nnz0 and ptr[row0 + nr] == nnz0 + cnt
+        seen[row0:row0 + nr] += 1
+    assert np.all(seen == 1)
+    per_cta = []
+    for b in range(ctas):
+        rows = [(r0, nr) for r0, _, nr, _ in ch[wc[b * warps]:wc[(b + 1) * warps]].tolist()]
+        lo, hi = min(r for r, _ in rows), max(r + k for r, k in rows)
+        assert sum(k for _, k in rows) == hi - lo            # contiguous range of rows
+        per_cta.append(cost[lo:hi].sum())
+    per_cta = np.array(per_cta)
+    assert per_cta.max() / per_cta.min() < 1.02              # equal cost per CTA (row granularity)
+    # the expensive half is spread over 4/5 of the CTAs
+    first_half_ctas = sum(1 for b in range(ctas) if ch[wc[b * warps], 0] < nrows // 2)
+    assert first_half_ctas in (6, 7)
+    # NULL costs: identical to the structural plan
+    ch0, wc0, _ = plan(None)
+    chunks = np.zeros(4 * cap, dtype=np.int32)
+    wcb = np.zeros(ctas * 64 + 1, dtype=np.int32)
+    info = np.zeros(6, dtype=np.int32)
+    n = L.abipgpu_plan_debug(nrows, ptr.ctypes.data, ctas, 0, chunks.ctypes.data, cap, wcb.ctypes.data, info.ctypes.data)
+    assert n == len(ch0) and np.array_equal(chunks[:4 * n].reshape(n, 4), ch0) and np.array_equal(wcb[:len(wc0)], wc0)

@@ -94,6 +94,31 @@ def test_host_scaling_matches_oracle(kw):
     assert abs(sb.value - sbo) < 1e-15
 
 
+def test_host_scaling_threads_are_bit_identical(monkeypatch):
+    """abip_qcp_scale_data on several host threads (problems of >= 400k nonzeros) returns bit-for-bit what one thread
+    returns: columns are independent, the row maxima of the Ruiz sweeps do not depend on the order, row sums stay serial."""
+    from abip_b200 import problems
+    L = qcp._bind()
+    p = problems.cfg3(scale=0.05)   # n = 25,000, nnz(A) ~ 500k
+    assert p.A.nnz + p.Q.nnz >= 400000
+    out = {}
+    for thr in ("1", "8"):
+        monkeypatch.setenv("ABIP_GPU_HOST_THREADS", thr)
+        st = qcp.default_settings(pc_scaling=1)
+        A, kA = qcp._mat(p.A.copy())
+        Qm, kQ = qcp._mat(p.Q.copy())
+        b, c = p.b.copy(), p.c.copy()
+        cone, _keep = qcp.make_cone(p.K)
+        D, E = np.zeros(p.m), np.zeros(p.n)
+        sb, sc = C.c_double(), C.c_double()
+        L.abip_qcp_scale_data(C.byref(A), C.byref(Qm), qcp._dp(b), qcp._dp(c), C.byref(cone), C.byref(st), qcp._dp(D),
+                              qcp._dp(E), C.byref(sb), C.byref(sc))
+        out[thr] = (kA[0].copy(), kQ[0].copy(), b, c, D, E, sb.value, sc.value)
+    for u, v in zip(out["1"][:6], out["8"][:6]):
+        assert np.array_equal(u, v)
+    assert out["1"][6:] == out["8"][6:]
+
+
 def test_cone_prox_properties():
     """Barrier prox outputs are strictly inside their cones and reduce to the orthant formula in 1-D."""
     rng = np.random.default_rng(1)

@@ -38,10 +38,13 @@ if hasattr(L, 'abipgpu_lp_phase_times'):
                 print('phase %-9s count %6d  avg %8.2f us  total %8.2f ms' % (nm, out[16 + i], out[i] / out[16 + i] / 1e3, out[i] / 1e6))
 if hasattr(L, 'abipgpu_lp_warp_times') and out[16:].sum() > 0:
     W = C.c_int(0)
-    buf = np.zeros(2 * 148 * 32 * 4)
+    buf = np.zeros(2 * 148 * 32 * 4 + 1024)
     L.abipgpu_lp_warp_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.abipgpu_lp_warp_times(e.e, buf.ctypes.data_as(C.POINTER(C.c_double)), C.byref(W))
     W = W.value
+    import os
+    os.makedirs('gpurun_out', exist_ok=True)
+    np.save('gpurun_out/warp_times.npy', buf[:2 * W + W // 16])
     calls = out[16 + 4]
     for which, nm in ((0, "A' pass"), (1, 'A pass')):
         t = buf[which * W:(which + 1) * W] / max(calls, 1) / 1e3   # us per call per warp
