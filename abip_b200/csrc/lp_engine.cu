@@ -1570,70 +1570,6 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     auto par = [&](long cnt, auto fn) { parallel_for(cnt, host_threads, fn); };
     std::vector<int> at_ptr, at_idx, a_ptr, a_idx, perm;
     if (transpose_csc(m, n, Ap, Ai, host_threads, &at_ptr, &at_idx, &a_ptr, &a_idx, &perm)) return -1;
-    // Locality ordering (sjds_host.h): whole-device engines work in a permuted index space in which structurally
-    // identical rows / columns are neighbours, so the 32 lanes of a gather touch a few lines instead of 32.
-    // e_* : the engine's matrices; e_a_src / e_at_src: position of every entry in the caller's CSC arrays.
-    lap(0);
-    std::vector<int> row_n2o, col_n2o;
-    bool reorder = env_int("ABIP_GPU_REORDER", 1) != 0 && t_order_request != 0 && !t_batch && t_grid_request == 0;
-    if (reorder) {
-        const auto t_o0 = std::chrono::steady_clock::now();
-        sjds::locality_order((int)m, (int)n, a_ptr, a_idx, at_ptr, at_idx, sjds::kLongRow, &row_n2o, &col_n2o, par);
-        bool ident = true;
-        for (long i = 0; i < m && ident; ++i) ident = row_n2o[i] == i;
-        for (long j = 0; j < n && ident; ++j) ident = col_n2o[j] == j;
-        if (ident) reorder = false;
-        e->order_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_o0).count();
-    }
-    e->permuted = reorder;
-    lap(1);
-    std::vector<int> e_a_ptr, e_a_idx, e_a_src, e_at_ptr, e_at_idx, e_at_src;
-    if (reorder) {
-        std::vector<int> row_o2n(m), col_o2n(n);
-        for (long i = 0; i < m; ++i) row_o2n[row_n2o[i]] = (int)i;
-        for (long j = 0; j < n; ++j) col_o2n[col_n2o[j]] = (int)j;
-        e_a_ptr.assign(m + 1, 0);
-        e_a_idx.resize(nnz);
-        e_a_src.resize(nnz);
-        for (long i = 0; i < m; ++i) e_a_ptr[i + 1] = e_a_ptr[i] + (a_ptr[row_n2o[i] + 1] - a_ptr[row_n2o[i]]);
-        par(m, [&](long i0, long i1, int) {
-            for (long i = i0; i < i1; ++i) {
-                int q = e_a_ptr[i];
-                for (int k = a_ptr[row_n2o[i]]; k < a_ptr[row_n2o[i] + 1]; ++k, ++q) {
-                    e_a_idx[q] = col_o2n[a_idx[k]];
-                    e_a_src[q] = perm[k];
-                }
-            }
-        });
-        e_at_ptr.assign(n + 1, 0);
-        e_at_idx.resize(nnz);
-        e_at_src.resize(nnz);
-        for (long j = 0; j < n; ++j) e_at_ptr[j + 1] = e_at_ptr[j] + (at_ptr[col_n2o[j] + 1] - at_ptr[col_n2o[j]]);
-        par(n, [&](long j0, long j1, int) {
-            for (long j = j0; j < j1; ++j) {
-                int q = e_at_ptr[j];
-                for (int k = at_ptr[col_n2o[j]]; k < at_ptr[col_n2o[j] + 1]; ++k, ++q) {
-                    e_at_idx[q] = row_o2n[at_idx[k]];
-                    e_at_src[q] = k;
-                }
-            }
-        });
-    } else {
-        e_a_ptr = a_ptr;
-        e_a_idx = a_idx;
-        e_a_src = perm;
-        e_at_ptr = at_ptr;
-        e_at_idx = at_idx;
-    }
-    std::vector<double> a_val(scale_out ? 0 : nnz), at_val(scale_out ? 0 : nnz);
-    if (!scale_out) {
-        par(nnz, [&](long q0, long q1, int) {
-            for (long q = q0; q < q1; ++q) a_val[q] = Ax[e_a_src[q]];
-            if (reorder) for (long q = q0; q < q1; ++q) at_val[q] = Ax[e_at_src[q]];
-            else memcpy(at_val.data() + q0, Ax + q0, sizeof(double) * (q1 - q0));
-        });
-    }
-    lap(2);
     // persistent grid: a multiple of the SM count, common to all SpMV-bearing kernels
     {
         int g1, g2, g3, g4;
@@ -1675,19 +1611,98 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         }
     }
     const int W = e->grid * kWarps;
-    // measured balance (tune_balance): whole-device engines of at least ABIP_GPU_TUNE_MIN_NNZ nonzeros, contiguous row ranges
-    const bool tune = env_int("ABIP_GPU_TUNE", 1) != 0 && !e->batch && t_grid_request == 0 && e->grid > 1 &&
+    // Locality ordering (sjds_host.h): whole-device engines work in a permuted index space in which structurally
+    // identical rows / columns are neighbours, so the 32 lanes of a gather touch a few lines instead of 32.
+    // e_* : the engine's matrices; e_a_src / e_at_src: position of every entry in the caller's CSC arrays.
+    lap(0);
+    std::vector<int> row_n2o, col_n2o;
+    bool reorder = env_int("ABIP_GPU_REORDER", 1) != 0 && t_order_request != 0 && !t_batch && t_grid_request == 0;
+    if (reorder) {
+        const auto t_o0 = std::chrono::steady_clock::now();
+        sjds::locality_order((int)m, (int)n, a_ptr, a_idx, at_ptr, at_idx, sjds::kLongRow, &row_n2o, &col_n2o, par);
+        bool ident = true;
+        for (long i = 0; i < m && ident; ++i) ident = row_n2o[i] == i;
+        for (long j = 0; j < n && ident; ++j) ident = col_n2o[j] == j;
+        if (ident) reorder = false;
+        e->order_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_o0).count();
+    }
+    e->permuted = reorder;
+    lap(1);
+    // measured balance (tune_balance, opt-in: measured at cfg2 and found to change nothing, profiles/r02_spmv.md): whole-device
+    // engines of at least ABIP_GPU_TUNE_MIN_NNZ nonzeros, contiguous row ranges
+    const bool tune = env_int("ABIP_GPU_TUNE", 0) != 0 && !e->batch && t_grid_request == 0 && e->grid > 1 &&
                       nnz >= (long)env_int("ABIP_GPU_TUNE_MIN_NNZ", 1000000) && env_int("ABIP_GPU_PLAN_DEAL", 0) == 0;
+    std::vector<int> e_a_ptr, e_a_idx, e_a_src, e_at_ptr, e_at_idx, e_at_src;
     SpmvPlan planA, planAT;
-    if (host_threads > 1) {
-        std::thread tp([&] { build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data(), nullptr, tune); });
+    bool jds_at = false;
+    if (reorder) {
+        // A' first: its plan decides the chunks, and on the lane-per-row path the rows inside every chunk are then sorted by
+        // length and stored step-major (order_host.h: jds_sort_chunks) -- that is one more permutation of the columns of A,
+        // so CSR(A) is labelled afterwards
+        std::vector<int> row_o2n(m), col_o2n(n);
+        for (long i = 0; i < m; ++i) row_o2n[row_n2o[i]] = (int)i;
+        e_at_ptr.assign(n + 1, 0);
+        e_at_idx.resize(nnz);
+        e_at_src.resize(nnz);
+        for (long j = 0; j < n; ++j) e_at_ptr[j + 1] = e_at_ptr[j] + (at_ptr[col_n2o[j] + 1] - at_ptr[col_n2o[j]]);
+        par(n, [&](long j0, long j1, int) {
+            for (long j = j0; j < j1; ++j) {
+                int q = e_at_ptr[j];
+                for (int k = at_ptr[col_n2o[j]]; k < at_ptr[col_n2o[j] + 1]; ++k, ++q) {
+                    e_at_idx[q] = row_o2n[at_idx[k]];
+                    e_at_src[q] = k;
+                }
+            }
+        });
+        lap(2);
         build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data(), nullptr, tune);
-        tp.join();
-    } else {
+        if (planAT.lanes_log2 == 0 && !tune && env_int("ABIP_GPU_JDS", 1) != 0) {
+            sjds::jds_sort_chunks(planAT.chunk, e_at_ptr, e_at_idx, e_at_src, col_n2o, par);
+            jds_at = true;
+        }
+        lap(3);
+        for (long j = 0; j < n; ++j) col_o2n[col_n2o[j]] = (int)j;
+        e_a_ptr.assign(m + 1, 0);
+        e_a_idx.resize(nnz);
+        e_a_src.resize(nnz);
+        for (long i = 0; i < m; ++i) e_a_ptr[i + 1] = e_a_ptr[i] + (a_ptr[row_n2o[i] + 1] - a_ptr[row_n2o[i]]);
+        par(m, [&](long i0, long i1, int) {
+            for (long i = i0; i < i1; ++i) {
+                int q = e_a_ptr[i];
+                for (int k = a_ptr[row_n2o[i]]; k < a_ptr[row_n2o[i] + 1]; ++k, ++q) {
+                    e_a_idx[q] = col_o2n[a_idx[k]];
+                    e_a_src[q] = perm[k];
+                }
+            }
+        });
+        lap(2);
         build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data(), nullptr, tune);
-        build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data(), nullptr, tune);
+    } else {
+        e_a_ptr = a_ptr;
+        e_a_idx = a_idx;
+        e_a_src = perm;
+        e_at_ptr = at_ptr;
+        e_at_idx = at_idx;
+        lap(2);
+        if (host_threads > 1) {
+            std::thread tp([&] { build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data(), nullptr, tune); });
+            build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data(), nullptr, tune);
+            tp.join();
+        } else {
+            build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data(), nullptr, tune);
+            build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data(), nullptr, tune);
+        }
     }
     lap(3);
+    std::vector<double> a_val(scale_out ? 0 : nnz), at_val(scale_out ? 0 : nnz);
+    if (!scale_out) {
+        par(nnz, [&](long q0, long q1, int) {
+            for (long q = q0; q < q1; ++q) a_val[q] = Ax[e_a_src[q]];
+            if (reorder) for (long q = q0; q < q1; ++q) at_val[q] = Ax[e_at_src[q]];
+            else memcpy(at_val.data() + q0, Ax + q0, sizeof(double) * (q1 - q0));
+        });
+    }
+    lap(2);
     // One device arena for all matrix and plan arrays: packed on the host (zero padding of kPad elements behind every
     // array included) and uploaded with ONE allocation and ONE copy -- 14 arrays x (malloc + memset + copy) were a
     // third of the driver calls of an engine set-up, which is what limits a batch of small LPs.
@@ -1794,6 +1809,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
               e->A_cl, e->A_lr, e->A_lp, 1, nullptr, nullptr, nullptr};
     c.AT = Csr{e->AT_ptr, e->AT_idx, e->AT_val, (int)n, e->AT_wc, e->AT_chunk, planAT.lanes_log2,
                e->AT_cl, e->AT_lr, e->AT_lp, 2, nullptr, nullptr, nullptr};
+    c.AT.jds = jds_at ? 1 : 0;
     c.M = e->dM;
     c.D = nullptr;
     c.E = nullptr;
@@ -1867,7 +1883,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
              "%d lane(s)/row | nnz=%ld | locality ordering %s | set-up ms: transpose %.0f, ordering %.0f, permuted CSR %.0f, grid+plans %.0f, arena+upload %.0f, scaling %.0f, precond %.0f, measured balance %.0f (%d rounds, kept round %d: slowest CTA A' %.1f -> %.1f us, A %.1f -> %.1f us)",
              device, prop.name, e->num_sms, e->grid, kBlock, (size_t)e->smem, (int)m, planA.mean, planA.max_len,
              planA.chunk.size(), planA.n_long, 1 << planA.lanes_log2, (int)n, planAT.mean, planAT.max_len,
-             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, reorder ? "on" : "off", e->setup_ms[0], e->setup_ms[1], e->setup_ms[2], e->setup_ms[3], e->setup_ms[4], e->setup_ms[5], e->setup_ms[6], e->setup_ms[7], e->tune_rounds, e->tune_best_round, e->tune_first_us[0], e->tune_best_us[0], e->tune_first_us[1], e->tune_best_us[1]);
+             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, reorder ? (jds_at ? "on, A' chunks step-major" : "on") : "off", e->setup_ms[0], e->setup_ms[1], e->setup_ms[2], e->setup_ms[3], e->setup_ms[4], e->setup_ms[5], e->setup_ms[6], e->setup_ms[7], e->tune_rounds, e->tune_best_round, e->tune_first_us[0], e->tune_best_us[0], e->tune_first_us[1], e->tune_best_us[1]);
     return 0;
 }
 
