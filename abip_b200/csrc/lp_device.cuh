@@ -27,7 +27,6 @@ namespace cg = cooperative_groups;
 constexpr int kBlock = ABIP_BLOCK;
 constexpr int kWarps = kBlock / 32;
 constexpr int kMaxRed = 24;  // max scalars reduced between two grid barriers
-constexpr int kFinishSlots = 10;  // Reducer::finish keeps up to 32 * kFinishSlots block partials in flight per slot
 
 // Virtual grid: the persistent device code never reads blockIdx / gridDim directly.  An ordinary launch maps them
 // 1:1; the batched launch (k_batch, lp_engine.cu: one CTA = one independent small LP) presents every CTA as block 0 of a
@@ -80,10 +79,6 @@ struct Csr {
     const double* sm_val;
     const unsigned short* sm_idx;
     const int* sm_ptr;
-    // chunk-local JDS layout (lane-per-row matrices of reordered engines, order_host.h: jds_sort_chunks): inside every
-    // chunk of whole rows the rows are sorted by decreasing length and val / idx are stored step-major (step j of all
-    // rows that have one, in row order), so that the 32 lanes of a step read consecutive shared-memory words
-    int jds;
 };
 
 // Per-warp staging buffer in shared memory: [val window | idx window | row-ptr window].  The value and index windows
@@ -267,24 +262,9 @@ struct Reducer {
             const double* src = partials + (parity * kMaxRed + k) * G;
             const bool mx = (MAXMASK >> k) & 1u;
             double s = 0.0;
-            if (G <= 32 * kFinishSlots) {
-                // all partials of the slot in flight at once, then the same lane-serial sum as the loop below: a loop of
-                // dependent L2 round trips (10 per lane at G = 296) made this the longest step between two SpMV passes
-                // (ncu r02: 12 % of the warp samples of k_bb_round were CTA-barrier waits inside finish())
-                double t[kFinishSlots];
-#pragma unroll
-                for (int j = 0; j < kFinishSlots; ++j) {
-                    const int i = lane + 32 * j;
-                    t[j] = i < G ? __ldcg(src + i) : 0.0;
-                }
-#pragma unroll
-                for (int j = 0; j < kFinishSlots; ++j)
-                    if (lane + 32 * j < G) s = mx ? fmax(s, t[j]) : s + t[j];
-            } else {
-                for (int i = lane; i < G; i += 32) {
-                    const double t = __ldcg(src + i);
-                    s = mx ? fmax(s, t) : s + t;
-                }
+            for (int i = lane; i < G; i += 32) {
+                const double t = __ldcg(src + i);
+                s = mx ? fmax(s, t) : s + t;
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
@@ -415,32 +395,6 @@ __device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, WarpSme
             if (lane + 32 < nr) { a1 = rp[lane + 32]; b1 = rp[lane + 33]; }
             const int mx = __reduce_max_sync(0xffffffffu, max(b0 - a0, b1 - a1));
             double acc0 = 0.0, acc1 = 0.0;
-            if (A.jds) {
-                // step-major chunk: step j of row r (rows sorted by decreasing length) sits at base_j + r, base_j = number of
-                // elements of the steps before j -- consecutive lanes read consecutive words (1 wavefront per index load, 2
-                // per value load; the row-major layout cost 1.8x that in bank conflicts, ncu r02).  Same summation order.
-                const int len0 = b0 - a0, len1 = b1 - a1;
-                const double* vj = vw + off + lane;
-                const int* ij = iw + off + lane;
-                int base = 0;
-                for (int j = 0; j < mx; j += kL1U) {
-                    double x0[kL1U], x1[kL1U];
-                    int pos[kL1U];
-#pragma unroll
-                    for (int u = 0; u < kL1U; ++u) {
-                        const bool h0 = j + u < len0, h1 = j + u < len1;
-                        pos[u] = base;
-                        x0[u] = h0 ? x[ij[base]] : 0.0;
-                        x1[u] = h1 ? x[ij[base + 32]] : 0.0;
-                        base += __popc(__ballot_sync(0xffffffffu, h0)) + __popc(__ballot_sync(0xffffffffu, h1));
-                    }
-#pragma unroll
-                    for (int u = 0; u < kL1U; ++u) {
-                        if (j + u < len0) acc0 = __dadd_rn(acc0, __dmul_rn(vj[pos[u]], x0[u]));
-                        if (j + u < len1) acc1 = __dadd_rn(acc1, __dmul_rn(vj[pos[u] + 32], x1[u]));
-                    }
-                }
-            } else
             for (int j = 0; j < mx; j += kL1U) {
                 double x0[kL1U], x1[kL1U];
 #pragma unroll
@@ -482,40 +436,46 @@ __device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, WarpSme
         }
         double sum0 = 0.0, sum1 = 0.0;
         int epi_rows = 0;
-        // 1. gather x for the whole window (8 independent loads per lane), multiply.  Lane l owns the element pairs
-        //    l + 32 i (i = 0..3): consecutive lanes read consecutive 8-byte index pairs and 16-byte value pairs (with four
-        //    consecutive elements per lane the 128-bit value loads and stores had a 32-byte stride: 2-way bank conflicts
-        //    on every one of them, ncu r02)
-        double xv[4][2];
-        int2 ci[4];
+        // 1. gather x for the whole window (8 independent loads per lane), multiply
+        double xv[2][4];
+        int4 ci[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ci[i] = reinterpret_cast<const int2*>(iw)[lane + 32 * i];
+        for (int u = 0; u < 2; ++u) ci[u] = reinterpret_cast<const int4*>(iw)[lane + 32 * u];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            xv[i][0] = x[ci[i].x];
-            xv[i][1] = x[ci[i].y];
+        for (int u = 0; u < 2; ++u) {
+            xv[u][0] = x[ci[u].x];
+            xv[u][1] = x[ci[u].y];
+            xv[u][2] = x[ci[u].z];
+            xv[u][3] = x[ci[u].w];
         }
         if (nr <= 0) {  // piece of a long row: elements [off, off + n) of the window; slot -nr - 1 of the scratch
             double acc = 0.0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int q = lane + 32 * i;
-                const double2 v = reinterpret_cast<const double2*>(vw)[q];
-                const int k = 2 * q - off;
-                if ((unsigned)k < (unsigned)n) acc = fma(v.x, xv[i][0], acc);
-                if ((unsigned)(k + 1) < (unsigned)n) acc = fma(v.y, xv[i][1], acc);
+            for (int u = 0; u < 2; ++u) {
+                const int q = lane + 32 * u;
+                const double2 v01 = reinterpret_cast<const double2*>(vw)[2 * q];
+                const double2 v23 = reinterpret_cast<const double2*>(vw)[2 * q + 1];
+                const int k = 4 * q - off;
+                if ((unsigned)k < (unsigned)n) acc = fma(v01.x, xv[u][0], acc);
+                if ((unsigned)(k + 1) < (unsigned)n) acc = fma(v01.y, xv[u][1], acc);
+                if ((unsigned)(k + 2) < (unsigned)n) acc = fma(v23.x, xv[u][2], acc);
+                if ((unsigned)(k + 3) < (unsigned)n) acc = fma(v23.y, xv[u][3], acc);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) A.long_part[-nr - 1] = acc;
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int q = lane + 32 * i;
-                double2 v = reinterpret_cast<const double2*>(vw)[q];
-                v.x *= xv[i][0];
-                v.y *= xv[i][1];
-                reinterpret_cast<double2*>(vw)[q] = v;
+            for (int u = 0; u < 2; ++u) {
+                const int q = lane + 32 * u;
+                double2 v01 = reinterpret_cast<const double2*>(vw)[2 * q];
+                double2 v23 = reinterpret_cast<const double2*>(vw)[2 * q + 1];
+                v01.x *= xv[u][0];
+                v01.y *= xv[u][1];
+                v23.x *= xv[u][2];
+                v23.y *= xv[u][3];
+                reinterpret_cast<double2*>(vw)[2 * q] = v01;
+                reinterpret_cast<double2*>(vw)[2 * q + 1] = v23;
             }
             __syncwarp();
             SPROF(1);

@@ -364,12 +364,15 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
 // seven-sum epilogue, then the vector update, same barriers) on the engine's own matrices; every CTA reports the SM cycles
 // between the start of a pass and the moment its last warp has finished its rows.  The first iteration is a warm-up.
 // The PCG workspace it runs on is all zeros (alpha = 0 keeps it so); only the timing matters.
-__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_tune(LpCtx c, double* t_out /* [3][G] */, int reps) {
+__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_tune(LpCtx c, double* t_out /* [3 + 8][G] */, int reps) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Reducer R = make_reducer(smem_raw, c.partials);
     const int m = c.m;
     long long acc_at = 0, acc_a = 0;
+    // sections of one iteration as seen by thread 0 of every CTA (SM cycles): [0] A' pass, [1] wait at barrier 1, [2] A pass,
+    // [3] block_store, [4] wait at barrier 2, [5] finish, [6] vector update, [7] wait at barrier 3
+    long long sec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double sink = 0.0;
     spmv_prefetch(c.AT, R.ws);
     grid_sync(grid);
@@ -397,8 +400,11 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_tune(LpCtx c
         __syncthreads();
         const long long t3 = clock64();
         R.block_store<7>(d);
+        const long long t4 = clock64();
         grid_sync(grid);
+        const long long t5 = clock64();
         R.finish<7>(d);
+        const long long t6 = clock64();
         sink += d[0] + d[1] + d[2] + d[3] + d[4] + d[5] + d[6];
         const double alpha = 0.0 * sink;
         GRID_STRIDE(i, m) {
@@ -407,10 +413,15 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_tune(LpCtx c
             c.r[i] = ri;
             c.p[i] = fma(1.0, pi, alpha * (__ldg(c.M + i) * ri));
         }
+        __syncthreads();
+        const long long t7 = clock64();
         grid_sync(grid);
+        const long long t8 = clock64();
         if (rep > 0) {
             acc_at += t1 - t0;
             acc_a += t3 - t2;
+            sec[0] += t1 - t0; sec[1] += t2 - t1; sec[2] += t3 - t2; sec[3] += t4 - t3;
+            sec[4] += t5 - t4; sec[5] += t6 - t5; sec[6] += t7 - t6; sec[7] += t8 - t7;
         }
     }
     release_reducer(R);
@@ -418,6 +429,8 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_tune(LpCtx c
         t_out[VB()] = (double)acc_at;
         t_out[VG() + VB()] = (double)acc_a;
         t_out[2 * VG() + VB()] = sink;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t_out[(3 + k) * VG() + VB()] = (double)sec[k];
     }
 }
 
@@ -1435,8 +1448,8 @@ static int tune_balance(abipgpu_lp* e, const std::vector<int>& a_ptr, const std:
     cur[1] = *planAT;
     CK(cudaFuncSetAttribute((const void*)k_tune, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     double* d_t = nullptr;
-    CK(dev_alloc((void**)&d_t, sizeof(double) * 3 * G, e->stream));
-    std::vector<double> t(3 * (size_t)G);
+    CK(dev_alloc((void**)&d_t, sizeof(double) * 11 * G, e->stream));
+    std::vector<double> t(11 * (size_t)G);
     double best_score = 1e300;
     int best_round = -1, uploaded_round = 0;
     int cl = 0;
@@ -1444,7 +1457,7 @@ static int tune_balance(abipgpu_lp* e, const std::vector<int>& a_ptr, const std:
     const double us_per_cycle = cl > 0 ? 1e3 / (double)cl : 1.0 / 1965.0;
     for (int round = 0; round <= rounds; ++round) {
         if (launch_coop(e, (const void*)k_tune, G, e->smem, e->ctx, d_t, reps)) return -1;
-        CK(cudaMemcpyAsync(t.data(), d_t, sizeof(double) * 3 * G, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(t.data(), d_t, sizeof(double) * 11 * G, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         double mx[2] = {0, 0}, mean[2] = {0, 0};
         for (int k = 0; k < 2; ++k) {
@@ -1463,6 +1476,18 @@ static int tune_balance(abipgpu_lp* e, const std::vector<int>& a_ptr, const std:
         if (env_int("ABIP_GPU_TUNE_VERBOSE", 0))
             fprintf(stderr, "[abip_gpu] balance round %d: slowest CTA A' %.1f us (mean %.1f), A %.1f us (mean %.1f)\n", round,
                     mx[1] * to_us, mean[1] * to_us, mx[0] * to_us, mean[0] * to_us);
+        if (env_int("ABIP_GPU_TUNE_VERBOSE", 0) > 1) {
+            static const char* nm[8] = {"A' pass", "barrier 1 wait", "A pass", "block_store", "barrier 2 wait", "finish", "update", "barrier 3 wait"};
+            double tot = 0;
+            for (int k = 0; k < 8; ++k) {
+                const double* sk = t.data() + (size_t)(3 + k) * G;
+                double mn = 1e300, mxs = 0, av = 0;
+                for (int b = 0; b < G; ++b) { mn = std::min(mn, sk[b]); mxs = std::max(mxs, sk[b]); av += sk[b] / G; }
+                fprintf(stderr, "[abip_gpu]   section %-15s us per iteration: mean %6.2f  min %6.2f  max %6.2f\n", nm[k], av * to_us, mn * to_us, mxs * to_us);
+                tot += av * to_us;
+            }
+            fprintf(stderr, "[abip_gpu]   sum of the means %.2f us per iteration\n", tot);
+        }
         if (score < best_score) {
             best_score = score;
             best_round = round;
@@ -1570,6 +1595,70 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     auto par = [&](long cnt, auto fn) { parallel_for(cnt, host_threads, fn); };
     std::vector<int> at_ptr, at_idx, a_ptr, a_idx, perm;
     if (transpose_csc(m, n, Ap, Ai, host_threads, &at_ptr, &at_idx, &a_ptr, &a_idx, &perm)) return -1;
+    // Locality ordering (sjds_host.h): whole-device engines work in a permuted index space in which structurally
+    // identical rows / columns are neighbours, so the 32 lanes of a gather touch a few lines instead of 32.
+    // e_* : the engine's matrices; e_a_src / e_at_src: position of every entry in the caller's CSC arrays.
+    lap(0);
+    std::vector<int> row_n2o, col_n2o;
+    bool reorder = env_int("ABIP_GPU_REORDER", 1) != 0 && t_order_request != 0 && !t_batch && t_grid_request == 0;
+    if (reorder) {
+        const auto t_o0 = std::chrono::steady_clock::now();
+        sjds::locality_order((int)m, (int)n, a_ptr, a_idx, at_ptr, at_idx, sjds::kLongRow, &row_n2o, &col_n2o, par);
+        bool ident = true;
+        for (long i = 0; i < m && ident; ++i) ident = row_n2o[i] == i;
+        for (long j = 0; j < n && ident; ++j) ident = col_n2o[j] == j;
+        if (ident) reorder = false;
+        e->order_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_o0).count();
+    }
+    e->permuted = reorder;
+    lap(1);
+    std::vector<int> e_a_ptr, e_a_idx, e_a_src, e_at_ptr, e_at_idx, e_at_src;
+    if (reorder) {
+        std::vector<int> row_o2n(m), col_o2n(n);
+        for (long i = 0; i < m; ++i) row_o2n[row_n2o[i]] = (int)i;
+        for (long j = 0; j < n; ++j) col_o2n[col_n2o[j]] = (int)j;
+        e_a_ptr.assign(m + 1, 0);
+        e_a_idx.resize(nnz);
+        e_a_src.resize(nnz);
+        for (long i = 0; i < m; ++i) e_a_ptr[i + 1] = e_a_ptr[i] + (a_ptr[row_n2o[i] + 1] - a_ptr[row_n2o[i]]);
+        par(m, [&](long i0, long i1, int) {
+            for (long i = i0; i < i1; ++i) {
+                int q = e_a_ptr[i];
+                for (int k = a_ptr[row_n2o[i]]; k < a_ptr[row_n2o[i] + 1]; ++k, ++q) {
+                    e_a_idx[q] = col_o2n[a_idx[k]];
+                    e_a_src[q] = perm[k];
+                }
+            }
+        });
+        e_at_ptr.assign(n + 1, 0);
+        e_at_idx.resize(nnz);
+        e_at_src.resize(nnz);
+        for (long j = 0; j < n; ++j) e_at_ptr[j + 1] = e_at_ptr[j] + (at_ptr[col_n2o[j] + 1] - at_ptr[col_n2o[j]]);
+        par(n, [&](long j0, long j1, int) {
+            for (long j = j0; j < j1; ++j) {
+                int q = e_at_ptr[j];
+                for (int k = at_ptr[col_n2o[j]]; k < at_ptr[col_n2o[j] + 1]; ++k, ++q) {
+                    e_at_idx[q] = row_o2n[at_idx[k]];
+                    e_at_src[q] = k;
+                }
+            }
+        });
+    } else {
+        e_a_ptr = a_ptr;
+        e_a_idx = a_idx;
+        e_a_src = perm;
+        e_at_ptr = at_ptr;
+        e_at_idx = at_idx;
+    }
+    std::vector<double> a_val(scale_out ? 0 : nnz), at_val(scale_out ? 0 : nnz);
+    if (!scale_out) {
+        par(nnz, [&](long q0, long q1, int) {
+            for (long q = q0; q < q1; ++q) a_val[q] = Ax[e_a_src[q]];
+            if (reorder) for (long q = q0; q < q1; ++q) at_val[q] = Ax[e_at_src[q]];
+            else memcpy(at_val.data() + q0, Ax + q0, sizeof(double) * (q1 - q0));
+        });
+    }
+    lap(2);
     // persistent grid: a multiple of the SM count, common to all SpMV-bearing kernels
     {
         int g1, g2, g3, g4;
@@ -1611,98 +1700,20 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         }
     }
     const int W = e->grid * kWarps;
-    // Locality ordering (sjds_host.h): whole-device engines work in a permuted index space in which structurally
-    // identical rows / columns are neighbours, so the 32 lanes of a gather touch a few lines instead of 32.
-    // e_* : the engine's matrices; e_a_src / e_at_src: position of every entry in the caller's CSC arrays.
-    lap(0);
-    std::vector<int> row_n2o, col_n2o;
-    bool reorder = env_int("ABIP_GPU_REORDER", 1) != 0 && t_order_request != 0 && !t_batch && t_grid_request == 0;
-    if (reorder) {
-        const auto t_o0 = std::chrono::steady_clock::now();
-        sjds::locality_order((int)m, (int)n, a_ptr, a_idx, at_ptr, at_idx, sjds::kLongRow, &row_n2o, &col_n2o, par);
-        bool ident = true;
-        for (long i = 0; i < m && ident; ++i) ident = row_n2o[i] == i;
-        for (long j = 0; j < n && ident; ++j) ident = col_n2o[j] == j;
-        if (ident) reorder = false;
-        e->order_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_o0).count();
-    }
-    e->permuted = reorder;
-    lap(1);
-    // measured balance (tune_balance, opt-in: measured at cfg2 and found to change nothing, profiles/r02_spmv.md): whole-device
+    // measured balance (tune_balance; opt-in: measured at cfg2 and found to change nothing, profiles/r02_spmv.md): whole-device
     // engines of at least ABIP_GPU_TUNE_MIN_NNZ nonzeros, contiguous row ranges
     const bool tune = env_int("ABIP_GPU_TUNE", 0) != 0 && !e->batch && t_grid_request == 0 && e->grid > 1 &&
                       nnz >= (long)env_int("ABIP_GPU_TUNE_MIN_NNZ", 1000000) && env_int("ABIP_GPU_PLAN_DEAL", 0) == 0;
-    std::vector<int> e_a_ptr, e_a_idx, e_a_src, e_at_ptr, e_at_idx, e_at_src;
     SpmvPlan planA, planAT;
-    bool jds_at = false;
-    if (reorder) {
-        // A' first: its plan decides the chunks, and on the lane-per-row path the rows inside every chunk are then sorted by
-        // length and stored step-major (order_host.h: jds_sort_chunks) -- that is one more permutation of the columns of A,
-        // so CSR(A) is labelled afterwards
-        std::vector<int> row_o2n(m), col_o2n(n);
-        for (long i = 0; i < m; ++i) row_o2n[row_n2o[i]] = (int)i;
-        e_at_ptr.assign(n + 1, 0);
-        e_at_idx.resize(nnz);
-        e_at_src.resize(nnz);
-        for (long j = 0; j < n; ++j) e_at_ptr[j + 1] = e_at_ptr[j] + (at_ptr[col_n2o[j] + 1] - at_ptr[col_n2o[j]]);
-        par(n, [&](long j0, long j1, int) {
-            for (long j = j0; j < j1; ++j) {
-                int q = e_at_ptr[j];
-                for (int k = at_ptr[col_n2o[j]]; k < at_ptr[col_n2o[j] + 1]; ++k, ++q) {
-                    e_at_idx[q] = row_o2n[at_idx[k]];
-                    e_at_src[q] = k;
-                }
-            }
-        });
-        lap(2);
+    if (host_threads > 1) {
+        std::thread tp([&] { build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data(), nullptr, tune); });
         build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data(), nullptr, tune);
-        if (planAT.lanes_log2 == 0 && !tune && env_int("ABIP_GPU_JDS", 1) != 0) {
-            sjds::jds_sort_chunks(planAT.chunk, e_at_ptr, e_at_idx, e_at_src, col_n2o, par);
-            jds_at = true;
-        }
-        lap(3);
-        for (long j = 0; j < n; ++j) col_o2n[col_n2o[j]] = (int)j;
-        e_a_ptr.assign(m + 1, 0);
-        e_a_idx.resize(nnz);
-        e_a_src.resize(nnz);
-        for (long i = 0; i < m; ++i) e_a_ptr[i + 1] = e_a_ptr[i] + (a_ptr[row_n2o[i] + 1] - a_ptr[row_n2o[i]]);
-        par(m, [&](long i0, long i1, int) {
-            for (long i = i0; i < i1; ++i) {
-                int q = e_a_ptr[i];
-                for (int k = a_ptr[row_n2o[i]]; k < a_ptr[row_n2o[i] + 1]; ++k, ++q) {
-                    e_a_idx[q] = col_o2n[a_idx[k]];
-                    e_a_src[q] = perm[k];
-                }
-            }
-        });
-        lap(2);
-        build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data(), nullptr, tune);
+        tp.join();
     } else {
-        e_a_ptr = a_ptr;
-        e_a_idx = a_idx;
-        e_a_src = perm;
-        e_at_ptr = at_ptr;
-        e_at_idx = at_idx;
-        lap(2);
-        if (host_threads > 1) {
-            std::thread tp([&] { build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data(), nullptr, tune); });
-            build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data(), nullptr, tune);
-            tp.join();
-        } else {
-            build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data(), nullptr, tune);
-            build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data(), nullptr, tune);
-        }
+        build_spmv_plan(e_a_ptr, (int)m, W, "ABIP_GPU_LANES_A", &planA, e_a_idx.data(), nullptr, tune);
+        build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data(), nullptr, tune);
     }
     lap(3);
-    std::vector<double> a_val(scale_out ? 0 : nnz), at_val(scale_out ? 0 : nnz);
-    if (!scale_out) {
-        par(nnz, [&](long q0, long q1, int) {
-            for (long q = q0; q < q1; ++q) a_val[q] = Ax[e_a_src[q]];
-            if (reorder) for (long q = q0; q < q1; ++q) at_val[q] = Ax[e_at_src[q]];
-            else memcpy(at_val.data() + q0, Ax + q0, sizeof(double) * (q1 - q0));
-        });
-    }
-    lap(2);
     // One device arena for all matrix and plan arrays: packed on the host (zero padding of kPad elements behind every
     // array included) and uploaded with ONE allocation and ONE copy -- 14 arrays x (malloc + memset + copy) were a
     // third of the driver calls of an engine set-up, which is what limits a batch of small LPs.
@@ -1809,7 +1820,6 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
               e->A_cl, e->A_lr, e->A_lp, 1, nullptr, nullptr, nullptr};
     c.AT = Csr{e->AT_ptr, e->AT_idx, e->AT_val, (int)n, e->AT_wc, e->AT_chunk, planAT.lanes_log2,
                e->AT_cl, e->AT_lr, e->AT_lp, 2, nullptr, nullptr, nullptr};
-    c.AT.jds = jds_at ? 1 : 0;
     c.M = e->dM;
     c.D = nullptr;
     c.E = nullptr;
@@ -1883,7 +1893,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
              "%d lane(s)/row | nnz=%ld | locality ordering %s | set-up ms: transpose %.0f, ordering %.0f, permuted CSR %.0f, grid+plans %.0f, arena+upload %.0f, scaling %.0f, precond %.0f, measured balance %.0f (%d rounds, kept round %d: slowest CTA A' %.1f -> %.1f us, A %.1f -> %.1f us)",
              device, prop.name, e->num_sms, e->grid, kBlock, (size_t)e->smem, (int)m, planA.mean, planA.max_len,
              planA.chunk.size(), planA.n_long, 1 << planA.lanes_log2, (int)n, planAT.mean, planAT.max_len,
-             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, reorder ? (jds_at ? "on, A' chunks step-major" : "on") : "off", e->setup_ms[0], e->setup_ms[1], e->setup_ms[2], e->setup_ms[3], e->setup_ms[4], e->setup_ms[5], e->setup_ms[6], e->setup_ms[7], e->tune_rounds, e->tune_best_round, e->tune_first_us[0], e->tune_best_us[0], e->tune_first_us[1], e->tune_best_us[1]);
+             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, reorder ? "on" : "off", e->setup_ms[0], e->setup_ms[1], e->setup_ms[2], e->setup_ms[3], e->setup_ms[4], e->setup_ms[5], e->setup_ms[6], e->setup_ms[7], e->tune_rounds, e->tune_best_round, e->tune_first_us[0], e->tune_best_us[0], e->tune_first_us[1], e->tune_best_us[1]);
     return 0;
 }
 
