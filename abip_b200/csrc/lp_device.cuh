@@ -79,10 +79,6 @@ struct Csr {
     const double* sm_val;
     const unsigned short* sm_idx;
     const int* sm_ptr;
-    // chunk-local step-major ("JDS") layout, reordered whole-device engines (order_host.h: jds_sort_chunks): inside every chunk
-    // of whole rows the rows are sorted by decreasing length and val / idx hold step 0 of all rows (in row order), then
-    // step 1 of the rows that have one, ...  Entry j of row r of the chunk sits at (entries of the steps before j) + r.
-    int jds;
 };
 
 // Per-warp staging buffer in shared memory: [val window | idx window | row-ptr window].  The value and index windows
@@ -383,53 +379,6 @@ __device__ __forceinline__ void spmv_rows(const Csr& A, const double* x, WarpSme
         SPROF(0);
         const int row0 = d.x, s = d.y, nr = d.z, n = d.w;
         const int off = s & 3;
-        if (nr > 0 && A.jds) {
-            // Step-major chunk.  (1) element-parallel: lane l owns the window positions l + 32 t -- ALL gathers of the chunk
-            // are in flight at once (one round trip to L2 per chunk; the lane-per-row loop needed one per kL1U steps), and
-            // a request covers 32 consecutive positions = the same step of neighbouring rows, which the locality ordering
-            // has made neighbours in x as well; products go back to the window.  (2) lane-per-row sums out of shared
-            // memory: step j of row r is at base_j + r, consecutive lanes read consecutive words; the row is summed in its
-            // own order with separate multiply and add (the reference's summation order, linsys/common.c:624-634).
-            const int* rp = reinterpret_cast<const int*>(st + kValWin + kIdxWin) + (row0 & 3);
-            int len0 = 0, len1 = 0;
-            if (lane < nr) len0 = rp[lane + 1] - rp[lane];
-            if (lane + 32 < nr) len1 = rp[lane + 33] - rp[lane + 32];
-            {
-                int ci[8];
-                double xg[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) ci[t] = iw[lane + 32 * t];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) xg[t] = x[ci[t]];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) vw[lane + 32 * t] = __dmul_rn(vw[lane + 32 * t], xg[t]);
-            }
-            __syncwarp();
-            SPROF(1);
-            const double* vs = vw + off + lane;
-            const int mx = __reduce_max_sync(0xffffffffu, max(len0, len1));
-            double acc0 = 0.0, acc1 = 0.0;
-            int base = 0;
-            for (int j = 0; j < mx; ++j) {
-                const bool h0 = j < len0, h1 = j < len1;
-                if (h0) acc0 = __dadd_rn(acc0, vs[base]);
-                if (h1) acc1 = __dadd_rn(acc1, vs[base + 32]);
-                base += __popc(__ballot_sync(0xffffffffu, h0)) + __popc(__ballot_sync(0xffffffffu, h1));
-            }
-            __syncwarp();  // every lane is done reading the buffer before it is overwritten
-            SPROF(2);
-            if (c + 1 < c1) ws.issue(A, c + 1, dn);
-            else if (next && nx_c < nx_c1) ws.issue(*next, nx_c, dn);
-            else ws.cur = nullptr;
-            d = dn;
-            SPROF(3);
-            if (lane < nr) fn(row0 + lane, acc0);
-            if (lane + 32 < nr) fn(row0 + lane + 32, acc1);
-#ifdef ABIP_PHASE_TIMING
-            ++_pn;
-#endif
-            continue;
-        }
         if (nr > 0 && L == 1) {
             // short rows (mean <= 16 nonzeros): one lane per row straight out of the staged windows -- index, value,
             // gather, multiply, add in the row's own order (the reference's summation order, no FMA contraction so the

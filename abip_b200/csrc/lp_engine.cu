@@ -790,35 +790,9 @@ __global__ void k_build_h(const double* b, const double* c, double* h, double* g
 __global__ void k_precond(Csr A, double* M) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= A.nrows) return;
-    const int a = A.ptr[row], b = A.ptr[row + 1];
-    if (A.jds && b - a <= kChunk) return;  // rows inside step-major chunks: k_precond_jds
     double s = 0.0;
-    for (int k = a; k < b; ++k) s = fma(A.val[k], A.val[k], s);
+    for (int k = A.ptr[row]; k < A.ptr[row + 1]; ++k) s = fma(A.val[k], A.val[k], s);
     M[row] = 1.0 / s;
-}
-// same for the rows of step-major chunks (Csr::jds): one warp per chunk, lane l = rows l and l + 32 of the chunk, entry j of
-// row r at (entries of the steps before j) + r; every row is summed in its own order, as above
-__global__ void k_precond_jds(Csr A, int nchunks, double* M) {
-    const int c = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (c >= nchunks) return;
-    const int4 d = A.chunk[c];
-    if (d.z <= 0) return;  // piece of a long row
-    const int row0 = d.x, nr = d.z;
-    int len0 = 0, len1 = 0;
-    if (lane < nr) len0 = A.ptr[row0 + lane + 1] - A.ptr[row0 + lane];
-    if (lane + 32 < nr) len1 = A.ptr[row0 + lane + 33] - A.ptr[row0 + lane + 32];
-    const int mx = __reduce_max_sync(0xffffffffu, max(len0, len1));
-    const double* v = A.val + d.y + lane;
-    double s0 = 0.0, s1 = 0.0;
-    int base = 0;
-    for (int j = 0; j < mx; ++j) {
-        const bool h0 = j < len0, h1 = j < len1;
-        if (h0) s0 = fma(v[base], v[base], s0);
-        if (h1) s1 = fma(v[base + 32], v[base + 32], s1);
-        base += __popc(__ballot_sync(0xffffffffu, h0)) + __popc(__ballot_sync(0xffffffffu, h1));
-    }
-    if (lane < nr) M[row0 + lane] = 1.0 / s0;
-    if (lane + 32 < nr) M[row0 + lane + 32] = 1.0 / s1;
 }
 
 
@@ -1639,8 +1613,6 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     e->permuted = reorder;
     lap(1);
     std::vector<int> e_a_ptr, e_a_idx, e_a_src, e_at_ptr, e_at_idx, e_at_src;
-    std::vector<int> e_a_ocol, e_at_orow;  // the caller's column / row index of every entry (step-major chunks, below)
-    const bool jds = reorder && env_int("ABIP_GPU_JDS", 1) != 0 && env_int("ABIP_GPU_TUNE", 0) == 0;
     if (reorder) {
         std::vector<int> row_o2n(m), col_o2n(n);
         for (long i = 0; i < m; ++i) row_o2n[row_n2o[i]] = (int)i;
@@ -1648,7 +1620,6 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         e_a_ptr.assign(m + 1, 0);
         e_a_idx.resize(nnz);
         e_a_src.resize(nnz);
-        if (jds) { e_a_ocol.resize(nnz); e_at_orow.resize(nnz); }
         for (long i = 0; i < m; ++i) e_a_ptr[i + 1] = e_a_ptr[i] + (a_ptr[row_n2o[i] + 1] - a_ptr[row_n2o[i]]);
         par(m, [&](long i0, long i1, int) {
             for (long i = i0; i < i1; ++i) {
@@ -1656,7 +1627,6 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
                 for (int k = a_ptr[row_n2o[i]]; k < a_ptr[row_n2o[i] + 1]; ++k, ++q) {
                     e_a_idx[q] = col_o2n[a_idx[k]];
                     e_a_src[q] = perm[k];
-                    if (jds) e_a_ocol[q] = a_idx[k];
                 }
             }
         });
@@ -1670,7 +1640,6 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
                 for (int k = at_ptr[col_n2o[j]]; k < at_ptr[col_n2o[j] + 1]; ++k, ++q) {
                     e_at_idx[q] = row_o2n[at_idx[k]];
                     e_at_src[q] = k;
-                    if (jds) e_at_orow[q] = at_idx[k];
                 }
             }
         });
@@ -1680,6 +1649,14 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         e_a_src = perm;
         e_at_ptr = at_ptr;
         e_at_idx = at_idx;
+    }
+    std::vector<double> a_val(scale_out ? 0 : nnz), at_val(scale_out ? 0 : nnz);
+    if (!scale_out) {
+        par(nnz, [&](long q0, long q1, int) {
+            for (long q = q0; q < q1; ++q) a_val[q] = Ax[e_a_src[q]];
+            if (reorder) for (long q = q0; q < q1; ++q) at_val[q] = Ax[e_at_src[q]];
+            else memcpy(at_val.data() + q0, Ax + q0, sizeof(double) * (q1 - q0));
+        });
     }
     lap(2);
     // persistent grid: a multiple of the SM count, common to all SpMV-bearing kernels
@@ -1737,34 +1714,6 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
         build_spmv_plan(e_at_ptr, (int)n, W, "ABIP_GPU_LANES_AT", &planAT, e_at_idx.data(), nullptr, tune);
     }
     lap(3);
-    if (jds) {
-        // Step-major chunks (lp_device.cuh, Csr::jds): inside every chunk of whole rows of BOTH matrices the rows are sorted by
-        // length and the entries stored step by step (order_host.h: jds_sort_chunks).  That permutes the columns of A inside
-        // the chunks of A' and the rows of A inside the chunks of A: one more (local) change of the engine's index space,
-        // so the entries are labelled afterwards from the caller's indices carried along.
-        sjds::jds_sort_chunks(planAT.chunk, e_at_ptr, e_at_orow, e_at_src, col_n2o, par);
-        sjds::jds_sort_chunks(planA.chunk, e_a_ptr, e_a_ocol, e_a_src, row_n2o, par);
-        std::vector<int> row_o2n(m), col_o2n(n);
-        for (long i = 0; i < m; ++i) row_o2n[row_n2o[i]] = (int)i;
-        for (long j = 0; j < n; ++j) col_o2n[col_n2o[j]] = (int)j;
-        par(nnz, [&](long q0, long q1, int) {
-            for (long q = q0; q < q1; ++q) {
-                e_at_idx[q] = row_o2n[e_at_orow[q]];
-                e_a_idx[q] = col_o2n[e_a_ocol[q]];
-            }
-        });
-        std::vector<int>().swap(e_a_ocol);
-        std::vector<int>().swap(e_at_orow);
-    }
-    std::vector<double> a_val(scale_out ? 0 : nnz), at_val(scale_out ? 0 : nnz);
-    if (!scale_out) {
-        par(nnz, [&](long q0, long q1, int) {
-            for (long q = q0; q < q1; ++q) a_val[q] = Ax[e_a_src[q]];
-            if (reorder) for (long q = q0; q < q1; ++q) at_val[q] = Ax[e_at_src[q]];
-            else memcpy(at_val.data() + q0, Ax + q0, sizeof(double) * (q1 - q0));
-        });
-    }
-    lap(2);
     // One device arena for all matrix and plan arrays: packed on the host (zero padding of kPad elements behind every
     // array included) and uploaded with ONE allocation and ONE copy -- 14 arrays x (malloc + memset + copy) were a
     // third of the driver calls of an engine set-up, which is what limits a batch of small LPs.
@@ -1871,7 +1820,6 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
               e->A_cl, e->A_lr, e->A_lp, 1, nullptr, nullptr, nullptr};
     c.AT = Csr{e->AT_ptr, e->AT_idx, e->AT_val, (int)n, e->AT_wc, e->AT_chunk, planAT.lanes_log2,
                e->AT_cl, e->AT_lr, e->AT_lp, 2, nullptr, nullptr, nullptr};
-    c.A.jds = c.AT.jds = jds ? 1 : 0;
     c.M = e->dM;
     c.D = nullptr;
     c.E = nullptr;
@@ -1930,7 +1878,6 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
     }
     lap(5);
     k_precond<<<(unsigned)((m + 255) / 256), 256, 0, e->stream>>>(c.A, e->dM);
-    if (jds) k_precond_jds<<<(unsigned)((planA.chunk.size() * 32 + 255) / 256), 256, 0, e->stream>>>(c.A, (int)planA.chunk.size(), e->dM);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     lap(6);
@@ -1946,7 +1893,7 @@ static int create_impl(abipgpu_lp* e, abip_int m, abip_int n, const abip_int* Ap
              "%d lane(s)/row | nnz=%ld | locality ordering %s | set-up ms: transpose %.0f, ordering %.0f, permuted CSR %.0f, grid+plans %.0f, arena+upload %.0f, scaling %.0f, precond %.0f, measured balance %.0f (%d rounds, kept round %d: slowest CTA A' %.1f -> %.1f us, A %.1f -> %.1f us)",
              device, prop.name, e->num_sms, e->grid, kBlock, (size_t)e->smem, (int)m, planA.mean, planA.max_len,
              planA.chunk.size(), planA.n_long, 1 << planA.lanes_log2, (int)n, planAT.mean, planAT.max_len,
-             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, reorder ? (jds ? "on, step-major chunks" : "on") : "off", e->setup_ms[0], e->setup_ms[1], e->setup_ms[2], e->setup_ms[3], e->setup_ms[4], e->setup_ms[5], e->setup_ms[6], e->setup_ms[7], e->tune_rounds, e->tune_best_round, e->tune_first_us[0], e->tune_best_us[0], e->tune_first_us[1], e->tune_best_us[1]);
+             planAT.chunk.size(), planAT.n_long, 1 << planAT.lanes_log2, nnz, reorder ? "on" : "off", e->setup_ms[0], e->setup_ms[1], e->setup_ms[2], e->setup_ms[3], e->setup_ms[4], e->setup_ms[5], e->setup_ms[6], e->setup_ms[7], e->tune_rounds, e->tune_best_round, e->tune_first_us[0], e->tune_best_us[0], e->tune_first_us[1], e->tune_best_us[1]);
     return 0;
 }
 

@@ -117,53 +117,4 @@ static inline void locality_order(int m, int n, const std::vector<int>& a_ptr, c
 }
 
 
-// Chunk-local JDS layout for a matrix on the lane-per-row path of the SpMV (lp_device.cuh, Csr::jds).  `chunks` are the plan's
-// descriptors {row0, nnz0, rows, nnz}; only chunks of whole rows (rows > 0) are touched, and only their inside:
-//   * the rows of a chunk are sorted by decreasing length (stable): `new2old` (row new -> old map of the engine's index space)
-//     and `ptr` (pointers of the sorted rows; the chunk still covers [nnz0, nnz0 + nnz)) are rewritten accordingly;
-//   * idx and src (position of every entry in the caller's arrays) are stored step-major: all first entries of the rows
-//     in row order, then all second entries of the rows that have one, ...  Entry j of sorted row r sits at
-//     nnz0 + (number of entries of the steps before j) + r.
-// The order of the entries of a row (its summation order) is unchanged.  Pure function of the structure.
-template <class Desc, class ParFor>
-static inline void jds_sort_chunks(const std::vector<Desc>& chunks, std::vector<int>& ptr, std::vector<int>& idx,
-                                   std::vector<int>& src, std::vector<int>& new2old, ParFor par) {
-    par((long)chunks.size(), [&](long c0, long c1, int) {
-        std::vector<int> lens, order, t_idx, t_src, t_n2o;
-        for (long c = c0; c < c1; ++c) {
-            const int row0 = chunks[c].x, s = chunks[c].y, nr = chunks[c].z, cnt = chunks[c].w;
-            if (nr <= 0) continue;
-            lens.resize(nr);
-            order.resize(nr);
-            for (int i = 0; i < nr; ++i) {
-                lens[i] = ptr[row0 + i + 1] - ptr[row0 + i];
-                order[i] = i;
-            }
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
-            t_idx.resize(cnt);
-            t_src.resize(cnt);
-            t_n2o.resize(nr);
-            int pos = 0;
-            const int maxlen = lens[order[0]];
-            for (int j = 0; j < maxlen; ++j)
-                for (int r = 0; r < nr && lens[order[r]] > j; ++r) {
-                    const int k = ptr[row0 + order[r]] + j;
-                    t_idx[pos] = idx[k];
-                    t_src[pos] = src[k];
-                    ++pos;
-                }
-            for (int r = 0; r < nr; ++r) t_n2o[r] = new2old[row0 + order[r]];
-            // (pos == cnt: the chunk covers whole rows)
-            std::copy(t_idx.begin(), t_idx.begin() + pos, idx.begin() + s);
-            std::copy(t_src.begin(), t_src.begin() + pos, src.begin() + s);
-            int q = s;
-            for (int r = 0; r < nr; ++r) {
-                new2old[row0 + r] = t_n2o[r];
-                ptr[row0 + r] = q;
-                q += lens[order[r]];
-            }
-        }
-    });
-}
-
 }  // namespace sjds
