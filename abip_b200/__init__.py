@@ -5,5 +5,7 @@ host-side mirror of the reference's `abip(data, K, params)` entry (api.py).  No 
 """
 from .api import abip, lp_solve, lp_solve_batch, get_params, LinSysPlugin, LpEngine, LpSolver  # noqa: F401
 from . import problems  # noqa: F401
+from .lasso import lasso_solve, lasso_cone_program  # noqa: F401
 
-__all__ = ["abip", "lp_solve", "get_params", "LinSysPlugin", "LpEngine", "LpSolver", "lp_solve_batch", "problems"]
+__all__ = ["abip", "lp_solve", "get_params", "LinSysPlugin", "LpEngine", "LpSolver", "lp_solve_batch", "problems",
+           "lasso_solve", "lasso_cone_program"]

@@ -270,3 +270,33 @@ def cfg3(seed: int = 3, scale: float = 1.0) -> QCPProblem:
     m = max(4, int(round(100000 * scale)))
     return random_qcp(m, n_soc, 50, nnz_per_col=20, q_offdiag_per_col=2, seed=seed, with_q=True,
                       name=f"cfg3_socp_scale{scale:g}")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Lasso instances (abip_b200/lasso.py): seeded, shared by tests/golden/make_golden_lasso.py and the tests; the recipe
+# follows the reference's scripts/bench-qcp/get_lasso_simu_data.m (Gaussian design, sparse ground truth, noisy response,
+# lambda a fraction of |X'y|_inf)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def _lasso_case(m, n, density, k, seed, frac):
+    def make():
+        rng = np.random.default_rng(seed)
+        if density < 1.0:
+            X = sp.random(m, n, density=density, random_state=seed, format="csc")
+            X.data = rng.standard_normal(X.nnz)
+        else:
+            X = sp.csc_matrix(rng.standard_normal((m, n)))
+        w0 = np.zeros(n)
+        w0[rng.choice(n, k, replace=False)] = rng.standard_normal(k)
+        y = X @ w0 + 0.01 * rng.standard_normal(m)
+        lam = frac * float(np.max(np.abs(X.T @ y)))
+        return X, y, lam
+    return make
+
+
+LASSO_CASES = {
+    "sparse_wide": _lasso_case(60, 150, 0.3, 8, 11, 0.1),
+    "dense_tall": _lasso_case(120, 40, 1.0, 6, 12, 0.05),
+    "sparse_wide_more_features": _lasso_case(80, 200, 0.1, 10, 13, 0.1),
+}
