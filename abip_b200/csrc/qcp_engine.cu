@@ -10,7 +10,8 @@
 //     H = Q + rho_x I,   (rho_y I + A H^-1 A') y = b_y - A H^-1 b_x,   x = H^-1 (b_x + A'y),
 // an m-space system as well conditioned as ABIP-LP's (rho_y I + AA'), solved by Jacobi-preconditioned CG to a
 // relative residual (default 1e-8).  H^-1 is exact when Q is diagonal or absent and an inner Jacobi-PCG (1e-13)
-// otherwise.  With that accuracy the ADMM iteration counts equal those of the reference's direct (QDLDL) path.
+// otherwise (1e-3 x the outer tolerance inside the operator of the outer CG).  With that accuracy the ADMM iteration counts
+// equal those of the reference's direct (QDLDL) path.
 #include "qcp_engine.h"
 
 #include <cmath>
@@ -46,7 +47,7 @@ struct QcpIterArgs {
 // visible grid-wide (last phase is followed by a grid barrier).
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int dev_hinv_general(const QcpCtx& c, Reducer& R, cg::grid_group& grid, const double* v,
-                                                double* x) {
+                                                double* x, double itol = 1e-13) {
     const int n = c.n;
     double s1[1] = {0.0};
     GRID_STRIDE(j, n) {
@@ -57,7 +58,7 @@ __device__ __forceinline__ int dev_hinv_general(const QcpCtx& c, Reducer& R, cg:
     R.block_store<1>(s1);
     grid_sync(grid);
     R.finish<1>(s1);
-    const double tol = 1e-13 * sqrt(s1[0]);
+    const double tol = itol * sqrt(s1[0]);
     double s2[2] = {0.0, 0.0};
     spmv_rows(c.Q, x, R.ws, nullptr, [&](int row, double a) {
         const double rj = v[row] - fma(c.rho_x, x[row], a);
@@ -72,35 +73,43 @@ __device__ __forceinline__ int dev_hinv_general(const QcpCtx& c, Reducer& R, cg:
     R.finish<2>(s2);
     double rr = s2[0], rz = s2[1];
     int its = 0;
+    // Two grid barriers per iteration (as in the LP engine's PCG, lp_device.cuh: dev_solve_lin_sys): the epilogue of the Q
+    // pass also reduces r.Hp, Hp.Hp, (M r).Hp, (M Hp).Hp, so |r - al Hp|^2 and (M r').r' -- the stopping test and beta --
+    // are known right after alpha, and x, r, p are updated in ONE phase; (M r).r and |r|^2 of the current residual are
+    // re-measured by the same epilogue, so the expanded forms never accumulate.
     while (sqrt(rr) > tol && its < 500) {
-        double d1[1] = {0.0};
+        double d[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         spmv_rows(c.Q, c.ip, R.ws, nullptr, [&](int row, double a) {
-            const double pj = c.ip[row];
+            const double pj = c.ip[row], rj = c.ir[row], hd = __ldg(c.Hd + row);
             const double hp = fma(c.rho_x, pj, a);
             c.iHp[row] = hp;
-            d1[0] = fma(pj, hp, d1[0]);
+            const double zj = rj / hd, mg = hp / hd;
+            d[0] = fma(pj, hp, d[0]);
+            d[1] = fma(zj, hp, d[1]);
+            d[2] = fma(mg, hp, d[2]);
+            d[3] = fma(rj, hp, d[3]);
+            d[4] = fma(hp, hp, d[4]);
+            d[5] = fma(zj, rj, d[5]);
+            d[6] = fma(rj, rj, d[6]);
         });
-        R.block_store<1>(d1);
+        R.block_store<7>(d);
         grid_sync(grid);
-        R.finish<1>(d1);
-        const double al = rz / d1[0];
-        double d2[2] = {0.0, 0.0};
+        R.finish<7>(d);
+        rz = d[5];
+        const double al = rz / d[0];
+        const double rr_new = fma(al, fma(al, d[4], -2.0 * d[3]), d[6]);
+        const double rz_new = fma(al, fma(al, d[2], -2.0 * d[1]), rz);
+        const double be = rz_new / rz;
+        rr = fmax(rr_new, 0.0);
+        ++its;
+        const bool stop = !(sqrt(rr) > tol);
         GRID_STRIDE(j, n) {
-            x[j] = fma(al, c.ip[j], x[j]);
+            const double pj = c.ip[j];
+            x[j] = fma(al, pj, x[j]);
             const double rj = fma(-al, c.iHp[j], c.ir[j]);
             c.ir[j] = rj;
-            const double zj = rj / __ldg(c.Hd + j);
-            d2[0] = fma(rj, rj, d2[0]);
-            d2[1] = fma(rj, zj, d2[1]);
+            if (!stop) c.ip[j] = fma(be, pj, rj / __ldg(c.Hd + j));
         }
-        R.block_store<2>(d2);
-        grid_sync(grid);
-        R.finish<2>(d2);
-        const double be = d2[1] / rz;
-        rr = d2[0];
-        rz = d2[1];
-        ++its;
-        GRID_STRIDE(j, n) c.ip[j] = fma(be, c.ip[j], c.ir[j] / __ldg(c.Hd + j));
         grid_sync(grid);
     }
     return its;
@@ -270,9 +279,13 @@ __device__ __forceinline__ void dev_qcp_solve(const QcpCtx& c, Reducer& R, cg::g
     grid_sync(grid);
     R.finish<1>(a1);
     const double tol = rtol * sqrt(a1[0]);
+    // H^-1 inside the operator of the outer CG: three digits below the outer target are enough (an operator error of
+    // itol perturbs the attainable outer residual by ~ itol x iterations); the two solves that enter the solution
+    // directly (hb above, x below) stay at 1e-13
+    const double itol = fmin(1e-10, fmax(1e-13, 1e-3 * rtol));
     double* t1 = c.tn2;
     if (warm && !diag) {
-        inner += dev_hinv_general(c, R, grid, c.tn2, c.tn1);
+        inner += dev_hinv_general(c, R, grid, c.tn2, c.tn1, itol);
         t1 = c.tn1;
     }
     // 3. r = rhs - (rho_y w + A t), y = w; z = Ms r; p = z
@@ -312,7 +325,7 @@ __device__ __forceinline__ void dev_qcp_solve(const QcpCtx& c, Reducer& R, cg::g
             grid_sync(grid);
             t1 = c.tn2;
             if (!diag) {
-                inner += dev_hinv_general(c, R, grid, c.tn2, c.tn1);
+                inner += dev_hinv_general(c, R, grid, c.tn2, c.tn1, itol);
                 t1 = c.tn1;
             }
             double d1[1] = {0.0};
