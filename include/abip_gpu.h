@@ -174,7 +174,10 @@ abip_int abip_gpu_main(const ABIPData *d, ABIPSolution *sol, ABIPInfo *info);
  * abip_gpu_init_dist; rank r keeps a block of columns of A (a row block of the stored A').  The ranks then exchange
  * the 64-byte CUDA-IPC handles (abip_gpu_comm_export -> all-gather -> abip_gpu_comm_connect) and call abip_gpu_solve
  * collectively; sol->y is complete on every rank, sol->x / sol->s hold this rank's shard [c0, c0+nl) and zeros
- * elsewhere (sum over ranks = full vectors). */
+ * elsewhere (sum over ranks = full vectors).
+ * Not supported by the sharded engine: settings->half_update = 1 (abip_gpu_init_dist prints an error and returns NULL; the
+ * half-update pair of src/abip.c:607-700 is implemented in the single-GPU and batch engines only).  Wall-clock decisions
+ * (time limit, SIGINT) are taken per rank: give every rank the same limits. */
 ABIPGpuWork *abip_gpu_init_dist(const ABIPData *d, ABIPInfo *info, abip_int rank, abip_int world);
 abip_int abip_gpu_comm_export(ABIPGpuWork *w, void *handle64);
 abip_int abip_gpu_comm_connect(ABIPGpuWork *w, const void *handles /* world x 64 bytes, rank order */);
