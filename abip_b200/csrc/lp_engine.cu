@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(kBlock) k_mu_stats(const double* u, const doub
 // engine) as block 0 of a one-block virtual grid, then copies the engine's scalar block to the host-mapped output.
 // Replaces one launch + one copy + one synchronisation per problem and step by one launch + one synchronisation per
 // batch and step (the per-context driver lock serialised the per-problem calls at ~13 us each).
-enum { BATCH_ADMM = 0, BATCH_BB = 1, BATCH_MU = 2, BATCH_INNER = 3, BATCH_BBSEARCH = 4 };
+enum { BATCH_ADMM = 0, BATCH_BB = 1, BATCH_MU = 2, BATCH_INNER = 3, BATCH_BBSEARCH = 4, BATCH_SOLVE = 5 };
 struct BBSearchArgs {
     int lookback;
     double eps_cor, eps_pen;
@@ -542,16 +542,15 @@ struct BatchItem {
     IterArgs it;
     BBArgs bb;
     MuArgs mu;
-    LpInnerArgs inner;
+    LpSolveArgs solve;  // BATCH_INNER reads solve.in only
     BBSearchArgs search;
     int resident_bytes;  // shared memory needed to keep A and A' resident (0: not eligible)
     PreOp pre[kMaxPre];
     double* vec[21];
 };
-__device__ __forceinline__ void apply_pre_ops(const BatchItem& it) {
+__device__ __noinline__ void dev_pre_op(const BatchItem& it, const PreOp op) {
     const int m = it.c.m, l = it.c.m + it.c.n + 1;
-    for (int q = 0; q < it.n_pre; ++q) {
-        const PreOp op = it.pre[q];
+    {
         if (op.code == PRE_COLD) {  // cold_start_vars, src/abip.c:361-381
             const double val = sqrt(op.d0 / op.d1);
             double *u = it.vec[ABIPGPU_VEC_U], *v = it.vec[ABIPGPU_VEC_V];
@@ -613,6 +612,9 @@ __device__ __forceinline__ void apply_pre_ops(const BatchItem& it) {
         __syncthreads();
     }
 }
+__device__ __forceinline__ void apply_pre_ops(const BatchItem& it) {
+    for (int q = 0; q < it.n_pre; ++q) dev_pre_op(it, it.pre[q]);
+}
 // Shared-memory-resident matrices of a batch problem: [A: val f64 | A': val f64 | A: ptr i32 | A': ptr i32 | A: idx u16 |
 // A': idx u16] behind the reducer / barrier / plan-cache area (the TMA stages are not used in this mode).
 __host__ __device__ inline size_t resident_bytes_for(long m, long n, long nnz) {
@@ -672,77 +674,146 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_batch(const 
     apply_pre_ops(it);
     if (it.kind == BATCH_ADMM) body_admm_iter<false>(it.c, it.it, smem_raw, true);
     else if (it.kind == BATCH_BB) body_bb_round<false>(it.c, it.bb, smem_raw, true);
-    else if (it.kind == BATCH_INNER) {
-        // the inner ADMM loop of one outer iteration without leaving the device: every thread of the CTA reads the
-        // scalar block of the iteration and takes the decisions of the host loop (lp_logic.h) redundantly
-        const LpInnerArgs& L = it.inner;
+    else if (it.kind == BATCH_INNER || it.kind == BATCH_BBSEARCH || it.kind == BATCH_SOLVE) {
+        // Device-resident loops (decisions of the host loop taken redundantly by every thread of the CTA from the scalar block,
+        // lp_logic.h):  BATCH_INNER = the inner ADMM loop of one outer iteration (src/abip.c:2131-2214), BATCH_BBSEARCH = one
+        // Barzilai-Borwein search (src/adaptive.c:34-256), BATCH_SOLVE = the OUTER loop (src/abip.c:2093-2295): inner loop,
+        // convergence check, mu rule, re-initialisation, BB search, next outer iteration ... until the solve ends, the
+        // launch cap is reached or the restart bookkeeping needs the host.  One copy of the ADMM step and of the BB round
+        // serves all three kinds.
+        const LpSolveArgs& S = it.solve;
+        const LpInnerArgs& L = S.in;
+        const bool only_bb = it.kind == BATCH_BBSEARCH, whole = it.kind == BATCH_SOLVE;
         IterArgs a = it.it;
-        long j = L.j0, k = L.k0, done = 0;
-        double cg = 0.0;
-        int avg = L.avg_in, code = LP_INNER_CONTINUE;
-        for (;;) {
-            if (k >= L.restart_thresh) { code = LP_INNER_HOST; break; }
-            a.j = j;
-            a.k = k;
-            a.restart_active = 0;
-            a.restart_fire = 0;
-            body_admm_iter<false>(it.c, a, smem_raw, true);
-            __syncthreads();
-            const double* sc = it.c.sc;
-            k += 1;
-            done += 1;
-            cg += sc[ABIPGPU_SC_CG_ITS];
-            const double q = lp_qnorm_decide(sc, (double)L.max_admm_iters, &avg);
-            if (q < L.gamma * L.mu) {
-                if (L.half_update) {  // src/abip.c:2175-2186
-                    double* v = a.v;
-                    for (int i = threadIdx.x; i < it.c.m + it.c.n + 1; i += kBlock)
-                        if (v[i] < 0) v[i] = 1e-6;
-                }
-                code = LP_INNER_CONVERGED;
-                break;
-            }
-            if (L.final_check) {
-                LpResid r;
-                lp_calc_residuals(L.rin, sc, avg, &r);
-                const int status = lp_has_converged(L.eps, L.pfeasopt, &r, L.ipm_iter, k);
-                if (status != 0 || k + 1 >= L.max_admm_iters || L.ipm_iter + 1 >= L.max_ipm_iters) { code = LP_INNER_FINISHED; break; }
-            }
-            ++j;
-            if (j >= L.j_end) { code = LP_INNER_STOPPER; break; }
-            if (done >= L.cap) break;
-            __syncthreads();  // every thread has read the scalar block before the next iteration rewrites it
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            it.c.sc[ABIPGPU_SC_LOOP_EXIT] = (double)code;
-            it.c.sc[ABIPGPU_SC_LOOP_ITERS] = (double)done;
-            it.c.sc[ABIPGPU_SC_LOOP_CG] = cg;
-            it.c.sc[ABIPGPU_SC_LOOP_AVG] = (double)avg;
-        }
-    } else if (it.kind == BATCH_BBSEARCH) {
-        // the whole Barzilai-Borwein search (src/adaptive.c:34-256): lookback rounds + the safeguarded step on the device
         BBArgs b = it.bb;
-        double beta_prev = 1.0, beta = 0.0, cg = 0.0;
-        int carry = 0, rounds = 0;
-        for (int i = 0; i < it.search.lookback; ++i) {
-            b.carry = carry;
-            b.beta_prev = beta_prev;
-            body_bb_round<false>(it.c, b, smem_raw, true);
-            __syncthreads();
-            const double* sc = it.c.sc;
-            cg += sc[ABIPGPU_SC_CG_ITS] + sc[ABIPGPU_SC_CG_ITS2];
-            ++rounds;
-            const int action = lp_bb_step(sc, it.search.eps_cor, it.search.eps_pen, &beta_prev, &beta);
-            if (action == 0) break;
-            carry = action;
-            __syncthreads();
+        LpMuState ms{L.mu, S.sigma, L.gamma, S.dynamic_sigma, L.final_check, S.double_check};
+        double beta = L.beta, cg = 0.0, bb_beta = 0.0;
+        long i = L.ipm_iter, j = L.j0, k = L.k0, done = 0;
+        int avg = L.avg_in, code = LP_INNER_CONTINUE, rounds = 0;
+        bool resume = !whole || S.resume_inner != 0;
+        const double spmin = fmin(S.mp.sp, S.mp.sparsity_ratio);
+        for (;; ++i) {
+            if (!only_bb) {
+                if (whole && i >= L.max_ipm_iters) { code = LP_SOLVE_IPM; break; }
+                const long j_end = whole ? lp_inner_stopper(spmin, ms.mu, L.max_admm_iters) : L.j_end;
+                if (!resume) {  // start of an outer iteration (abipgpu_lp_outer_prologue)
+                    dev_pre_op(it, PreOp{PRE_PROLOGUE, avg, 0, 0, 0.0, 0.0});
+                    j = 0;
+                }
+                resume = false;
+                int icode = LP_INNER_STOPPER;
+                while (j < j_end) {
+                    if (k >= L.restart_thresh) { icode = LP_INNER_HOST; break; }
+                    if (done >= L.cap) { icode = LP_INNER_CONTINUE; break; }
+                    a.j = j;
+                    a.k = k;
+                    a.mu = ms.mu;
+                    a.beta = beta;
+                    a.restart_active = 0;
+                    a.restart_fire = 0;
+                    body_admm_iter<false>(it.c, a, smem_raw, true);
+                    __syncthreads();
+                    const double* sc = it.c.sc;
+                    k += 1;
+                    done += 1;
+                    cg += sc[ABIPGPU_SC_CG_ITS];
+                    const double q = lp_qnorm_decide(sc, (double)L.max_admm_iters, &avg);
+                    if (q < ms.gamma * ms.mu) {
+                        if (L.half_update) {  // src/abip.c:2175-2186
+                            double* v = a.v;
+                            for (int t = threadIdx.x; t < it.c.m + it.c.n + 1; t += kBlock)
+                                if (v[t] < 0) v[t] = 1e-6;
+                        }
+                        icode = LP_INNER_CONVERGED;
+                        break;
+                    }
+                    if (ms.final_check) {
+                        LpResid r;
+                        lp_calc_residuals(L.rin, sc, avg, &r);
+                        const int status = lp_has_converged(L.eps, L.pfeasopt, &r, i, k);
+                        if (status != 0 || k + 1 >= L.max_admm_iters || i + 1 >= L.max_ipm_iters) { icode = LP_INNER_FINISHED; break; }
+                    }
+                    ++j;
+                    icode = LP_INNER_STOPPER;
+                    __syncthreads();  // every thread has read the scalar block before the next iteration rewrites it
+                }
+                __syncthreads();
+                if (!whole || icode == LP_INNER_HOST || icode == LP_INNER_CONTINUE || icode == LP_INNER_FINISHED) {
+                    code = icode;
+                    break;
+                }
+                // after the inner loop (src/abip.c:2216-2277)
+                if (ms.mu < L.eps) ms.final_check = 1;
+                LpResid r;
+                lp_calc_residuals(L.rin, it.c.sc, avg, &r);
+                const int status = lp_has_converged(L.eps, L.pfeasopt, &r, i, k);
+                if (status != 0 || k + 1 >= L.max_admm_iters) { code = LP_SOLVE_DONE; break; }
+                const int rule = lp_mu_rule(&ms, S.mp);
+                if (rule == 1) lp_update_barrier(&ms, S.mp, r);
+                else if (rule == 2) lp_update_barrier_dynamic_2(&ms, S.mp);
+                else if (rule == 3) {
+                    __syncthreads();
+                    body_mu_stats(it.vec[avg ? ABIPGPU_VEC_UAVGC : ABIPGPU_VEC_U], it.vec[avg ? ABIPGPU_VEC_VAVGC : ABIPGPU_VEC_V],
+                                  it.c.m, it.c.m + it.c.n + 1, it.c.partials, it.c.sc, it.c.comm, true);
+                    __syncthreads();
+                    if (lp_update_barrier_dynamic(&ms, S.mp, it.c.sc[ABIPGPU_SC_MIN_XS], it.c.sc[ABIPGPU_SC_SUM_XS]) < 0) {
+                        code = LP_SOLVE_FAIL;
+                        break;
+                    }
+                }
+                __syncthreads();
+                dev_pre_op(it, PreOp{PRE_REINIT, 0, avg, 0, ms.sigma, 0.0});
+                if (!S.adaptive) continue;
+                if (S.adaptive_lookback <= 0) { code = LP_SOLVE_FAIL; break; }
+                dev_pre_op(it, PreOp{PRE_REINIT, 1, avg, 0, ms.sigma, 0.0});
+                beta = 1.0;
+                dev_pre_op(it, PreOp{PRE_BB_BEGIN, 0, 0, 0, 0.0, 0.0});
+            }
+            {  // the whole Barzilai-Borwein search: lookback rounds + the safeguarded step
+                double beta_prev = 1.0;
+                int carry = 0;
+                bb_beta = 0.0;
+                if (!only_bb) {
+                    b.k = k;
+                    b.mu = ms.mu;
+                }
+                const int lookback = only_bb ? it.search.lookback : S.adaptive_lookback;
+                const double eps_cor = only_bb ? it.search.eps_cor : S.eps_cor, eps_pen = only_bb ? it.search.eps_pen : S.eps_pen;
+                for (int t = 0; t < lookback; ++t) {
+                    b.carry = carry;
+                    b.beta_prev = beta_prev;
+                    body_bb_round<false>(it.c, b, smem_raw, true);
+                    __syncthreads();
+                    const double* sc = it.c.sc;
+                    cg += sc[ABIPGPU_SC_CG_ITS] + sc[ABIPGPU_SC_CG_ITS2];
+                    ++rounds;
+                    const int action = lp_bb_step(sc, eps_cor, eps_pen, &beta_prev, &bb_beta);
+                    if (action == 0) break;
+                    carry = action;
+                    __syncthreads();
+                }
+                __syncthreads();
+            }
+            if (only_bb) break;
+            beta = bb_beta;
+            dev_pre_op(it, PreOp{PRE_REINIT, 2, avg, 0, ms.sigma, 0.0});
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            it.c.sc[ABIPGPU_SC_LOOP_BETA] = beta;
-            it.c.sc[ABIPGPU_SC_LOOP_CG] = cg;
-            it.c.sc[ABIPGPU_SC_LOOP_ROUNDS] = (double)rounds;
+            double* sc = it.c.sc;
+            sc[ABIPGPU_SC_LOOP_EXIT] = (double)code;
+            sc[ABIPGPU_SC_LOOP_ITERS] = (double)done;
+            sc[ABIPGPU_SC_LOOP_CG] = cg;
+            sc[ABIPGPU_SC_LOOP_AVG] = (double)avg;
+            sc[ABIPGPU_SC_LOOP_BETA] = only_bb ? bb_beta : beta;
+            sc[ABIPGPU_SC_LOOP_ROUNDS] = (double)rounds;
+            sc[ABIPGPU_SC_LOOP_I] = (double)i;
+            sc[ABIPGPU_SC_LOOP_J] = (double)j;
+            sc[ABIPGPU_SC_LOOP_MU] = ms.mu;
+            sc[ABIPGPU_SC_LOOP_SIGMA] = ms.sigma;
+            sc[ABIPGPU_SC_LOOP_GAMMA] = ms.gamma;
+            sc[ABIPGPU_SC_LOOP_FLAGS] = (double)(ms.final_check | (ms.double_check << 1));
+            sc[ABIPGPU_SC_LOOP_DYN] = ms.dynamic_sigma;
         }
     } else body_mu_stats(it.mu.u, it.mu.v, it.c.m, it.c.m + it.c.n + 1, it.c.partials, it.c.sc, it.c.comm, true);
     __syncthreads();
@@ -2250,8 +2321,37 @@ int abipgpu_lp_inner_loop(abipgpu_lp* e, const LpInnerArgs* L, abip_float* sc) {
     r.item.kind = BATCH_INNER;
     fill_iter_args(e, &r.item.it);
     r.item.it.j = L->j0; r.item.it.k = L->k0; r.item.it.mu = L->mu; r.item.it.beta = L->beta;
-    r.item.inner = *L;
+    memset(&r.item.solve, 0, sizeof(r.item.solve));
+    r.item.solve.in = *L;
     if (batch_step(e, &r, sc)) return -1;
+    e->stats.n_admm_launch++;
+    return 0;
+}
+
+static void fill_bb_args(abipgpu_lp* e, BBArgs* a) {
+    a->u_prev = e->vec[ABIPGPU_VEC_BB_UPREV]; a->v_prev = e->vec[ABIPGPU_VEC_BB_VPREV]; a->ut = e->vec[ABIPGPU_VEC_BB_UT];
+    a->u = e->vec[ABIPGPU_VEC_BB_U]; a->v = e->vec[ABIPGPU_VEC_BB_V]; a->ut_next = e->vec[ABIPGPU_VEC_BB_UTNEXT];
+    a->u_next = e->vec[ABIPGPU_VEC_BB_UNEXT]; a->v_next = e->vec[ABIPGPU_VEC_BB_VNEXT];
+    a->carry = 0; a->k = 0; a->mu = 1.0; a->beta_prev = 1.0;
+}
+
+// the device-resident OUTER loop (LpSolveArgs, lp_logic.h): one batched step runs the solve until it ends, the launch cap is
+// reached or the host is needed; the state comes back in sc[ABIPGPU_SC_LOOP_*]
+int abipgpu_lp_solve_loop(abipgpu_lp* e, const LpSolveArgs* S, abip_float* sc) {
+    if (!e->batch) return -1;
+    BatchReq r;
+    r.e = e;
+    r.item.c = e->ctx;
+    r.item.kind = BATCH_SOLVE;
+    fill_iter_args(e, &r.item.it);
+    r.item.it.j = S->in.j0; r.item.it.k = S->in.k0; r.item.it.mu = S->in.mu; r.item.it.beta = S->in.beta;
+    fill_bb_args(e, &r.item.bb);
+    r.item.solve = *S;
+    r.item.search = BBSearchArgs{S->adaptive_lookback, S->eps_cor, S->eps_pen};
+    if (batch_step(e, &r, sc)) return -1;
+    // the device ran the prologue of the current outer iteration (u_sum = u_avg = 0) and leaves before the restart
+    // bookkeeping starts: the lazily materialised u_avg / v_avg of abipgpu_lp_admm_iter are still in sync
+    e->restart_synced = true;
     e->stats.n_admm_launch++;
     return 0;
 }
@@ -2264,10 +2364,9 @@ int abipgpu_lp_bb_search(abipgpu_lp* e, abip_int k, abip_float mu, int lookback,
     r.item.c = e->ctx;
     r.item.kind = BATCH_BBSEARCH;
     BBArgs& a = r.item.bb;
-    a.u_prev = e->vec[ABIPGPU_VEC_BB_UPREV]; a.v_prev = e->vec[ABIPGPU_VEC_BB_VPREV]; a.ut = e->vec[ABIPGPU_VEC_BB_UT];
-    a.u = e->vec[ABIPGPU_VEC_BB_U]; a.v = e->vec[ABIPGPU_VEC_BB_V]; a.ut_next = e->vec[ABIPGPU_VEC_BB_UTNEXT];
-    a.u_next = e->vec[ABIPGPU_VEC_BB_UNEXT]; a.v_next = e->vec[ABIPGPU_VEC_BB_VNEXT];
-    a.carry = 0; a.k = k; a.mu = mu; a.beta_prev = 1.0;
+    fill_bb_args(e, &a);
+    a.k = k; a.mu = mu;
+    memset(&r.item.solve, 0, sizeof(r.item.solve));
     r.item.search = BBSearchArgs{lookback, eps_cor, eps_pen};
     if (batch_step(e, &r, sc)) return -1;
     e->stats.n_bb_launch++;

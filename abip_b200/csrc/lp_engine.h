@@ -13,8 +13,10 @@ int abipgpu_lp_dims(const abipgpu_lp* e, int* m, int* n);
 int abipgpu_lp_sync(abipgpu_lp* e);
 void abipgpu_lp_drop_pending(abipgpu_lp* e);
 struct LpInnerArgs;
+struct LpSolveArgs;
 extern "C" int abipgpu_lp_is_batch(const abipgpu_lp* e);
 extern "C" int abipgpu_lp_inner_loop(abipgpu_lp* e, const LpInnerArgs* L, abip_float* sc);
+extern "C" int abipgpu_lp_solve_loop(abipgpu_lp* e, const LpSolveArgs* S, abip_float* sc);
 extern "C" int abipgpu_lp_bb_search(abipgpu_lp* e, abip_int k, abip_float mu, int lookback, abip_float eps_cor, abip_float eps_pen, abip_float* sc);  // batch engines: forget deferred vector operations (failed solve)
 int abipgpu_lp_solve_timer(abipgpu_lp* e, int stop);
 extern "C" int abipgpu_lp_comm_export(abipgpu_lp* e, void* handle64);

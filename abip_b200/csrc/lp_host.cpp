@@ -408,77 +408,35 @@ abip_int has_converged(const ABIP_GPU_WORK* w, const Resid* r, abip_int ipm_iter
     return lp_has_converged(w->stgs.eps, (int)w->stgs.pfeasopt, &q, (long)ipm_iter, (long)admm_iter);
 }
 
-// table-driven mu rule (src/abip.c:753-921)
-void update_barrier(ABIP_GPU_WORK* w, const Resid* r) {
+// mu rules (src/abip.c:753-992) and their selection (:2251-2277): the scalar logic lives in lp_logic.h (shared with the
+// device-resident outer loop); min / sum of u_i v_i for the LOQO rule are reduced on the device
+static LpMuParams mu_params(const ABIP_GPU_WORK* w) {
     const ABIPSettings& s = w->stgs;
-    const double ratio = w->mu / s.eps;
-    const double err = std::max(std::max(r->res_pri, r->res_dual), r->rel_gap) / s.eps;
-    const bool dense = std::max(w->sp, s.sparsity_ratio) > 0.4 || std::min(w->sp, s.sparsity_ratio) > 0.1;
-    static const double lo[] = {10.0, 1.0, 0.5, 0.1, 0.05, 0.01, 0.005, 0.001};
-    const double gam[] = {dense ? 2.0 : 3.0, 1.0, 0.9, 0.8, 0.7, 0.6, 0.5, 0.4};
-    double gamma = 0.3, sigma = w->sigma;
-    for (int q = 0; q < 8; ++q)
-        if (ratio > lo[q]) { gamma = gam[q]; break; }
-    if (dense) {
-        if (err > 6 && err <= 10) sigma = 0.5;
-        else if (err > 3 && err <= 6) { sigma = 0.6; gamma *= 0.8; }
-        else if (err > 1 && err <= 3) { w->final_check = 1; gamma *= 0.4; sigma = ratio < 0.1 ? 0.8 : 0.7; }
-    } else {
-        if (err > 6 && err <= 10) { sigma = 0.82; gamma *= 0.8; }
-        else if (err > 4 && err <= 6) { sigma = 0.84; gamma *= 0.6; }
-        else if (err > 3 && err <= 4) { sigma = 0.85; gamma *= 0.5; w->final_check = 1; }
-        else if (err > 1 && err <= 3) {
-            w->final_check = 1;
-            if (ratio < 0.1) {
-                if (w->double_check) { sigma = 0.9; gamma *= 0.4; w->double_check = 0; }
-                else { sigma = 1.0; gamma *= 0.1; w->double_check = 1; }
-            } else { sigma = 0.88; gamma *= 0.4; }
-        }
-    }
-    w->mu *= sigma;
-    w->sigma = sigma;
-    w->gamma = gamma;
+    return LpMuParams{s.eps, w->sp, s.sparsity_ratio, s.dynamic_sigma_second, s.dynamic_x, s.hybrid_thresh, (int)s.hybrid_mu,
+                      (long)w->n + 1};
 }
-
-// LOQO rule (src/abip.c:930-977); min / sum of u_i v_i are reduced on the device
-int update_barrier_dynamic(ABIP_GPU_WORK* w) {
-    double sc[ABIPGPU_SC_COUNT];
-    if (abipgpu_lp_mu_stats(w->eng, (int)w->stgs.avg_criterion, sc) != 0) return -1;
-    const double minxs = sc[ABIPGPU_SC_MIN_XS];
-    if (!(minxs > 0.0)) {  // the reference assert(0)s here (:962-965)
-        printf("Invalid xisi < 0 \n");
-        return -1;
-    }
-    const double xs = sc[ABIPGPU_SC_SUM_XS] / (w->n + 1);
-    const double ksi = minxs / xs;
-    double sigma = std::min(0.05 * (1 - ksi) / ksi, 2.0);
-    sigma = std::max(0.1 * sigma * sigma * sigma, w->stgs.dynamic_sigma);
-    w->mu *= sigma;
-    return 0;
-}
-
-void update_barrier_dynamic_2(ABIP_GPU_WORK* w) {  // src/abip.c:982-992; eta = dynamic_sigma (parity trap 6)
-    w->mu *= std::min(w->stgs.dynamic_x * w->mu, std::pow(w->mu, w->stgs.dynamic_sigma));
-}
-
-int update_mu(ABIP_GPU_WORK* w, const Resid* r) {  // selection logic, src/abip.c:2251-2277
+int update_mu(ABIP_GPU_WORK* w, const Resid* r) {
     ABIPSettings& s = w->stgs;
-    if (s.hybrid_mu) {
-        if (s.dynamic_sigma_second > 0.0 && w->mu < s.hybrid_thresh * s.eps) {
-            s.dynamic_sigma = s.dynamic_sigma_second;
-            return update_barrier_dynamic(w);
-        } else if (s.dynamic_sigma_second == 0.0 && w->mu < s.hybrid_thresh * s.eps) {
-            s.dynamic_sigma = s.dynamic_sigma_second;
-            update_barrier(w, r);
-        } else if (s.dynamic_sigma < 0.0) {
-            update_barrier_dynamic_2(w);
+    LpMuState st{w->mu, w->sigma, w->gamma, s.dynamic_sigma, w->final_check, w->double_check};
+    const LpMuParams mp = mu_params(w);
+    int rc = 0;
+    const int rule = lp_mu_rule(&st, mp);
+    if (rule == 1) {
+        const LpResid q{r->res_pri, r->res_dual, r->rel_gap, r->res_infeas, r->res_unbdd, r->ct_x_by_tau, r->bt_y_by_tau, r->tau, r->kap};
+        lp_update_barrier(&st, mp, q);
+    } else if (rule == 2) {
+        lp_update_barrier_dynamic_2(&st, mp);
+    } else if (rule == 3) {
+        double sc[ABIPGPU_SC_COUNT];
+        if (abipgpu_lp_mu_stats(w->eng, (int)s.avg_criterion, sc) != 0) return -1;
+        if (lp_update_barrier_dynamic(&st, mp, sc[ABIPGPU_SC_MIN_XS], sc[ABIPGPU_SC_SUM_XS]) < 0) {  // the reference assert(0)s here (:962-965)
+            printf("Invalid xisi < 0 \n");
+            rc = -1;
         }
-    } else {
-        if (s.dynamic_sigma == 0.0) update_barrier(w, r);
-        else if (s.dynamic_sigma < 0.0) update_barrier_dynamic_2(w);
-        else return update_barrier_dynamic(w);
     }
-    return 0;
+    w->mu = st.mu; w->sigma = st.sigma; w->gamma = st.gamma; s.dynamic_sigma = st.dynamic_sigma;
+    w->final_check = st.final_check; w->double_check = st.double_check;
+    return rc;
 }
 
 // Barzilai-Borwein search for beta (src/adaptive.c:34-256): the two ADMM steps and the five inner products of a
@@ -970,12 +928,78 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
     struct TraceCloser { FILE* f; ABIP_GPU_WORK* w; ~TraceCloser() { if (f) fclose(f); w->trace = nullptr; } } trace_closer{trace, w};
 
     abip_int k = 0;
-    for (abip_int i = 0; i < s.max_ipm_iters; ++i) {  // outer loop
+    abip_int i_start = 0, j_start = 0;
+    bool resume = false;  // the host loop takes over inside the inner loop of outer iteration i_start at j_start
+    if (w->device_loops && !trace && !s.verbose && getenv("ABIP_GPU_BATCH_HOST_OUTER") == nullptr) {
+        // Batch engines: the OUTER loop runs on the device as well (lp_engine.cu: k_batch, BATCH_SOLVE; decisions in
+        // lp_logic.h) -- a problem is one batched step (one launch per `cap` ADMM iterations) instead of ~45 host round trips.
+        // The host is back in charge when the solve is over, between launches (time limit, SIGINT), or for the restart
+        // bookkeeping (k >= restart_thresh), where it continues with single steps from the state handed back.
+        LpSolveArgs S;
+        memset(&S, 0, sizeof(S));
+        S.in.cap = 4096;
+        S.in.max_ipm_iters = s.max_ipm_iters;
+        S.in.restart_thresh = s.restart_thresh;
+        S.in.eps = s.eps;
+        S.in.pfeasopt = (int)s.pfeasopt; S.in.half_update = (int)s.half_update;
+        S.in.rin = resid_in(w);
+        S.adaptive = (int)s.adaptive; S.adaptive_lookback = (int)s.adaptive_lookback;
+        S.eps_cor = s.eps_cor; S.eps_pen = s.eps_pen;
+        abip_int i = 0, j = 0;
+        int code = LP_INNER_CONTINUE;
+        for (;;) {
+            S.in.j0 = j; S.in.k0 = k; S.in.ipm_iter = i; S.in.max_admm_iters = s.max_admm_iters;
+            S.in.mu = w->mu; S.in.beta = w->beta; S.in.gamma = w->gamma;
+            S.in.final_check = w->final_check; S.in.avg_in = (int)s.avg_criterion;
+            S.mp = mu_params(w);
+            S.sigma = w->sigma; S.dynamic_sigma = s.dynamic_sigma; S.double_check = w->double_check;
+            S.resume_inner = resume ? 1 : 0;
+            if (abipgpu_lp_solve_loop(w->eng, &S, w->sc) != 0)
+                return failure(m, n, sol, info, ABIP_FAILED, "error in project_lin_sys", "Failure");
+            code = (int)w->sc[ABIPGPU_SC_LOOP_EXIT];
+            k += (abip_int)w->sc[ABIPGPU_SC_LOOP_ITERS];
+            w->tot_cg_its += (abip_int)w->sc[ABIPGPU_SC_LOOP_CG];
+            i = (abip_int)w->sc[ABIPGPU_SC_LOOP_I];
+            j = (abip_int)w->sc[ABIPGPU_SC_LOOP_J];
+            s.avg_criterion = (abip_int)w->sc[ABIPGPU_SC_LOOP_AVG];
+            w->mu = w->sc[ABIPGPU_SC_LOOP_MU]; w->beta = w->sc[ABIPGPU_SC_LOOP_BETA];
+            w->sigma = w->sc[ABIPGPU_SC_LOOP_SIGMA]; w->gamma = w->sc[ABIPGPU_SC_LOOP_GAMMA];
+            s.dynamic_sigma = w->sc[ABIPGPU_SC_LOOP_DYN];
+            const int flags = (int)w->sc[ABIPGPU_SC_LOOP_FLAGS];
+            w->final_check = flags & 1; w->double_check = (flags >> 1) & 1;
+            if (g_interrupted) return failure(m, n, sol, info, ABIP_SIGINT, "Interrupted", "Interrupted");
+            if (code != LP_INNER_CONTINUE) break;
+            resume = true;  // launch cap reached inside an inner loop: go on from (i, j, k)
+            if ((now_ms() - t0) / 1e3 > max_time) {  // wall clock, checked between launches
+                printf("Timelimit reached. \n");
+                s.max_admm_iters = (abip_int)(k * 1.05);
+            }
+        }
+        if (code == LP_SOLVE_FAIL) return failure(m, n, sol, info, ABIP_FAILED, "error in mu update", "Failure");
+        if (code == LP_INNER_FINISHED || code == LP_SOLVE_DONE) {
+            calc_residuals(w, &r, i, k);
+            info->status_val = has_converged(w, &r, i, k);
+            if (get_solution(w, sol, info, &r, i, k) != 0)
+                return failure(m, n, sol, info, ABIP_FAILED, "error in get_solution", "Failure");
+            info->solve_time = now_ms() - t0;
+            return info->status_val;
+        }
+        if (code == LP_SOLVE_IPM) {
+            i_start = s.max_ipm_iters;  // skip the host loop: straight to the final get_solution
+        } else {  // LP_INNER_HOST: restart bookkeeping ahead
+            w->device_loops = false;
+            i_start = i;
+            j_start = j;
+            resume = true;
+        }
+    }
+    for (abip_int i = i_start; i < s.max_ipm_iters; ++i) {  // outer loop
+        const bool resumed = resume && i == i_start;
         abip_int inner_stopper;
         if (spmin > 0.5) inner_stopper = (abip_int)std::round(std::pow(w->mu, -0.35));
         else if (spmin > 0.2) inner_stopper = (abip_int)std::round(std::pow(w->mu, -1));
         else inner_stopper = s.max_admm_iters;
-        if (abipgpu_lp_outer_prologue(w->eng, (int)s.avg_criterion) != 0)
+        if (!resumed && abipgpu_lp_outer_prologue(w->eng, (int)s.avg_criterion) != 0)
             return failure(m, n, sol, info, ABIP_FAILED, "error in outer prologue", "Failure");
 
         // a solve is over inside the inner loop when final_check finds convergence or an iteration limit (abip.c:2190-2211)
@@ -987,7 +1011,7 @@ abip_int abip_gpu_solve(ABIPGpuWork* w, const ABIPData* d, ABIPSolution* sol, AB
             if (s.verbose) print_footer(w, info);
             return info->status_val;
         };
-        for (abip_int j = 0; j < inner_stopper;) {  // inner loop
+        for (abip_int j = resumed ? j_start : 0; j < inner_stopper;) {  // inner loop
             if (w->device_loops && !trace) {
                 // batch engines: up to `cap` iterations per batched step, decisions taken on the device (lp_logic.h)
                 LpInnerArgs L;

@@ -112,5 +112,104 @@ enum {
     LP_INNER_CONVERGED = 1,  // criterion < gamma * mu: the inner loop is over (abip.c:2173-2188)
     LP_INNER_FINISHED = 2,   // final_check: converged / iteration limit -> the solve is over (abip.c:2190-2211)
     LP_INNER_STOPPER = 3,    // j reached inner_stopper
-    LP_INNER_HOST = 4        // restart bookkeeping ahead (k >= restart_thresh): the host steps from here on
+    LP_INNER_HOST = 4,       // restart bookkeeping ahead (k >= restart_thresh): the host steps from here on
+    // device-resident OUTER loop (LpSolveArgs, k_batch kind BATCH_SOLVE) in addition:
+    LP_SOLVE_DONE = 5,       // the check after an inner loop found convergence / the ADMM limit (abip.c:2225-2249): get_solution
+    LP_SOLVE_IPM = 6,        // max_ipm_iters outer iterations done (abip.c:2296)
+    LP_SOLVE_FAIL = 7        // the LOQO mu rule met min(u_i v_i) <= 0 (the reference asserts, abip.c:962-965)
+};
+
+// ---- mu rules (src/abip.c:753-992, selection :2251-2277), shared by the host loop and the device-resident outer loop ----
+struct LpMuState {
+    double mu, sigma, gamma, dynamic_sigma;
+    int final_check, double_check;
+};
+struct LpMuParams {
+    double eps, sp, sparsity_ratio, dynamic_sigma_second, dynamic_x, hybrid_thresh;
+    int hybrid_mu;
+    long n_plus_1;
+};
+// which rule update_mu applies: 0 none, 1 the table rule (update_barrier), 2 update_barrier_dynamic_2, 3 the LOQO rule
+// (update_barrier_dynamic: needs min and sum of u_i v_i over the (x, tau) tail)
+ABIP_HD int lp_mu_rule(LpMuState* st, const LpMuParams& p) {
+    if (p.hybrid_mu) {
+        if (p.dynamic_sigma_second > 0.0 && st->mu < p.hybrid_thresh * p.eps) {
+            st->dynamic_sigma = p.dynamic_sigma_second;
+            return 3;
+        } else if (p.dynamic_sigma_second == 0.0 && st->mu < p.hybrid_thresh * p.eps) {
+            st->dynamic_sigma = p.dynamic_sigma_second;
+            return 1;
+        } else if (st->dynamic_sigma < 0.0) {
+            return 2;
+        }
+        return 0;
+    }
+    if (st->dynamic_sigma == 0.0) return 1;
+    if (st->dynamic_sigma < 0.0) return 2;
+    return 3;
+}
+// table-driven mu rule (src/abip.c:753-921)
+ABIP_HD void lp_update_barrier(LpMuState* st, const LpMuParams& p, const LpResid& r) {
+    const double ratio = st->mu / p.eps;
+    const double err = fmax(fmax(r.res_pri, r.res_dual), r.rel_gap) / p.eps;
+    const bool dense = fmax(p.sp, p.sparsity_ratio) > 0.4 || fmin(p.sp, p.sparsity_ratio) > 0.1;
+    const double lo[8] = {10.0, 1.0, 0.5, 0.1, 0.05, 0.01, 0.005, 0.001};
+    const double gam[8] = {dense ? 2.0 : 3.0, 1.0, 0.9, 0.8, 0.7, 0.6, 0.5, 0.4};
+    double gamma = 0.3, sigma = st->sigma;
+    for (int q = 0; q < 8; ++q)
+        if (ratio > lo[q]) { gamma = gam[q]; break; }
+    if (dense) {
+        if (err > 6 && err <= 10) sigma = 0.5;
+        else if (err > 3 && err <= 6) { sigma = 0.6; gamma *= 0.8; }
+        else if (err > 1 && err <= 3) { st->final_check = 1; gamma *= 0.4; sigma = ratio < 0.1 ? 0.8 : 0.7; }
+    } else {
+        if (err > 6 && err <= 10) { sigma = 0.82; gamma *= 0.8; }
+        else if (err > 4 && err <= 6) { sigma = 0.84; gamma *= 0.6; }
+        else if (err > 3 && err <= 4) { sigma = 0.85; gamma *= 0.5; st->final_check = 1; }
+        else if (err > 1 && err <= 3) {
+            st->final_check = 1;
+            if (ratio < 0.1) {
+                if (st->double_check) { sigma = 0.9; gamma *= 0.4; st->double_check = 0; }
+                else { sigma = 1.0; gamma *= 0.1; st->double_check = 1; }
+            } else { sigma = 0.88; gamma *= 0.4; }
+        }
+    }
+    st->mu *= sigma;
+    st->sigma = sigma;
+    st->gamma = gamma;
+}
+// src/abip.c:982-992; eta = dynamic_sigma (parity trap 6)
+ABIP_HD void lp_update_barrier_dynamic_2(LpMuState* st, const LpMuParams& p) {
+    st->mu *= fmin(p.dynamic_x * st->mu, pow(st->mu, st->dynamic_sigma));
+}
+// LOQO rule (src/abip.c:930-977) from min / sum of u_i v_i; -1: invalid (min <= 0)
+ABIP_HD int lp_update_barrier_dynamic(LpMuState* st, const LpMuParams& p, double minxs, double sumxs) {
+    if (!(minxs > 0.0)) return -1;
+    const double xs = sumxs / (double)p.n_plus_1;
+    const double ksi = minxs / xs;
+    double sigma = fmin(0.05 * (1 - ksi) / ksi, 2.0);
+    sigma = fmax(0.1 * sigma * sigma * sigma, st->dynamic_sigma);
+    st->mu *= sigma;
+    return 0;
+}
+// inner_stopper of an outer iteration (src/abip.c:2098-2112)
+ABIP_HD long lp_inner_stopper(double spmin, double mu, long max_admm_iters) {
+    if (spmin > 0.5) return (long)round(pow(mu, -0.35));
+    if (spmin > 0.2) return (long)round(pow(mu, -1.0));
+    return max_admm_iters;
+}
+
+// Device-resident OUTER loop (src/abip.c:2093-2295): inner loops, the convergence check after each of them, the mu rule,
+// re-initialisation and the Barzilai-Borwein search run inside ONE batched step until the solve ends, the launch cap
+// (in.cap ADMM iterations) is reached or the restart bookkeeping needs the host.  in.ipm_iter / in.j0 / in.k0 / in.mu /
+// in.beta / in.gamma / in.final_check / in.avg_in carry the state in; the state comes back in the scalar block
+// (ABIPGPU_SC_LOOP_*).
+struct LpSolveArgs {
+    LpInnerArgs in;
+    LpMuParams mp;
+    double sigma, dynamic_sigma;
+    int double_check;
+    int resume_inner;  // 1: the launch starts inside the inner loop of outer iteration in.ipm_iter at j0 (prologue done)
+    int adaptive, adaptive_lookback;
+    double eps_cor, eps_pen;
 };

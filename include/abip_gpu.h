@@ -249,6 +249,10 @@ enum {
     /* device-resident loops of the batch kernel (abipgpu_lp_inner_loop / abipgpu_lp_bb_search) */
     ABIPGPU_SC_LOOP_EXIT = 51, ABIPGPU_SC_LOOP_ITERS = 52, ABIPGPU_SC_LOOP_CG = 53, ABIPGPU_SC_LOOP_AVG = 54,
     ABIPGPU_SC_LOOP_BETA = 56, ABIPGPU_SC_LOOP_ROUNDS = 57,
+    /* state of the device-resident outer loop (batch engines) */
+    ABIPGPU_SC_LOOP_I = 58, ABIPGPU_SC_LOOP_J = 59, ABIPGPU_SC_LOOP_MU = 60, ABIPGPU_SC_LOOP_SIGMA = 61,
+    ABIPGPU_SC_LOOP_GAMMA = 62, ABIPGPU_SC_LOOP_FLAGS = 55 /* final_check | double_check << 1 */,
+    ABIPGPU_SC_LOOP_DYN = 45 /* dynamic_sigma */,
     ABIPGPU_SC_COMM_ERR = 63, /* multi-GPU: a peer did not answer within the spin limit */
     ABIPGPU_SC_COUNT = 64
 };
