@@ -641,9 +641,12 @@ __device__ __forceinline__ void load_resident_idx(Csr& A, unsigned char*& p) {
     p += 2 * (size_t)((nnz + 7) & ~7);
 }
 
-__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_batch(const BatchItem* items, double* sc_out, int resident) {
+__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_batch(const BatchItem* items, double* sc_out, int resident,
+                                                                          double seq) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(16) BatchItem s_item;
+    unsigned long long t_begin = 0;
+    if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
     {
         const int* src = reinterpret_cast<const int*>(items + blockIdx.x);
         int* dst = reinterpret_cast<int*>(&s_item);
@@ -817,7 +820,19 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_batch(const 
         }
     } else body_mu_stats(it.mu.u, it.mu.v, it.c.m, it.c.m + it.c.n + 1, it.c.partials, it.c.sc, it.c.comm, true);
     __syncthreads();
-    if (threadIdx.x < ABIPGPU_SC_COUNT) sc_out[(size_t)blockIdx.x * ABIPGPU_SC_COUNT + threadIdx.x] = it.c.sc[threadIdx.x];
+    // scalar block of the item to the host-mapped output; then its time on the SM and, last, the completion flag (the launch
+    // sequence number): the executor releases the owner of an item as soon as the flag shows, not when the whole launch ends
+    double* out = sc_out + (size_t)blockIdx.x * ABIPGPU_SC_COUNT;
+    if (threadIdx.x < ABIPGPU_SC_COUNT && threadIdx.x != ABIPGPU_SC_BATCH_DONE && threadIdx.x != ABIPGPU_SC_BATCH_NS)
+        out[threadIdx.x] = it.c.sc[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        out[ABIPGPU_SC_BATCH_NS] = (double)(t_end - t_begin);
+        __threadfence_system();
+        *(volatile double*)(out + ABIPGPU_SC_BATCH_DONE) = seq;
+    }
 }
 
 // reinitialize_vars, src/abip.c:996-1075
@@ -1132,6 +1147,7 @@ struct BatchReq {
     bool done = false;
     int rc = 0;
     sem_t sem;                   // per-request wake-up: no contention on the executor's mutex when a batch completes
+    std::chrono::steady_clock::time_point t_submit;
     BatchReq() { sem_init(&sem, 0, 0); }
     ~BatchReq() { sem_destroy(&sem); }
 };
@@ -1161,12 +1177,18 @@ struct BatchExec {
     bool stop = false;
     std::atomic<long> n_launches{0}, n_items{0};
     double t_wait_ms = 0, t_kernel_ms = 0;
+    bool early = true;          // release the owner of an item when its completion flag shows (ABIP_GPU_BATCH_EARLY=0: at launch end)
+    std::atomic<long> seq{0};   // launch sequence numbers (completion flags)
+    // statistics (ABIP_GPU_BATCH_VERBOSE): time of the launches, time of the items on their SMs, queueing of the requests
+    std::mutex stat_mu;
+    double st_launch_ms = 0, st_item_ms = 0, st_item_max_ms = 0, st_queue_ms = 0, st_release_lag_ms = 0;
 
     int start(int dev, int capacity) {
         device = dev;
         cap = capacity;
         wait_us = std::max(0, env_int("ABIP_GPU_BATCH_WAIT_US", 200));
         use_resident = env_int("ABIP_GPU_BATCH_RESIDENT", 1) != 0;
+        early = env_int("ABIP_GPU_BATCH_EARLY", 1) != 0;
         const int nslots = std::max(1, std::min(env_int("ABIP_GPU_BATCH_SLOTS", 6), 32));
         CK(cudaSetDevice(dev));
         CK(cudaFuncSetAttribute((const void*)k_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentMax));
@@ -1209,21 +1231,68 @@ struct BatchExec {
                 else smem = std::max(smem, (size_t)need);
             }
             if (!resident) smem = kSmemBytes;
-            k_batch<<<n, kBlock, smem, sl.stream>>>(sl.items, sl.sc_out, resident);
+            const double my_seq = (double)(++seq);
+            for (int i = 0; i < n; ++i) sl.sc_out[(size_t)i * ABIPGPU_SC_COUNT + ABIPGPU_SC_BATCH_DONE] = 0.0;
+            const auto t_l0 = std::chrono::steady_clock::now();
+            double queue_ms = 0, item_ms = 0, item_max = 0, lag_ms = 0;
+            for (int i = 0; i < n; ++i) queue_ms += std::chrono::duration<double, std::milli>(t_l0 - batch[i]->t_submit).count();
+            k_batch<<<n, kBlock, smem, sl.stream>>>(sl.items, sl.sc_out, resident, my_seq);
             cudaError_t err = cudaGetLastError();
+            // release every item as soon as its CTA has written the completion flag (host-mapped memory); the items of one
+            // launch differ by 2x in length and their owners have the next problem to set up
+            auto release = [&](int i, bool ok) {
+                const double* src = sl.sc_out + (size_t)i * ABIPGPU_SC_COUNT;
+                const double ms = src[ABIPGPU_SC_BATCH_NS] * 1e-6;
+                item_ms += ms;
+                item_max = std::max(item_max, ms);
+                memcpy(batch[i]->e->hsc, src, sizeof(double) * ABIPGPU_SC_COUNT);
+                batch[i]->e->hsc[ABIPGPU_SC_BATCH_DONE] = 0.0;
+                batch[i]->rc = ok ? 0 : -1;
+                sem_post(&batch[i]->sem);  // the request may be gone right after this
+                batch[i] = nullptr;
+            };
+            int remaining = n;
+            if (err == cudaSuccess && early) {
+                while (remaining > 0) {
+                    for (int i = 0; i < n; ++i)
+                        if (batch[i] && *(volatile double*)(sl.sc_out + (size_t)i * ABIPGPU_SC_COUNT + ABIPGPU_SC_BATCH_DONE) == my_seq) {
+                            std::atomic_thread_fence(std::memory_order_acquire);
+                            release(i, true);
+                            --remaining;
+                        }
+                    if (remaining == 0) break;
+                    const cudaError_t q = cudaStreamQuery(sl.stream);
+                    if (q != cudaErrorNotReady) {  // finished (flags are all set by now) or failed
+                        if (q != cudaSuccess) err = q;
+                        break;
+                    }
+                    std::this_thread::sleep_for(std::chrono::microseconds(50));
+                }
+            }
             if (err == cudaSuccess) err = cudaStreamSynchronize(sl.stream);
             if (err != cudaSuccess) fprintf(stderr, "[abip_gpu] batched step failed: %s\n", cudaGetErrorString(err));
-            for (int i = 0; i < n; ++i) {
-                memcpy(batch[i]->e->hsc, sl.sc_out + (size_t)i * ABIPGPU_SC_COUNT, sizeof(double) * ABIPGPU_SC_COUNT);
-                batch[i]->rc = (err == cudaSuccess) ? 0 : -1;
-            }
+            const auto t_l1 = std::chrono::steady_clock::now();
+            for (int i = 0; i < n; ++i)
+                if (batch[i]) {
+                    const double ms = sl.sc_out[(size_t)i * ABIPGPU_SC_COUNT + ABIPGPU_SC_BATCH_NS] * 1e-6;
+                    lag_ms += std::chrono::duration<double, std::milli>(t_l1 - t_l0).count() - ms;
+                    release(i, err == cudaSuccess);
+                }
             n_launches++;
             n_items += n;
-            for (int i = 0; i < n; ++i) sem_post(&batch[i]->sem);  // the request may be gone right after this
+            {
+                std::lock_guard<std::mutex> sk(stat_mu);
+                st_launch_ms += std::chrono::duration<double, std::milli>(t_l1 - t_l0).count();
+                st_item_ms += item_ms;
+                st_item_max_ms += item_max;
+                st_queue_ms += queue_ms;
+                st_release_lag_ms += lag_ms;
+            }
             lk.lock();
         }
     }
     int submit(BatchReq* r) {
+        r->t_submit = std::chrono::steady_clock::now();
         {
             std::lock_guard<std::mutex> lk(mu);
             pending.push_back(r);
@@ -1287,9 +1356,13 @@ extern "C" void abipgpu_batch_end(void* b, long* launches, long* items) {
     BatchExec* x = (BatchExec*)b;
     if (!x) return;
     x->finish();
-    if (getenv("ABIP_GPU_BATCH_VERBOSE"))
-        printf("[abip_gpu] batch executor: %.1f ms waiting for requests, %.1f ms in launches (fill + kernel + sync)\n",
-               x->t_wait_ms, x->t_kernel_ms);
+    if (getenv("ABIP_GPU_BATCH_VERBOSE")) {
+        const long nl = std::max(1L, x->n_launches.load()), ni = std::max(1L, x->n_items.load());
+        printf("[abip_gpu] batch executor: %ld launches, %.1f items per launch; per launch %.1f ms (longest item %.1f ms); per item: "
+               "%.1f ms on its SM, %.2f ms queued before the launch, %.2f ms between its end and its release\n",
+               x->n_launches.load(), (double)ni / nl, x->st_launch_ms / nl, x->st_item_max_ms / nl, x->st_item_ms / ni,
+               x->st_queue_ms / ni, x->st_release_lag_ms / ni);
+    }
     if (launches) *launches = x->n_launches.load();
     if (items) *items = x->n_items.load();
     delete x;

@@ -1152,7 +1152,7 @@ abip_int abip_gpu_batch_main(const ABIPData* const* problems, ABIPSolution* sols
     // threads fight for it at once starves the executor's own launch + synchronise, so only a few threads at a time
     // may be in set-up / tear-down
     const char* gate_env = getenv("ABIP_GPU_BATCH_SETUP_GATE");
-    int gate_free = gate_env ? std::max(1, atoi(gate_env)) : 3;
+    int gate_free = gate_env ? std::max(1, atoi(gate_env)) : 8;
     std::mutex gate_mu;
     std::condition_variable gate_cv;
     auto gate_enter = [&] {

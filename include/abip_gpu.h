@@ -253,6 +253,8 @@ enum {
     ABIPGPU_SC_LOOP_I = 58, ABIPGPU_SC_LOOP_J = 59, ABIPGPU_SC_LOOP_MU = 60, ABIPGPU_SC_LOOP_SIGMA = 61,
     ABIPGPU_SC_LOOP_GAMMA = 62, ABIPGPU_SC_LOOP_FLAGS = 55 /* final_check | double_check << 1 */,
     ABIPGPU_SC_LOOP_DYN = 45 /* dynamic_sigma */,
+    /* batch executor: nanoseconds the item spent on its SM, and its completion flag (host-mapped output only) */
+    ABIPGPU_SC_BATCH_NS = 37, ABIPGPU_SC_BATCH_DONE = 38,
     ABIPGPU_SC_COMM_ERR = 63, /* multi-GPU: a peer did not answer within the spin limit */
     ABIPGPU_SC_COUNT = 64
 };
