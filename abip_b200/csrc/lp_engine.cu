@@ -1186,10 +1186,12 @@ struct BatchExec {
     int start(int dev, int capacity) {
         device = dev;
         cap = capacity;
-        wait_us = std::max(0, env_int("ABIP_GPU_BATCH_WAIT_US", 200));
+        wait_us = std::max(0, env_int("ABIP_GPU_BATCH_WAIT_US", 100));
         use_resident = env_int("ABIP_GPU_BATCH_RESIDENT", 1) != 0;
         early = env_int("ABIP_GPU_BATCH_EARLY", 1) != 0;
-        const int nslots = std::max(1, std::min(env_int("ABIP_GPU_BATCH_SLOTS", 6), 32));
+        // a slot is tied up for the length of its launch (a whole solve: ~70 ms at cfg5); with 6 slots a request waited
+        // 15 - 35 ms for a free one (executor statistics, profiles/r02_batch.md)
+        const int nslots = std::max(1, std::min(env_int("ABIP_GPU_BATCH_SLOTS", 16), 64));
         CK(cudaSetDevice(dev));
         CK(cudaFuncSetAttribute((const void*)k_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentMax));
         slots.resize(nslots);
@@ -1266,7 +1268,9 @@ struct BatchExec {
                         if (q != cudaSuccess) err = q;
                         break;
                     }
-                    std::this_thread::sleep_for(std::chrono::microseconds(50));
+                    // coarse while nothing can have finished yet (steps last milliseconds), fine afterwards
+                    const double waited = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_l0).count();
+                    std::this_thread::sleep_for(std::chrono::microseconds(waited < 2.0 ? 50 : (remaining == n ? 500 : 100)));
                 }
             }
             if (err == cudaSuccess) err = cudaStreamSynchronize(sl.stream);

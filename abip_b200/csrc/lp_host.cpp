@@ -1167,6 +1167,8 @@ abip_int abip_gpu_batch_main(const ABIPData* const* problems, ABIPSolution* sols
         }
         gate_cv.notify_one();
     };
+    std::mutex stat_mu;
+    double stat_ms[4] = {0, 0, 0, 0};  // per problem: waiting at the set-up gate, init, solve, finish (incl. its gate)
     auto worker = [&]() {
         if (exec) abipgpu_batch_attach(exec);
         else abipgpu_lp_request_grid((int)ctas_per_problem);
@@ -1175,9 +1177,12 @@ abip_int abip_gpu_batch_main(const ABIPData* const* problems, ABIPSolution* sols
             if (i >= count) break;
             abip_int st;
             if (exec) {
+                const double t_a = now_ms();
                 gate_enter();
+                const double t_b = now_ms();
                 ABIPGpuWork* w = abip_gpu_init(problems[i], &infos[i]);
                 gate_leave();
+                const double t_c = now_ms();
                 if (w) {
                     abip_gpu_solve(w, problems[i], &sols[i], &infos[i]);
                     st = infos[i].status_val;
@@ -1185,9 +1190,15 @@ abip_int abip_gpu_batch_main(const ABIPData* const* problems, ABIPSolution* sols
                     st = failure(problems[i] ? problems[i]->m : -1, problems[i] ? problems[i]->n : -1, &sols[i], &infos[i],
                                  ABIP_FAILED, "could not initialize work", "Failure");
                 }
+                const double t_d = now_ms();
                 gate_enter();
                 abip_gpu_finish(w);
                 gate_leave();
+                const double t_e = now_ms();
+                {
+                    std::lock_guard<std::mutex> lk(stat_mu);
+                    stat_ms[0] += t_b - t_a; stat_ms[1] += t_c - t_b; stat_ms[2] += t_d - t_c; stat_ms[3] += t_e - t_d;
+                }
             } else {
                 st = abip_gpu_main(problems[i], &sols[i], &infos[i]);
             }
@@ -1203,8 +1214,10 @@ abip_int abip_gpu_batch_main(const ABIPData* const* problems, ABIPSolution* sols
         long launches = 0, items = 0;
         abipgpu_batch_end(exec, &launches, &items);
         if (getenv("ABIP_GPU_BATCH_VERBOSE"))
-            printf("[abip_gpu] lock-step batch: %ld problems, %ld batched launches, %.1f steps per launch\n", (long)count,
-                   launches, launches ? (double)items / launches : 0.0);
+            printf("[abip_gpu] batch: %ld problems, %ld batched launches, %.1f steps per launch; host thread per problem: %.2f ms at "
+                   "the set-up gate, %.2f ms init, %.2f ms solve, %.2f ms finish\n", (long)count, launches,
+                   launches ? (double)items / launches : 0.0, stat_ms[0] / count, stat_ms[1] / count, stat_ms[2] / count,
+                   stat_ms[3] / count);
     }
     return (abip_int)failed.load();
 }
