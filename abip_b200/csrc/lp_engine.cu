@@ -1254,6 +1254,7 @@ struct BatchExec {
                 batch[i] = nullptr;
             };
             int remaining = n;
+            unsigned polls = 0;
             if (err == cudaSuccess && early) {
                 while (remaining > 0) {
                     for (int i = 0; i < n; ++i)
@@ -1263,10 +1264,12 @@ struct BatchExec {
                             --remaining;
                         }
                     if (remaining == 0) break;
-                    const cudaError_t q = cudaStreamQuery(sl.stream);
-                    if (q != cudaErrorNotReady) {  // finished (flags are all set by now) or failed
-                        if (q != cudaSuccess) err = q;
-                        break;
+                    if ((++polls & 31) == 0) {  // the stream itself only now and then (a driver call): failed launches
+                        const cudaError_t q = cudaStreamQuery(sl.stream);
+                        if (q != cudaErrorNotReady) {  // finished (flags are all set by now) or failed
+                            if (q != cudaSuccess) err = q;
+                            break;
+                        }
                     }
                     // coarse while nothing can have finished yet (steps last milliseconds), fine afterwards
                     const double waited = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_l0).count();
