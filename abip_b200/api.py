@@ -176,7 +176,7 @@ class LpSolver:
             pass
 
 
-def lp_solve_batch(problems, params: dict | None = None, concurrency: int = 224, ctas_per_problem: int = 1,
+def lp_solve_batch(problems, params: dict | None = None, concurrency: int = 192, ctas_per_problem: int = 1,
                    **raw_settings):
     """Batch of independent LPs on the current GPU (abip_gpu_batch_main).  problems: iterable of objects with
     csc()/m/n/b/c (abip_b200.problems.LPProblem) or (A, b, c) tuples.  Returns a list of (x, y, s, info).

@@ -1167,7 +1167,8 @@ abip_int abip_gpu_batch_main(const ABIPData* const* problems, ABIPSolution* sols
         }
         gate_cv.notify_one();
     };
-    const bool finish_gated = getenv("ABIP_GPU_BATCH_FINISH_GATE") ? atoi(getenv("ABIP_GPU_BATCH_FINISH_GATE")) != 0 : true;
+    // tear-down is a handful of stream-ordered frees: outside the gate (12 - 24 ms per problem inside it, profiles/r02_batch.md)
+    const bool finish_gated = getenv("ABIP_GPU_BATCH_FINISH_GATE") ? atoi(getenv("ABIP_GPU_BATCH_FINISH_GATE")) != 0 : false;
     std::mutex stat_mu;
     double stat_ms[4] = {0, 0, 0, 0};  // per problem: waiting at the set-up gate, init, solve, finish (incl. its gate)
     auto worker = [&]() {

@@ -161,7 +161,7 @@ def shard_indices(count: int, world: int, rank: int) -> list:
     return list(range(rank, count, world))
 
 
-def lp_solve_batch_sharded(problems, params: dict | None = None, concurrency: int = 224, ctas_per_problem: int = 1,
+def lp_solve_batch_sharded(problems, params: dict | None = None, concurrency: int = 192, ctas_per_problem: int = 1,
                            group=None, gather: bool = True, solve_fn=None, **raw_settings):
     """BASELINE.json configs[4]: a batch of independent LPs sharded one problem set per GPU (one process per GPU,
     no data-path collective).  Every rank calls it with the FULL list; rank r solves problems r, r + world, ... with

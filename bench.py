@@ -464,7 +464,7 @@ def run_ours(args):
         lp_solve_batch(probs[:32], dict(tol=args.eps, verbose=0), concurrency=32)  # warm-up
         barrier()
         t_b = time.perf_counter()
-        res = lp_solve_batch(probs, dict(tol=args.eps, verbose=0), concurrency=min(per_gpu, 224))
+        res = lp_solve_batch(probs, dict(tol=args.eps, verbose=0), concurrency=min(per_gpu, 192))
         torch.cuda.synchronize()
         dt = allmax(time.perf_counter() - t_b)
         solved = allsum(sum(1 for r in res if r[3]["status"] == "Solved"))
