@@ -1,5 +1,6 @@
 // lp_engine.h -- internal interface between the CUDA engine (lp_engine.cu) and the host solver (lp_host.cpp).
 #pragma once
+#include <cstddef>
 #include "../../include/abip_gpu.h"
 #ifdef __CUDACC__
 #include "lp_device.cuh"
@@ -29,6 +30,7 @@ extern "C" int abipgpu_equilibrate(abip_int m, abip_int n, const abip_int* Ap, c
 // lock-step batch executor (lp_engine.cu: BatchExec)
 extern "C" void* abipgpu_batch_begin(int device, int capacity);
 extern "C" void abipgpu_batch_attach(void* b);
+extern "C" void abipgpu_batch_reserve(void* b, std::size_t device_bytes, int engines);
 extern "C" int abipgpu_batch_attached();
 extern "C" void abipgpu_batch_end(void* b, long* launches, long* items);
 void abipgpu_lp_batch_solving(abipgpu_lp* e, int delta);

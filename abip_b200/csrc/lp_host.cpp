@@ -1147,6 +1147,15 @@ abip_int abip_gpu_batch_main(const ABIPData* const* problems, ABIPSolution* sols
         const char* dev = getenv("ABIP_GPU_DEVICE");
         exec = abipgpu_batch_begin(dev ? atoi(dev) : 0, (int)concurrency);
         if (!exec) return -1;
+        // device memory of the engines in flight, estimated from the largest of the first problems: both matrices (values,
+        // indices, plans) + ~30 vectors of length m + n + 1
+        size_t per_engine = 0;
+        for (abip_int i = 0; i < std::min<abip_int>(count, 16); ++i)
+            if (problems[i] && problems[i]->A && problems[i]->A->p) {
+                const size_t nnz = (size_t)problems[i]->A->p[problems[i]->n], l = (size_t)problems[i]->m + problems[i]->n + 1;
+                per_engine = std::max(per_engine, 40 * nnz + 30 * 8 * l + (size_t)65536);
+            }
+        abipgpu_batch_reserve(exec, per_engine * (size_t)concurrency * 5 / 4, (int)concurrency + 8);
     }
     // lock-step mode: set-up and tear-down of a problem are ~150 driver calls under the per-context lock; letting all
     // threads fight for it at once starves the executor's own launch + synchronise, so only a few threads at a time

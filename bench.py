@@ -461,7 +461,7 @@ def run_ours(args):
         per_gpu = max(8, int(round(512 * min(1.0, args.scale))))
         probs = [problems.random_lp(500, 2000, 5, seed=5000 + rank * per_gpu + i, name=f"cfg5_lp_{rank * per_gpu + i}")
                  for i in range(per_gpu)]
-        lp_solve_batch(probs[:32], dict(tol=args.eps, verbose=0), concurrency=32)  # warm-up
+        lp_solve_batch(probs[:192], dict(tol=args.eps, verbose=0), concurrency=min(per_gpu, 192))  # warm-up: one wave
         barrier()
         t_b = time.perf_counter()
         res = lp_solve_batch(probs, dict(tol=args.eps, verbose=0), concurrency=min(per_gpu, 192))
