@@ -403,6 +403,28 @@ def test_cfg5_batch_slice_against_reference_golden():
         assert abs(np.linalg.norm(x) - g["x_norm"]) < 1e-3 * g["x_norm"]
 
 
+@pytest.mark.parametrize("raw", [dict(), dict(hybrid_mu=0, dynamic_sigma=0.0), dict(hybrid_mu=0, dynamic_sigma=0.3),
+                                 dict(hybrid_mu=0, dynamic_sigma=-0.5), dict(adaptive=0), dict(restart_thresh=40)])
+def test_batch_device_outer_loop_equals_host_outer_loop(raw, monkeypatch):
+    """The device-resident OUTER loop of the batch engine (k_batch kind BATCH_SOLVE: inner loops, convergence checks, mu rules
+    of src/abip.c:753-992 and their selection :2251-2277, re-initialisation, BB search) takes the branches of the host loop:
+    same status, ADMM / IPM iteration counts and objective as with ABIP_GPU_BATCH_HOST_OUTER=1, for the default hybrid selection
+    (dynamic rule, then the LOQO rule with min / sum of u_i v_i reduced inside the launch), the table rule, the LOQO rule and
+    the dynamic rule alone, without the adaptive search, and with the hand-over to the host at the restart threshold."""
+    from abip_b200 import lp_solve_batch
+    probs = [problems.random_lp(60, 200, 4, seed=900 + i) for i in range(10)]
+    par = dict(tol=1e-4, verbose=0)
+    monkeypatch.setenv("ABIP_GPU_BATCH_HOST_OUTER", "1")
+    ref = lp_solve_batch(probs, par, concurrency=10, ctas_per_problem=1, **raw)
+    monkeypatch.delenv("ABIP_GPU_BATCH_HOST_OUTER")
+    dev = lp_solve_batch(probs, par, concurrency=10, ctas_per_problem=1, **raw)
+    for (xr, yr, sr, ir), (xd, yd, sd, idv) in zip(ref, dev):
+        assert (idv["status"], idv["ipm_iter"], idv["admm_iter"]) == (ir["status"], ir["ipm_iter"], ir["admm_iter"])
+        assert abs(idv["pobj"] - ir["pobj"]) <= 1e-9 * max(1.0, abs(ir["pobj"]))
+        assert np.max(np.abs(xd - xr)) <= 1e-9 * max(1.0, np.max(np.abs(xr)))
+    assert any(r[3]["status"] == "Solved" for r in dev)
+
+
 def test_sigint_handler_is_restored_after_a_batch():
     """the SIGINT listener is process-global but a batch runs one solve per host thread; it is
     reference-counted, so the host's own handler (Python's KeyboardInterrupt) is back in place afterwards."""
