@@ -988,7 +988,7 @@ __device__ __forceinline__ void dev_build_rhs(const LpCtx& c, Reducer& R, cg::gr
         w = fma(-tt, __ldg(c.h + i), w);
         ut[i] = w;
         const int slot = (DIST && i >= m) ? 1 : 0;
-        a[slot] = fma(w, __ldg(c.g + i), a[slot]);
+        a[slot] = fma(w, c.g[i], a[slot]);  // (plain load: a batch problem computes g earlier in the same launch)
     }
     if (VB() == 0 && threadIdx.x == 0) {
         ut[lm1] = tt;

@@ -310,11 +310,10 @@ __device__ __forceinline__ void body_bb_round(const LpCtx& c, const BBArgs& a, u
 
 // solve_lin_sys on a device vector; post_g: g_x *= -1 and g_th = h.g (src/abip.c:1922-1924)
 template <bool DIST>
-__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
-    k_solve_vec(LpCtx c, double* b, const double* s, long iter, int post_g) {
+__device__ __forceinline__ void body_solve_vec(const LpCtx& c, double* b, const double* s, long iter, int post_g,
+                                               unsigned char* smem_raw, bool batched) {
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Reducer R = make_reducer(smem_raw, c.partials);
+    Reducer R = make_reducer(smem_raw, c.partials, batched);
     CommState cs{DIST ? *c.comm.seq : 0ull, false};
     SolveOut so;
     spmv_prefetch(c.A, R.ws);
@@ -349,6 +348,13 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
         c.sc[ABIPGPU_SC_CG_TOL] = so.tol;
         c.sc[ABIPGPU_SC_CG_RES] = so.res;
     }
+    release_reducer(R);  // (a kernel that goes on with other bodies initialises the warp's mbarrier again)
+}
+template <bool DIST>
+__global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM)
+    k_solve_vec(LpCtx c, double* b, const double* s, long iter, int post_g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    body_solve_vec<DIST>(c, b, s, iter, post_g, smem_raw, false);
 }
 
 // y (+)= A x as a stand-alone launch (plugin accum_by_A / accum_by_Atrans and tests)
@@ -545,6 +551,7 @@ struct BatchItem {
     LpSolveArgs solve;  // BATCH_INNER reads solve.in only
     BBSearchArgs search;
     int resident_bytes;  // shared memory needed to keep A and A' resident (0: not eligible)
+    int solve_g;         // 1: g = K^-1 h and g_th = h.g (abipgpu_lp_set_problem) are still to be computed, before the step itself
     PreOp pre[kMaxPre];
     double* vec[21];
 };
@@ -675,6 +682,15 @@ __global__ void __launch_bounds__(kBlock, ABIP_MIN_BLOCKS_PER_SM) k_batch(const 
     }
     const BatchItem& it = s_item;
     apply_pre_ops(it);
+    if (it.solve_g) {
+        // g = K^-1 h, g_x *= -1, g_th = h.g (src/abip.c:1915-1924) inside the first step of the problem, on the resident
+        // matrices: as a launch of its own (57 KB of shared memory) it could not share an SM with a resident k_batch CTA and
+        // waited for a free one
+        body_solve_vec<false>(it.c, it.vec[ABIPGPU_VEC_G], nullptr, -1, 1, smem_raw, true);
+        __syncthreads();
+        if (threadIdx.x == 0) s_item.c.g_th = it.c.sc[ABIPGPU_SC_VEC_NORM2];
+        __syncthreads();
+    }
     if (it.kind == BATCH_ADMM) body_admm_iter<false>(it.c, it.it, smem_raw, true);
     else if (it.kind == BATCH_BB) body_bb_round<false>(it.c, it.bb, smem_raw, true);
     else if (it.kind == BATCH_INNER || it.kind == BATCH_BBSEARCH || it.kind == BATCH_SOLVE) {
@@ -1051,6 +1067,7 @@ struct ABIPGPU_LP {
     struct BatchExec* batch = nullptr;  // lock-step batch executor this engine belongs to
     bool own_stream = true;             // batch engines borrow the stream of their worker thread
     bool dirty = false;                 // batch engines: asynchronous work was queued on the stream since the last step
+    bool need_g = false;                // batch engines: g = K^-1 h is computed inside the next batched step (BatchItem::solve_g)
     int n_pend = 0;                     // batch engines: deferred vector operations (PreOp), executed by the next step
     PreOp pend[kMaxPre];
     // multi-GPU (column-block partition)
@@ -1421,11 +1438,16 @@ static int batch_step(abipgpu_lp* e, BatchReq* r, abip_float* sc) {
     e->n_pend = 0;
     for (int id = 0; id <= 20; ++id) r->item.vec[id] = e->vec[id];
     r->item.resident_bytes = e->resident_bytes;
+    r->item.solve_g = e->need_g ? 1 : 0;
     if (e->dirty) {  // copies / memsets / small kernels queued by this thread must have finished
         CK(cudaStreamSynchronize(e->stream));
         e->dirty = false;
     }
     if (e->batch->submit(r)) return -1;
+    if (e->need_g) {  // the step computed g and g_th first
+        e->ctx.g_th = e->hsc[ABIPGPU_SC_VEC_NORM2];
+        e->need_g = false;
+    }
     if (sc) memcpy(sc, e->hsc, sizeof(double) * ABIPGPU_SC_COUNT);
     return 0;
 }
@@ -2187,6 +2209,18 @@ void abipgpu_lp_destroy(abipgpu_lp* e) {
     delete e;
 }
 
+// g = K^-1 h, g_x *= -1, g_th = h.g (src/abip.c:1915-1924) as a launch of its own
+static int solve_g_now(abipgpu_lp* e) {
+    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_solve_vec<true> : (const void*)k_solve_vec<false>, e->grid, e->smem, e->ctx, e->vec[ABIPGPU_VEC_G], (const double*)nullptr,
+                    (long)-1, 1))
+        return -1;
+    if (read_sc(e, nullptr)) return -1;
+    e->ctx.g_th = e->hsc[ABIPGPU_SC_VEC_NORM2];
+    e->need_g = false;
+    account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], false);
+    return 0;
+}
+
 int abipgpu_lp_set_problem(abipgpu_lp* e, const abip_float* b, const abip_float* c, const abip_float* D,
                            const abip_float* E) {
     CK(cudaSetDevice(e->device));
@@ -2218,13 +2252,13 @@ int abipgpu_lp_set_problem(abipgpu_lp* e, const abip_float* b, const abip_float*
     e->ctx.E = e->have_scaling ? e->dE : nullptr;
     k_build_h<<<(m + n + 255) / 256, 256, 0, e->stream>>>(e->db, e->dc, e->vec[ABIPGPU_VEC_H], e->vec[ABIPGPU_VEC_G], m, n);
     CK(cudaGetLastError());
-    if (launch_coop(e, e->dist_G > 1 ? (const void*)k_solve_vec<true> : (const void*)k_solve_vec<false>, e->grid, e->smem, e->ctx, e->vec[ABIPGPU_VEC_G], (const double*)nullptr,
-                    (long)-1, 1))
-        return -1;
-    if (read_sc(e, nullptr)) return -1;
-    e->ctx.g_th = e->hsc[ABIPGPU_SC_VEC_NORM2];
-    account_solve(e, e->hsc[ABIPGPU_SC_CG_ITS], false);
-    return 0;
+    if (e->batch) {  // batch engines: inside the first batched step of the problem (k_batch, BatchItem::solve_g)
+        e->dirty = true;
+        e->need_g = true;
+        e->ctx.g_th = 0.0;
+        return 0;
+    }
+    return solve_g_now(e);
 }
 
 abip_float abipgpu_lp_g_th(const abipgpu_lp* e) { return e->ctx.g_th; }
@@ -2502,6 +2536,13 @@ int abipgpu_lp_solve_vec(abipgpu_lp* e, int rhs_id, int warm_id, abip_int iter, 
 // executes the deferred operations of a batch engine with ordinary launches (needed before anything other than a
 // batched step reads the vectors: get/set_vec, solve_vec)
 static int flush_pending(abipgpu_lp* e) {
+    if (e->need_g) {  // something other than a batched step is about to read the vectors: compute g with a launch of its own
+        if (e->dirty) {
+            CK(cudaStreamSynchronize(e->stream));
+            e->dirty = false;
+        }
+        if (solve_g_now(e)) return -1;
+    }
     if (!e->n_pend) return 0;
     BatchExec* b = e->batch;
     const bool synced = e->restart_synced;
