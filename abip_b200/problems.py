@@ -300,3 +300,28 @@ LASSO_CASES = {
     "dense_tall": _lasso_case(120, 40, 1.0, 6, 12, 0.05),
     "sparse_wide_more_features": _lasso_case(80, 200, 0.1, 10, 13, 0.1),
 }
+
+
+# Soft-margin SVM instances (abip_b200/svm.py): seeded Gaussian features, labels from a noisy linear rule
+
+
+def _svm_case(m, n, density, seed, C, noise):
+    def make():
+        rng = np.random.default_rng(seed)
+        if density < 1.0:
+            X = sp.random(m, n, density=density, random_state=seed, format="csc")
+            X.data = rng.standard_normal(X.nnz)
+        else:
+            X = sp.csc_matrix(rng.standard_normal((m, n)))
+        w0 = rng.standard_normal(n)
+        y = np.sign(X @ w0 + noise * rng.standard_normal(m))
+        y[y == 0] = 1.0
+        return X, y, float(C)
+    return make
+
+
+SVM_CASES = {
+    "dense_tall": _svm_case(120, 20, 1.0, 21, 1.0, 0.3),
+    "sparse_tall": _svm_case(200, 40, 0.3, 22, 0.5, 0.5),
+    "dense_wide": _svm_case(40, 60, 1.0, 23, 2.0, 0.2),
+}
