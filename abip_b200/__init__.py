@@ -6,7 +6,8 @@ host-side mirror of the reference's `abip(data, K, params)` entry (api.py).  No 
 from .api import abip, lp_solve, lp_solve_batch, get_params, LinSysPlugin, LpEngine, LpSolver  # noqa: F401
 from . import problems  # noqa: F401
 from .lasso import lasso_solve, lasso_cone_program  # noqa: F401
-from .svm import svm_solve, svm_cone_program  # noqa: F401
+from .svm import svm_solve, svm_cone_program, svm_qp_solve, svm_qp_program  # noqa: F401
 
 __all__ = ["abip", "lp_solve", "get_params", "LinSysPlugin", "LpEngine", "LpSolver", "lp_solve_batch", "problems",
-           "lasso_solve", "lasso_cone_program", "svm_solve", "svm_cone_program"]
+           "lasso_solve", "lasso_cone_program", "svm_solve", "svm_cone_program",
+           "svm_qp_solve", "svm_qp_program"]

@@ -73,3 +73,43 @@ def svm_solve(X, y, C: float, **settings):
     w, b0, xi = svm_split(x, m, n)
     info["objective"] = svm_objective(Xs, np.asarray(y, dtype=np.float64), C, w, b0)
     return w, b0, xi, info
+
+
+# ---------------------------------------------------------------------------------------------------------
+# QP form (prob_type = SVMQP, mex/abip_ml_mex.c:337-342; source/svm_qp_config.c:8-150):
+#     min 1/2 |w|^2 + 1/(m lambda) sum xi   s.t.   diag(y) X w + y b + xi - t = 1,  (w, b) free,  xi, t >= 0
+# variables x = [w (n), b | xi (m), t (m)], K = {f: n + 1, l: 2 m}, Q = diag(1_n, 0): the quadratic term goes to the
+# engine's Q instead of a rotated cone.
+# ---------------------------------------------------------------------------------------------------------
+def svm_qp_program(X, y, lam: float):
+    """(A, Q, b, c, K) of the QP form; the weight of the hinge losses is 1 / (m lambda) as in the reference."""
+    X = sp.csc_matrix(X, dtype=np.float64)
+    m, n = X.shape
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+    if y.size != m or not np.all(np.abs(y) == 1.0):
+        raise ValueError("y must hold one label in {-1, +1} per row of X")
+    if not lam > 0:
+        raise ValueError("lambda must be positive")
+    Im = sp.identity(m, format="csc")
+    A = sp.hstack([sp.diags(y) @ X, sp.csc_matrix(y.reshape(-1, 1)), Im, -Im], format="csc")
+    A.sort_indices()
+    q = 1 + n + 2 * m
+    Q = sp.diags(np.concatenate([np.ones(n), np.zeros(q - n)]), format="csc")
+    c = np.zeros(q)
+    c[n + 1:n + 1 + m] = 1.0 / (m * float(lam))
+    K = {"f": n + 1, "l": 2 * m}
+    return A, Q, np.ones(m), c, K
+
+
+def svm_qp_solve(X, y, lam: float, **settings):
+    """QP form on the GPU engine; returns (w, b, xi, info) with info["objective"] = 1/2 |w|^2 + sum(hinge) / (m lambda)."""
+    from . import qcp
+    A, Q, bb, c, K = svm_qp_program(X, y, lam)
+    Xs = sp.csc_matrix(X)
+    m, n = Xs.shape
+    opts = dict(verbose=0)
+    opts.update(settings)
+    x, yy, s, info = qcp.qcp_solve_raw(A, Q, bb, c, K, **opts)
+    w, b0, xi = x[:n], float(x[n]), x[n + 1:n + 1 + m]
+    info["objective"] = svm_objective(Xs, np.asarray(y, dtype=np.float64), 1.0 / (m * float(lam)), w, b0)
+    return w, b0, xi, info

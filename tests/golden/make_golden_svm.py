@@ -15,7 +15,8 @@ from abip_b200.problems import SVM_CASES as CASES  # noqa: E402
 from oracle import ref_qcp as R  # noqa: E402
 
 
-def ref_svm(X, y, Cpar, eps):
+def ref_svm(X, y, Cpar, eps, qp=False):
+    """qp: prob_type = SVMQP (enum value 3; K = {f: n + 1, l: 2 m}, lambda = 1 / (m C)) instead of SVM."""
     lib = R.load()
     m, n = X.shape
     A, keep = R._mat(X.copy())  # the reference scales A by the labels in place
@@ -23,15 +24,17 @@ def ref_svm(X, y, Cpar, eps):
     c = np.zeros(4 + 3 * n + 2 * m)
     st = R.ABIPSettings()
     d = R.ABIPData(m, n, C.pointer(A), None, b.ctypes.data_as(C.POINTER(C.c_double)),
-                   c.ctypes.data_as(C.POINTER(C.c_double)), float(Cpar), C.pointer(st))
+                   c.ctypes.data_as(C.POINTER(C.c_double)), 1.0 / (m * float(Cpar)) if qp else float(Cpar), C.pointer(st))
     lib.abip_set_default_settings(C.byref(d))
     st.linsys_solver = 1
-    st.prob_type = 1
+    st.prob_type = 3 if qp else 1
     st.verbose = 0
     st.time_limit = 600.0
     st.eps_p = st.eps_d = st.eps_g = eps
     rq = np.array([2 + n], dtype=np.int32)
     K = R.ABIPCone(None, 0, rq.ctypes.data_as(C.POINTER(C.c_int)), 1, 0, 0, 2 + 2 * m + 2 * n)
+    if qp:
+        K = R.ABIPCone(None, 0, None, 0, n + 1, 0, 2 * m)
     sol, info = R.ABIPSolution(), R.ABIPInfo()
     lib.abip(C.byref(d), C.byref(sol), C.byref(info), C.byref(K))
     w = np.ctypeslib.as_array(sol.x, shape=(n,)).copy()
@@ -48,4 +51,9 @@ if __name__ == "__main__":
         out[name] = {"status": info.status.decode(), "ipm_iter": int(info.ipm_iter), "admm_iter": int(info.admm_iter),
                      "pobj": info.pobj, "objective": 0.5 * float(w @ w) + Cpar * float(xi.sum()), "w": w.tolist(), "b": b0}
         print(name, out[name]["status"], out[name]["admm_iter"], out[name]["pobj"], out[name]["objective"])
+        w, b0, info = ref_svm(X, y, Cpar, 1e-5, qp=True)
+        xi = np.maximum(0.0, 1.0 - y * (X @ w + b0))
+        out[name + "_qp"] = {"status": info.status.decode(), "ipm_iter": int(info.ipm_iter), "admm_iter": int(info.admm_iter),
+                             "pobj": info.pobj, "objective": 0.5 * float(w @ w) + Cpar * float(xi.sum()), "w": w.tolist(), "b": b0}
+        print(name + "_qp", out[name + "_qp"]["status"], out[name + "_qp"]["admm_iter"], out[name + "_qp"]["pobj"], out[name + "_qp"]["objective"])
     json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "svm_golden.json"), "w"))

@@ -74,3 +74,42 @@ def test_svm_gpu_matches_reference(name):
     assert abs(info["admm_iter"] - r.admm_iter) <= max(2, 0.05 * r.admm_iter)
     assert np.max(np.abs(w - w_or)) <= 1e-4 * max(1.0, np.max(np.abs(w_or))) and abs(b0 - b_or) <= 1e-4
     assert np.all(xi >= -1e-9)
+
+
+def _oracle_qp(X, y, lam):
+    A, Q, b, c, K = svm.svm_qp_program(X, y, lam)
+    m, n = X.shape
+    r = O.solve(A, Q, b, c, K, O.Settings(eps_p=EPS, eps_d=EPS, eps_g=EPS))
+    return r, (r.x[:n], float(r.x[n]))
+
+
+@pytest.mark.parametrize("name", sorted(problems.SVM_CASES))
+def test_qp_form_reproduces_reference_svmqp(name):
+    """CPU: the QP form (svm_qp_config.c:8-150: (w, b) free, Q = diag(1_n, 0), hinge weight 1 / (m lambda)) on the oracle
+    against the reference's SVMQP mode."""
+    X, y, Cp = problems.SVM_CASES[name]()
+    m = X.shape[0]
+    g = GOLD[name + "_qp"]
+    r, (w, b0) = _oracle_qp(X, y, 1.0 / (m * Cp))
+    assert r.status == "Solved" == g["status"]
+    assert abs(svm.svm_objective(X, y, Cp, w, b0) - g["objective"]) <= 1e-3 * abs(g["objective"])
+    assert np.max(np.abs(w - np.array(g["w"]))) <= 1e-3 * max(1.0, np.max(np.abs(g["w"])))
+    assert abs(b0 - g["b"]) <= 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(problems.SVM_CASES))
+def test_svm_qp_gpu_matches_reference(name):
+    """GPU engine through svm_qp_solve (general QCP path with a diagonal Q and free variables) against the reference's SVMQP
+    mode and the oracle's iteration counts."""
+    X, y, Cp = problems.SVM_CASES[name]()
+    m = X.shape[0]
+    g = GOLD[name + "_qp"]
+    w, b0, xi, info = svm.svm_qp_solve(X, y, 1.0 / (m * Cp), eps_p=EPS, eps_d=EPS, eps_g=EPS)
+    r, (w_or, b_or) = _oracle_qp(X, y, 1.0 / (m * Cp))
+    assert info["status"] == "Solved" == g["status"]
+    assert abs(info["objective"] - g["objective"]) <= 1e-3 * abs(g["objective"])
+    assert np.max(np.abs(w - np.array(g["w"]))) <= 1e-3 * max(1.0, np.max(np.abs(g["w"])))
+    assert info["ipm_iter"] == r.ipm_iter
+    assert abs(info["admm_iter"] - r.admm_iter) <= max(2, 0.05 * r.admm_iter)
+    assert np.max(np.abs(w - w_or)) <= 1e-4 * max(1.0, np.max(np.abs(w_or))) and abs(b0 - b_or) <= 1e-4
