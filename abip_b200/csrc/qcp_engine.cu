@@ -278,7 +278,7 @@ __device__ __forceinline__ void dev_qcp_solve(const QcpCtx& c, Reducer& R, cg::g
     R.block_store<1>(a1);
     grid_sync(grid);
     R.finish<1>(a1);
-    const double tol = rtol * sqrt(a1[0]);
+    const double tol_rhs = rtol * sqrt(a1[0]);
     // H^-1 inside the operator of the outer CG: three digits below the outer target are enough (an operator error of
     // itol perturbs the attainable outer residual by ~ itol x iterations); the two solves that enter the solution
     // directly (hb above, x below) stay at 1e-13
@@ -318,6 +318,10 @@ __device__ __forceinline__ void dev_qcp_solve(const QcpCtx& c, Reducer& R, cg::g
     double ipzr = a2[1];
     int its = 0;
     const int max_its = 2 * m + 50;
+    // The target is relative to |rhs|; when the reduced right-hand side vanishes (it is exactly 0 in the first iteration of
+    // the SVM-QP program, abip_b200/svm.py) that target is 0 and CG would run on rounding noise until 0 / 0 turns the
+    // iterates into NaN: never ask for more than 13 digits below the residual of the warm start.
+    const double tol = fmax(tol_rhs, 1e-13 * rn);
     if (rn > tol) {
         for (int it = 0; it < max_its; ++it) {
             spmv_rows(c.AT, c.cg_p, R.ws, &c.A,
@@ -338,6 +342,7 @@ __device__ __forceinline__ void dev_qcp_solve(const QcpCtx& c, Reducer& R, cg::g
             R.block_store<1>(d1);
             grid_sync(grid);
             R.finish<1>(d1);
+            if (!(d1[0] > 0.0)) break;  // p = 0 (or not a number): nothing left to do in this direction
             const double al = ipzr / d1[0];
             double d2[2] = {0.0, 0.0};
             GRID_STRIDE(i, m) {

@@ -78,8 +78,9 @@ def svm_solve(X, y, C: float, **settings):
 # ---------------------------------------------------------------------------------------------------------
 # QP form (prob_type = SVMQP, mex/abip_ml_mex.c:337-342; source/svm_qp_config.c:8-150):
 #     min 1/2 |w|^2 + 1/(m lambda) sum xi   s.t.   diag(y) X w + y b + xi - t = 1,  (w, b) free,  xi, t >= 0
-# variables x = [w (n), b | xi (m), t (m)], K = {f: n + 1, l: 2 m}, Q = diag(1_n, 0): the quadratic term goes to the
-# engine's Q instead of a rotated cone.
+# variables x = [w (n), b | xi (m), t (m)], K = {f: n + 1, l: 2 m}, Q = diag(1_n, 0): the quadratic term goes to Q instead of
+# a rotated cone.  (In the first ADMM iteration of this program the reduced right-hand side of the Schur system is exactly
+# zero: the PCG tolerance of the engine is floored by 1e-13 x the warm-start residual for that case, qcp_engine.cu.)
 # ---------------------------------------------------------------------------------------------------------
 def svm_qp_program(X, y, lam: float):
     """(A, Q, b, c, K) of the QP form; the weight of the hinge losses is 1 / (m lambda) as in the reference."""
@@ -107,7 +108,7 @@ def svm_qp_solve(X, y, lam: float, **settings):
     A, Q, bb, c, K = svm_qp_program(X, y, lam)
     Xs = sp.csc_matrix(X)
     m, n = Xs.shape
-    opts = dict(verbose=0)
+    opts = dict(verbose=0, max_admm_iters=200000)
     opts.update(settings)
     x, yy, s, info = qcp.qcp_solve_raw(A, Q, bb, c, K, **opts)
     w, b0, xi = x[:n], float(x[n]), x[n + 1:n + 1 + m]

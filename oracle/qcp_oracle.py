@@ -329,7 +329,8 @@ class Work:
         op = lambda y: st.rho_y * y + self.Acsr @ self.hinv(self.A.T @ y)
         y = np.zeros(m) if warm is None else warm[:m].copy()
         r = rhs - op(y) if warm is not None else rhs.copy()
-        tol = self.pcg_rtol * math.sqrt(float(rhs @ rhs))
+        # relative to |rhs|, but never more than 13 digits below the residual of the warm start (rhs = 0 otherwise asks for 0)
+        tol = max(self.pcg_rtol * math.sqrt(float(rhs @ rhs)), 1e-13 * math.sqrt(float(r @ r)))
         its = 0
         if math.sqrt(float(r @ r)) > tol:
             z = r * self.Ms
@@ -337,6 +338,8 @@ class Work:
             rz = float(r @ z)
             for i in range(m * 2 + 50):
                 Gp = op(p)
+                if not float(p @ Gp) > 0.0:
+                    break
                 al = rz / float(p @ Gp)
                 y += al * p
                 r -= al * Gp

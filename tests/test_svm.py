@@ -97,7 +97,22 @@ def test_qp_form_reproduces_reference_svmqp(name):
     assert abs(b0 - g["b"]) <= 1e-3
 
 
+def test_schur_path_handles_a_vanishing_reduced_rhs():
+    """The engine's linear-system path (m-space Schur PCG, restated in the oracle) on the QP form: in the first ADMM iteration
+    the reduced right-hand side b_y - A H^-1 b_x is exactly zero with a non-zero warm start; a tolerance relative to |rhs|
+    alone is then 0 and CG runs into 0 / 0 (the GPU engine went on with NaN iterates until its iteration limit).  With the
+    floor of 1e-13 x the warm-start residual the Schur path reproduces the direct path."""
+    X, y, Cp = problems.SVM_CASES["dense_tall"]()
+    m = X.shape[0]
+    A, Q, b, c, K = svm.svm_qp_program(X, y, 1.0 / (m * Cp))
+    d = O.solve(A, Q, b, c, K, O.Settings(eps_p=EPS, eps_d=EPS, eps_g=EPS))
+    s = O.solve(A, Q, b, c, K, O.Settings(eps_p=EPS, eps_d=EPS, eps_g=EPS), linsys="schur", pcg_rtol=1e-8)
+    assert (s.status, s.ipm_iter, s.admm_iter) == (d.status, d.ipm_iter, d.admm_iter)
+    assert abs(s.pobj - d.pobj) <= 1e-6 * abs(d.pobj)
+
+
 @pytest.mark.gpu
+@pytest.mark.timeout(120)
 @pytest.mark.parametrize("name", sorted(problems.SVM_CASES))
 def test_svm_qp_gpu_matches_reference(name):
     """GPU engine through svm_qp_solve (general QCP path with a diagonal Q and free variables) against the reference's SVMQP
@@ -105,7 +120,7 @@ def test_svm_qp_gpu_matches_reference(name):
     X, y, Cp = problems.SVM_CASES[name]()
     m = X.shape[0]
     g = GOLD[name + "_qp"]
-    w, b0, xi, info = svm.svm_qp_solve(X, y, 1.0 / (m * Cp), eps_p=EPS, eps_d=EPS, eps_g=EPS)
+    w, b0, xi, info = svm.svm_qp_solve(X, y, 1.0 / (m * Cp), eps_p=EPS, eps_d=EPS, eps_g=EPS, max_admm_iters=20000)
     r, (w_or, b_or) = _oracle_qp(X, y, 1.0 / (m * Cp))
     assert info["status"] == "Solved" == g["status"]
     assert abs(info["objective"] - g["objective"]) <= 1e-3 * abs(g["objective"])
