@@ -471,7 +471,8 @@ def run_ours(args):
         out = {"workload": f"cfg5: {per_gpu} independent LPs m=500 n=2000 per GPU ({per_gpu * world} in total), eps={args.eps:g}",
                "value": per_gpu * world / dt, "unit": "LP/s", "scaling": "weak", "wall_s": dt, "solved": int(solved),
                "engine_wall_s": allmax(res[0][3]["batch_wall_s"]),  # inside abip_gpu_batch_main (without the Python marshalling)
-               "total": per_gpu * world, "timing": "host clock around abip_gpu_batch_main (set-up, H2D, solves, D2H), max over ranks"}
+               "total": per_gpu * world, "timing": "host clock around lp_solve_batch = abip_gpu_batch_main + marshalling (set-up, H2D, solves, D2H) of ONE batch, max over ranks; warm-up: one wave of 192 problems",
+               "in_flight": min(per_gpu, 192)}
         try:  # parity of a slice against the reference's own results (fixture: first 64 problems)
             gold = json.load(open(os.path.join(ROOT, "tests", "golden", "cfg5_golden.json")))
             if rank == 0:
