@@ -185,8 +185,11 @@ void abip_gpu_partition(const ABIPGpuWork *w, abip_int *c0, abip_int *nl);
 void abip_gpu_column_partition(abip_int n, const abip_int *Ap, abip_int world, abip_int rank, abip_int *c0, abip_int *nl);
 
 /* Batch of independent LPs on one GPU (configs[4]); `concurrency` = problems in flight (one host thread each).
- *   ctas_per_problem <= 1: lock-step mode -- one CTA per problem, the steps of all problems in flight are launched
- *     together (one k_batch launch per step for the whole batch; use ~2 x SM count problems in flight);
+ *   ctas_per_problem <= 1: one CTA per problem; the whole solve (outer loop of ABIP(solve), src/abip.c:2093-2295: inner ADMM
+ *     loops, convergence checks, mu rules, re-initialisation, Barzilai-Borwein searches) runs inside one launch of the batch
+ *     kernel, the requests of the problems in flight are launched in groups on several streams and every owner is woken
+ *     when its CTA has finished (~1.3 x SM count problems in flight is enough).  With verbose != 0, a trace file or past
+ *     restart_thresh the host drives the outer loop; time limit and SIGINT are checked between launches;
  *   ctas_per_problem >= 2: each problem on its own stream with a persistent grid of that many CTAs.
  * Returns the number of failed problems (< 0: bad arguments).
  * The reference equivalent is a loop of ABIP(main) calls (one process per core). */
